@@ -1,0 +1,178 @@
+// Shared device helpers for the CrossCat kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/cgpm_b200.h"
+
+#define CC_LOGPI   1.1447298858494001741434273513531
+#define CC_LOG2    0.69314718055994530941723212145818
+#define CC_LOG2PI  1.8378770664093454835606594728112
+
+void cc_set_error(const char* fmt, ...);
+int cc_check_cuda(cudaError_t e, const char* what);
+#define CC_CUDA(x) do { if (cc_check_cuda((x), #x)) return CC_ERR_CUDA; } while (0)
+
+// ---------------------------------------------------------------------------
+// index helpers
+__device__ __forceinline__ size_t sv_index(const cc_state& st, int s, int v) {
+    return (size_t)s * st.Vcap + v;
+}
+__device__ __forceinline__ double* stat_field(const cc_state& st, int s, int f) {
+    return st.stat + ((size_t)s * CC_NFIELD + f) * (size_t)st.Kcap * st.C;
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based generator for the device
+// stream.  u01 maps two 32-bit words to a double exactly like numpy's legacy
+// random_sample: (a>>5, b>>6) -> (a*2^26+b)/2^53, so the device stream has the
+// same support as the injected host stream.
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t ctr_lo, uint64_t ctr_hi) const {
+        uint32_t c0 = (uint32_t)ctr_lo, c1 = (uint32_t)(ctr_lo >> 32);
+        uint32_t c2 = (uint32_t)ctr_hi, c3 = (uint32_t)(ctr_hi >> 32);
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            uint32_t n0 = hi1 ^ c1 ^ a, n1 = lo1, n2 = hi0 ^ c3 ^ b, n3 = lo0;
+            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+__device__ __forceinline__ double u01_from_words(uint32_t a, uint32_t b) {
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+// stream ids (high counter word): purpose | chain | view/column
+__device__ __forceinline__ uint64_t stream_id(uint32_t purpose, uint32_t chain, uint32_t sub) {
+    return ((uint64_t)purpose << 56) | ((uint64_t)(chain & 0xFFFFFFu) << 32) | sub;
+}
+
+// ---------------------------------------------------------------------------
+// Normal with Normal-Gamma prior (src/primitives/normal.py).  The posterior
+// update keeps the reference's operand order and never contracts a*b+c into an
+// FMA, so (mn, sn) are the same doubles the reference computes from the same
+// sufficient statistics (normal.py:183-191).
+__device__ __forceinline__ void normal_posterior(double N, double sx, double sxx, double m, double r,
+                                                 double s, double nu, double& mn, double& rn,
+                                                 double& sn, double& nun) {
+    rn = __dadd_rn(r, N);
+    nun = __dadd_rn(nu, N);
+    mn = __ddiv_rn(__dadd_rn(__dmul_rn(r, m), sx), rn);
+    double t = __dadd_rn(__dadd_rn(s, sxx), __dmul_rn(__dmul_rn(r, m), m));
+    sn = __dsub_rn(t, __dmul_rn(__dmul_rn(rn, mn), mn));
+    if (sn == 0.0) sn = s;                                   // normal.py:189-190
+}
+// normal.py:193-200
+__device__ __forceinline__ double normal_log_Z(double r, double s, double nu) {
+    return ((nu + 1.0) * 0.5) * CC_LOG2 + 0.5 * CC_LOGPI - 0.5 * log(r) - (nu * 0.5) * log(s) + lgamma(nu * 0.5);
+}
+// normal.py:175-181
+__device__ __forceinline__ double normal_marginal(double N, double sx, double sxx, double m, double r,
+                                                  double s, double nu) {
+    double mn, rn, sn, nun;
+    normal_posterior(N, sx, sxx, m, r, s, nu, mn, rn, sn, nun);
+    return -(N * 0.5) * CC_LOG2PI + normal_log_Z(rn, sn, nun) - normal_log_Z(r, s, nu);
+}
+// G(N): the N-only part of the predictive Z(N+1)-Z(N)-log(2pi)/2 (normal.py:165-173):
+//   predictive(x) = G(N) - log(sn)/2 - ((nun+1)/2) log1p(rn (x-mn)^2 / ((rn+1) sn))
+__device__ __forceinline__ double normal_G(double N, double r, double nu) {
+    double h = 0.5 * (nu + N);
+    double rn = r + N;
+    return lgamma(h + 0.5) - lgamma(h) + 0.5 * log(rn / (rn + 1.0)) - 0.5 * CC_LOGPI;
+}
+struct NormalCache { double mn, a, cst; };
+__device__ __forceinline__ NormalCache normal_cache(double N, double sx, double sxx, double gN, double m,
+                                                    double r, double s, double nu) {
+    double mn, rn, sn, nun;
+    normal_posterior(N, sx, sxx, m, r, s, nu, mn, rn, sn, nun);
+    NormalCache c;
+    c.mn = mn;
+    c.a = rn / ((rn + 1.0) * sn);
+    c.cst = gN - 0.5 * log(sn);
+    return c;
+}
+__device__ __forceinline__ double normal_predictive_cached(double x, double mn, double a, double cst,
+                                                           double N, double nu) {
+    double z = x - mn;
+    return cst - 0.5 * (nu + N + 1.0) * log1p(a * z * z);
+}
+
+// Categorical with symmetric Dirichlet prior (src/primitives/categorical.py:144-155)
+__device__ __forceinline__ double categorical_marginal(double N, const double* counts, int k, double alpha) {
+    double A = k * alpha;
+    double lg = 0.0;
+    for (int j = 0; j < k; ++j) lg += lgamma(counts[j] + alpha);
+    return lgamma(A) - lgamma(A + N) + lg - k * lgamma(alpha);
+}
+
+// ---------------------------------------------------------------------------
+// warp helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier / async-copy PTX (sm_90+; SASS: SYNCS.*, UBLKCP, LDGSTS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared, completion on an mbarrier (TMA engine)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when all prior cp.async of this thread landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}

@@ -1,0 +1,351 @@
+// Sufficient-statistic rebuild, column marginal matrix and logpdf_score.
+//
+//   group_kernel   stable grouping of a view's member order by cluster
+//   stats_kernel   per (cluster, column): ordered sums -> tables (TABLE mode) or
+//                  -> per-(column, view) marginal likelihood (MARGINAL mode)
+//   score_kernel   State.logpdf_score
+//
+// References: View._bulk_incorporate (src/mixtures/view.py:483-494) sums each
+// cluster's members in the order of the view's CRP `data` OrderedDict; this is
+// reproduced exactly: a cluster's members are visited in `order`, one thread
+// owns one (cluster, column) accumulator, and x*x is rounded before it is added
+// (src/primitives/normal.py:64-70).  Dim.logpdf_score (src/mixtures/dim.py:121-122)
+// and the marginals of normal.py:175-181 / categorical.py:150-155 give the
+// column marginal matrix of State._gibbs_transition_dim (src/crosscat/state.py:1065-1072).
+#include "cc_common.cuh"
+
+#define CC_MAXCAT 256
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// One warp per (chain, view): rows grouped by cluster slot, members of a
+// cluster in `order` order.  grouped = st.moved (scratch), gstart = st.seq[0..Kcap)
+// of the same (chain, view) is NOT used (seq may be shorter than Kcap); the
+// start offsets go to `gstart` [n_work][Kcap+1].
+__global__ void group_kernel(const cc_state st, int n_work, const int32_t* __restrict__ chains,
+                             const int32_t* __restrict__ views, int32_t* __restrict__ gstart) {
+    const int w = blockIdx.x;
+    if (w >= n_work) return;
+    const int s = chains[w], v = views[w];
+    const int lane = threadIdx.x;
+    const size_t sv = sv_index(st, s, v);
+    const int R = st.R, Kcap = st.Kcap;
+    const int32_t* order = st.order + sv * R;
+    const int32_t* zr = st.zr + sv * R;
+    const int32_t* nk = st.nk + sv * Kcap;
+    int32_t* grouped = st.moved + sv * R;
+    int32_t* start = gstart + (size_t)w * (Kcap + 1);
+    extern __shared__ int s_cursor[];                  // [Kcap]
+    // exclusive scan of nk over slots (serial chunks of 32)
+    int carry = 0;
+    for (int base = 0; base < Kcap; base += 32) {
+        const int k = base + lane;
+        const int c = (k < Kcap) ? nk[k] : 0;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (k < Kcap) { start[k] = carry + inc - c; s_cursor[k] = carry + inc - c; }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) start[Kcap] = carry;
+    __syncwarp();
+    // stable scatter
+    for (int base = 0; base < R; base += 32) {
+        const int i = base + lane;
+        const bool act = i < R;
+        int r = 0, k = -1;
+        if (act) { r = order[i]; k = zr[r]; }
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        int pos = 0;
+        if (act) pos = s_cursor[k] + rank;
+        __syncwarp();
+        if (act && rank == __popc(peers) - 1) s_cursor[k] = pos + 1;   // last peer advances the cursor
+        if (act) grouped[pos] = r;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct StatsParams {
+    cc_state st;
+    int n_work;
+    const int32_t* chains;
+    const int32_t* views;
+    const int32_t* gstart;   // [n_work][Kcap+1]
+    int marginal;            // 0: TABLE mode (the view's own columns), 1: MARGINAL mode (columns `cols`)
+    const int32_t* cols;     // MARGINAL: [n_cols] column list (NULL = all)
+    int n_cols;
+    double* scratch;         // MARGINAL: [n_work][Kcap] x [n_cols] per-cluster marginals
+};
+
+// grid: (n_work, column tiles of 32).  block: NW warps; warp w owns clusters
+// pos = w, w+NW, ...; lane owns one column of the tile.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
+    const cc_state& st = p.st;
+    const int w = blockIdx.x;
+    const int s = p.chains[w], v = p.views[w];
+    const size_t sv = sv_index(st, s, v);
+    const int R = st.R, C = st.C, Cp = st.Cp, Kcap = st.Kcap, CT = st.CT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t* zv = st.zv + (size_t)s * C;
+
+    // column of this lane
+    __shared__ int s_cols[32];
+    __shared__ int s_ncols;
+    if (threadIdx.x == 0) {
+        int cnt = 0;
+        const int first = blockIdx.y * 32;
+        if (p.marginal) {
+            const int total = p.cols ? p.n_cols : C;
+            for (int j = first; j < total && cnt < 32; ++j) s_cols[cnt++] = p.cols ? p.cols[j] : j;
+        } else {
+            int seen = 0;
+            for (int c = 0; c < C && cnt < 32; ++c)
+                if (zv[c] == v) { if (seen >= first) s_cols[cnt++] = c; ++seen; }
+        }
+        s_ncols = cnt;
+    }
+    __syncthreads();
+    const int ncols = s_ncols;
+    if (ncols == 0) return;
+    const bool act = lane < ncols;
+    const int c = act ? s_cols[lane] : 0;
+    const int K = st.nclu[sv];
+    const int32_t* live = st.live + sv * Kcap;
+    const int32_t* grouped = st.moved + sv * R;
+    const int32_t* start = p.gstart + (size_t)w * (Kcap + 1);
+    const double* hyp = st.hyp + ((size_t)s * C + c) * 4;
+    const int ctype = st.ctype[c];
+    const int kc = st.ncat[c];
+    const double h0 = hyp[0], h1 = hyp[1], h2 = hyp[2], h3 = hyp[3];
+    const double* X = st.Xrm + c;
+
+    double lacc = 0.0;     // MARGINAL: this warp's partial over its clusters
+    for (int pos = warp; pos < K + (p.marginal ? 0 : 1); pos += NW) {
+        // pos == K (TABLE mode): the prior (empty-cluster) record at slot Kcap-1
+        const bool prior = pos >= K;
+        const int k = prior ? (Kcap - 1) : live[pos];
+        const int beg = prior ? 0 : start[k], end = prior ? 0 : start[k + 1];
+        double N = 0.0, sx = 0.0, sxx = 0.0;
+        uint32_t lc[CC_MAXCAT];
+        if (act && ctype == CC_CATEGORICAL) for (int q = 0; q < kc; ++q) lc[q] = 0;
+        int i = beg;
+        // ordered accumulation; loads are batched 4 deep, adds stay sequential
+        for (; i + 4 <= end; i += 4) {
+            const int r0 = grouped[i], r1 = grouped[i + 1], r2 = grouped[i + 2], r3 = grouped[i + 3];
+            if (act) {
+                const double x0 = X[(size_t)r0 * Cp], x1 = X[(size_t)r1 * Cp], x2 = X[(size_t)r2 * Cp], x3 = X[(size_t)r3 * Cp];
+                if (ctype == CC_NORMAL) {
+                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                    if (!isnan(x1)) { N += 1.0; sx = __dadd_rn(sx, x1); sxx = __dadd_rn(sxx, __dmul_rn(x1, x1)); }
+                    if (!isnan(x2)) { N += 1.0; sx = __dadd_rn(sx, x2); sxx = __dadd_rn(sxx, __dmul_rn(x2, x2)); }
+                    if (!isnan(x3)) { N += 1.0; sx = __dadd_rn(sx, x3); sxx = __dadd_rn(sxx, __dmul_rn(x3, x3)); }
+                } else {
+                    if (!isnan(x0)) { N += 1.0; lc[(int)x0]++; }
+                    if (!isnan(x1)) { N += 1.0; lc[(int)x1]++; }
+                    if (!isnan(x2)) { N += 1.0; lc[(int)x2]++; }
+                    if (!isnan(x3)) { N += 1.0; lc[(int)x3]++; }
+                }
+            }
+        }
+        for (; i < end; ++i) {
+            const int r0 = grouped[i];
+            if (act) {
+                const double x0 = X[(size_t)r0 * Cp];
+                if (!isnan(x0)) {
+                    N += 1.0;
+                    if (ctype == CC_NORMAL) { sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                    else lc[(int)x0]++;
+                }
+            }
+        }
+        if (!act) continue;
+        if (p.marginal) {
+            double mg;
+            if (ctype == CC_NORMAL) mg = normal_marginal(N, sx, sxx, h0, h1, h2, h3);
+            else {
+                const double A = kc * h0;
+                double lg = 0.0;
+                for (int q = 0; q < kc; ++q) lg += lgamma((double)lc[q] + h0);
+                mg = lgamma(A) - lgamma(A + N) + lg - kc * lgamma(h0);
+            }
+            lacc += mg;
+        } else {
+            const size_t e = (size_t)k * C + c;
+            stat_field(st, s, CC_F_N)[e] = N;
+            if (ctype == CC_NORMAL) {
+                const double gN = normal_G(N, h1, h3);
+                const double gM1 = (N >= 1.0) ? normal_G(N - 1.0, h1, h3) : 0.0;
+                const NormalCache cc = normal_cache(N, sx, sxx, gN, h0, h1, h2, h3);
+                stat_field(st, s, CC_F_SX)[e] = sx;
+                stat_field(st, s, CC_F_SXX)[e] = sxx;
+                stat_field(st, s, CC_F_MN)[e] = cc.mn;
+                stat_field(st, s, CC_F_A)[e] = cc.a;
+                stat_field(st, s, CC_F_CST)[e] = cc.cst;
+                stat_field(st, s, CC_F_GN)[e] = gN;
+                stat_field(st, s, CC_F_GM1)[e] = gM1;
+            } else {
+                stat_field(st, s, CC_F_SX)[e] = 0.0;
+                stat_field(st, s, CC_F_SXX)[e] = 0.0;
+                stat_field(st, s, CC_F_MN)[e] = 0.0;
+                stat_field(st, s, CC_F_A)[e] = 0.0;
+                stat_field(st, s, CC_F_CST)[e] = log(N + h0 * kc);
+                stat_field(st, s, CC_F_GN)[e] = 0.0;
+                stat_field(st, s, CC_F_GM1)[e] = 0.0;
+                double* cn = st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[c];
+                for (int q = 0; q < kc; ++q) cn[q] = (double)lc[q];
+            }
+        }
+    }
+    if (p.marginal) {
+        // deterministic cross-warp sum (warp order), one value per column
+        __shared__ double s_part[NW][32];
+        s_part[warp][lane] = lacc;
+        __syncthreads();
+        if (warp == 0 && act) {
+            double tot = 0.0;
+            for (int q = 0; q < NW; ++q) tot += s_part[q][lane];
+            st.colL[((size_t)s * C + c) * (st.Vcap + 1) + v] = tot;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// State.logpdf_score (src/crosscat/state.py:384-387): one CTA per chain.
+__device__ double crp_marginal_dev(int N, const int32_t* nk, const int32_t* live, int K, double alpha,
+                                   int tid, int nt, double* s_red) {
+    // crp.py:184-188: K log(alpha) + sum gammaln(n_k) + gammaln(alpha) - gammaln(N + alpha)
+    double acc = 0.0;
+    for (int i = tid; i < K; i += nt) acc += lgamma((double)nk[live ? live[i] : i]);
+    s_red[tid] = acc;
+    __syncthreads();
+    for (int o = nt >> 1; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+    const double tot = s_red[0];
+    __syncthreads();
+    return K * log(alpha) + tot + lgamma(alpha) - lgamma(N + alpha);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) score_kernel(const cc_state st, double* __restrict__ out) {
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int R = st.R, C = st.C, Kcap = st.Kcap, Vcap = st.Vcap, CT = st.CT;
+    __shared__ double s_red[NT];
+    __shared__ int s_vlist[1];
+    (void)s_vlist;
+    double total = 0.0;
+    // column CRP: counts nv over live view slots
+    {
+        double acc = 0.0;
+        int Kv = 0;
+        for (int v = 0; v < Vcap; ++v) if (st.nv[(size_t)s * Vcap + v] > 0) ++Kv;
+        for (int v = tid; v < Vcap; v += NT) { const int nvv = st.nv[(size_t)s * Vcap + v]; if (nvv > 0) acc += lgamma((double)nvv); }
+        s_red[tid] = acc;
+        __syncthreads();
+        for (int o = NT >> 1; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+        const double a = st.col_alpha[s];
+        total += Kv * log(a) + s_red[0] + lgamma(a) - lgamma(C + a);
+        __syncthreads();
+    }
+    for (int v = 0; v < Vcap; ++v) {
+        if (st.nv[(size_t)s * Vcap + v] <= 0) continue;
+        const size_t sv = sv_index(st, s, v);
+        const int K = st.nclu[sv];
+        const int32_t* live = st.live + sv * Kcap;
+        total += crp_marginal_dev(R, st.nk + sv * Kcap, live, K, st.view_alpha[sv], tid, NT, s_red);
+        // sum over (cluster, column in view) marginals
+        double acc = 0.0;
+        for (int e = tid; e < K * C; e += NT) {
+            const int pos = e / C, c = e - pos * C;
+            if (st.zv[(size_t)s * C + c] != v) continue;
+            const int k = live[pos];
+            const double* hyp = st.hyp + ((size_t)s * C + c) * 4;
+            const size_t idx = (size_t)k * C + c;
+            const double N = stat_field(st, s, CC_F_N)[idx];
+            if (st.ctype[c] == CC_NORMAL)
+                acc += normal_marginal(N, stat_field(st, s, CC_F_SX)[idx], stat_field(st, s, CC_F_SXX)[idx],
+                                       hyp[0], hyp[1], hyp[2], hyp[3]);
+            else
+                acc += categorical_marginal(N, st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[c], st.ncat[c], hyp[0]);
+        }
+        s_red[tid] = acc;
+        __syncthreads();
+        for (int o = NT >> 1; o > 0; o >>= 1) { if (tid < o) s_red[tid] += s_red[tid + o]; __syncthreads(); }
+        total += s_red[0];
+        __syncthreads();
+    }
+    if (tid == 0) out[s] = total;
+}
+
+__global__ void list_views_kernel(const cc_state st, int32_t* chains, int32_t* views, int32_t* count) {
+    // enumerate live (chain, view) pairs (single thread; S*Vcap is small)
+    if (blockIdx.x || threadIdx.x) return;
+    int n = 0;
+    for (int s = 0; s < st.S; ++s)
+        for (int v = 0; v < st.Vcap; ++v)
+            if (st.nv[(size_t)s * st.Vcap + v] > 0) { chains[n] = s; views[n] = v; ++n; }
+    *count = n;
+}
+
+}  // namespace
+
+// Host-side launcher shared by cc_rebuild and the column kernel.
+int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, const int32_t* d_views,
+                    int marginal, const int32_t* d_cols, int n_cols, cudaStream_t stream) {
+    if (n_work == 0) return CC_OK;
+    int32_t* gstart = nullptr;
+    CC_CUDA(cudaMallocAsync(&gstart, sizeof(int32_t) * (size_t)n_work * (st->Kcap + 1), stream));
+    group_kernel<<<n_work, 32, sizeof(int) * st->Kcap, stream>>>(*st, n_work, d_chains, d_views, gstart);
+    CC_CUDA(cudaGetLastError());
+    StatsParams p;
+    p.st = *st; p.n_work = n_work; p.chains = d_chains; p.views = d_views; p.gstart = gstart;
+    p.marginal = marginal; p.cols = d_cols; p.n_cols = n_cols; p.scratch = nullptr;
+    const int maxcols = marginal ? (d_cols ? n_cols : st->C) : st->C;
+    dim3 grid(n_work, (maxcols + 31) / 32);
+    stats_kernel<8><<<grid, 8 * 32, 0, stream>>>(p);
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaFreeAsync(gstart, stream));
+    return CC_OK;
+}
+
+extern "C" int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains, const int32_t* views,
+                          void* stream_) {
+    if (!st) { cc_set_error("cc_rebuild: null state"); return CC_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t *dch = nullptr, *dvw = nullptr, *dcount = nullptr;
+    int rc = CC_OK;
+    if (views == nullptr) {
+        const size_t cap = (size_t)st->S * st->Vcap;
+        CC_CUDA(cudaMallocAsync(&dch, sizeof(int32_t) * cap, stream));
+        CC_CUDA(cudaMallocAsync(&dvw, sizeof(int32_t) * cap, stream));
+        CC_CUDA(cudaMallocAsync(&dcount, sizeof(int32_t), stream));
+        list_views_kernel<<<1, 1, 0, stream>>>(*st, dch, dvw, dcount);
+        CC_CUDA(cudaGetLastError());
+        CC_CUDA(cudaMemcpyAsync(&n_work, dcount, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        CC_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        if (n_work < 0 || !chains) { cc_set_error("cc_rebuild: bad work list"); return CC_ERR_ARG; }
+        if (n_work == 0) return CC_OK;
+        CC_CUDA(cudaMallocAsync(&dch, sizeof(int32_t) * n_work, stream));
+        CC_CUDA(cudaMallocAsync(&dvw, sizeof(int32_t) * n_work, stream));
+        CC_CUDA(cudaMemcpyAsync(dch, chains, sizeof(int32_t) * n_work, cudaMemcpyHostToDevice, stream));
+        CC_CUDA(cudaMemcpyAsync(dvw, views, sizeof(int32_t) * n_work, cudaMemcpyHostToDevice, stream));
+    }
+    rc = cc_launch_stats(st, n_work, dch, dvw, 0, nullptr, 0, stream);
+    if (dch) cudaFreeAsync(dch, stream);
+    if (dvw) cudaFreeAsync(dvw, stream);
+    if (dcount) cudaFreeAsync(dcount, stream);
+    return rc;
+}
+
+extern "C" int cc_logpdf_score(const cc_state* st, double* out, void* stream_) {
+    if (!st || !out) { cc_set_error("cc_logpdf_score: null argument"); return CC_ERR_ARG; }
+    score_kernel<256><<<st->S, 256, 0, (cudaStream_t)stream_>>>(*st, out);
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}

@@ -1,0 +1,251 @@
+"""Device-resident chain state: torch tensors behind the `cc_state` C struct.
+
+PyTorch is used for device memory and streams only; every computation on the
+tensors is done by the CUDA kernels of libcgpm_b200.so through the C ABI
+(include/cgpm_b200.h).  Layouts are documented there.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+MAXCAT = 256
+
+
+def log_linspace(a, b, n):
+    """src/utils/general.py:203-205."""
+    return np.exp(np.linspace(math.log(a), math.log(b), n))
+
+
+def hyper_grids(xcol, ctype, n_grid=L.NGRID):
+    """Empirical-Bayes hyper grids of one column from its non-NaN values.
+    normal: src/primitives/normal.py:128-139; categorical:
+    src/primitives/categorical.py:110-114.  Returns float64 [4][n_grid]."""
+    X = xcol[~np.isnan(xcol)]
+    g = np.zeros((4, n_grid))
+    if ctype == L.NORMAL:
+        N = len(X) + 1.
+        ssqdev = np.var(X) * len(X) + 1.
+        g[0] = np.linspace(min(X), max(X) + 5, n_grid)
+        g[1] = log_linspace(1. / N, N, n_grid)
+        g[2] = log_linspace(ssqdev / 100., ssqdev, n_grid)
+        g[3] = log_linspace(1., N, n_grid)
+    else:
+        g[0] = log_linspace(1., float(len(X)), n_grid)
+    return g
+
+
+def crp_grid(n, n_grid=L.NGRID):
+    """src/primitives/crp.py:148-152 with n members."""
+    return log_linspace(1. / n, n, n_grid)
+
+
+class DeviceChains(object):
+    """S CrossCat chains over one shared table, resident on one GPU."""
+
+    def __init__(self, X, ctype, ncat, S, Vcap=None, Kcap=None, device=None):
+        L.load()          # fail loudly when the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise L.CgpmB200Error('cgpm_b200 needs a CUDA device (no CPU fallback).')
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        R, Cn = X.shape
+        ctype = np.asarray(ctype, dtype=np.int32)
+        ncat = np.asarray(ncat, dtype=np.int32)
+        if np.any(ncat > MAXCAT):
+            raise ValueError('categorical(k) supports k <= %d' % MAXCAT)
+        for c in range(Cn):
+            if ctype[c] == L.CATEGORICAL:
+                col = X[:, c]
+                ok = np.isnan(col) | ((col % 1 == 0) & (col >= 0) & (col < ncat[c]))
+                if not np.all(ok):      # categorical.py:56-57
+                    bad = col[~ok][0]
+                    raise ValueError('Invalid Categorical(%d): %s' % (ncat[c], bad))
+        self.device = torch.device('cuda', torch.cuda.current_device()) \
+            if device is None else torch.device(device)
+        self.R, self.C, self.S = R, Cn, int(S)
+        self.Cp = (Cn + 1) & ~1
+        self.Vcap = int(Vcap) if Vcap else int(min(Cn, 16))
+        self.Kcap = int(Kcap) if Kcap else int(min(max(R + 1, 4), 1024))
+        if not 4 <= self.Kcap <= 4096:
+            raise ValueError('Kcap must be in [4, 4096]')
+        self.ctype_h, self.ncat_h = ctype, ncat
+        catoff = np.zeros(Cn, dtype=np.int32)
+        catoff[1:] = np.cumsum(ncat)[:-1]
+        self.catoff_h = catoff
+        self.CT = int(max(int(ncat.sum()), 1))
+        self.X_h = X
+        self.grids_h = np.stack([hyper_grids(X[:, c], ctype[c]) for c in range(Cn)])
+        self.row_alpha_grid_h = crp_grid(R)
+        self.col_alpha_grid_h = crp_grid(Cn)
+        dev = self.device
+        f64, i32 = torch.float64, torch.int32
+        Xp = np.full((R, self.Cp), np.nan)
+        Xp[:, :Cn] = X
+        t = {}
+        t['Xrm'] = torch.from_numpy(Xp).to(dev)
+        t['Xcm'] = torch.from_numpy(np.ascontiguousarray(X.T)).to(dev)
+        t['ctype'] = torch.from_numpy(ctype).to(dev)
+        t['ncat'] = torch.from_numpy(ncat).to(dev)
+        t['catoff'] = torch.from_numpy(catoff).to(dev)
+        t['grids'] = torch.from_numpy(self.grids_h).to(dev)
+        t['row_alpha_grid'] = torch.from_numpy(self.row_alpha_grid_h).to(dev)
+        t['col_alpha_grid'] = torch.from_numpy(self.col_alpha_grid_h).to(dev)
+        S_, V, K = self.S, self.Vcap, self.Kcap
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+        t['hyp'] = z((S_, Cn, 4), f64)
+        t['zv'] = z((S_, Cn), i32)
+        t['nv'] = z((S_, V), i32)
+        t['view_id'] = torch.full((S_, V), -1, dtype=i32, device=dev)
+        t['col_alpha'] = torch.ones((S_,), dtype=f64, device=dev)
+        t['view_alpha'] = torch.ones((S_, V), dtype=f64, device=dev)
+        t['nclu'] = z((S_, V), i32)
+        t['live'] = torch.full((S_, V, K), -1, dtype=i32, device=dev)
+        t['cid'] = z((S_, V, K), i32)
+        t['nk'] = z((S_, V, K), i32)
+        t['zr'] = z((S_, V, R), i32)
+        t['order'] = z((S_, V, R), i32)
+        t['stat'] = z((S_, L.NFIELD, K, Cn), f64)
+        t['cnt'] = z((S_, K, self.CT), f64)
+        t['err'] = z((S_,), i32)
+        t['seq'] = z((S_, V, R), i32)
+        t['moved'] = z((S_, V, R), i32)
+        t['movedflag'] = z((S_, V, R), torch.uint8)
+        t['colL'] = z((S_, Cn, V + 1), f64)
+        t['aux_zr'] = z((S_, R), i32)
+        t['aux_alpha'] = z((S_, Cn), f64)
+        self.t = t
+        self.arena = None
+        st = L.cc_state()
+        st.R, st.C, st.Cp, st.S = R, Cn, self.Cp, S_
+        st.Vcap, st.Kcap, st.CT = V, K, self.CT
+        for name in ('Xrm', 'Xcm', 'ctype', 'ncat', 'catoff', 'grids', 'row_alpha_grid',
+                     'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha',
+                     'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'seq',
+                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_alpha'):
+            setattr(st, name, t[name].data_ptr())
+        st.arena = None
+        st.arena_bytes = 0
+        self.st = st
+        self.lib = L.load()
+
+    # ------------------------------------------------------------------ helpers
+    def stream_ptr(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        torch.cuda.synchronize(self.device)
+
+    def check_errors(self):
+        err = self.t['err'].cpu().numpy()
+        if np.any(err != 0):
+            bad = np.nonzero(err)[0]
+            code = int(err[bad[0]])
+            self.t['err'].zero_()
+            if code == L.ERR_CAPACITY:
+                raise L.CgpmB200Error(
+                    'cluster/view capacity exceeded in chains %s (Kcap=%d, Vcap=%d): '
+                    'recreate the engine with larger capacities' % (bad.tolist(), self.Kcap, self.Vcap))
+            raise L.CgpmB200Error('numerical failure (NaN or zero-mass conditional) in chains %s'
+                                  % (bad.tolist(),))
+
+    # ------------------------------------------------------- chain load / read
+    def upload_chain(self, s, ch):
+        """ch: dict from codec.pack_chain (numpy arrays, slot form)."""
+        t, dev = self.t, self.device
+        V, K, R = self.Vcap, self.Kcap, self.R
+        nviews = len(ch['view_slots'])
+        if nviews > V:
+            raise L.CgpmB200Error('chain needs %d views > Vcap=%d' % (nviews, V))
+        t['hyp'][s].copy_(torch.from_numpy(ch['hyp']))
+        t['zv'][s].copy_(torch.from_numpy(ch['zv']))
+        nv = np.zeros(V, np.int32); view_id = np.full(V, -1, np.int32)
+        valpha = np.ones(V); nclu = np.zeros(V, np.int32)
+        live = np.full((V, K), -1, np.int32); cid = np.zeros((V, K), np.int32)
+        nk = np.zeros((V, K), np.int32)
+        for j, v in enumerate(ch['view_slots']):
+            Kv = len(ch['cid'][j])
+            if Kv > K - 1:
+                raise L.CgpmB200Error('view needs %d clusters > Kcap-1=%d' % (Kv, K - 1))
+            nv[v] = ch['nv'][j]; view_id[v] = ch['view_id'][j]; valpha[v] = ch['view_alpha'][j]
+            nclu[v] = Kv
+            live[v, :Kv] = np.arange(Kv); cid[v, :Kv] = ch['cid'][j]; nk[v, :Kv] = ch['nk'][j]
+            t['zr'][s, v].copy_(torch.from_numpy(ch['zr'][j]))
+            t['order'][s, v].copy_(torch.from_numpy(ch['order'][j]))
+        t['nv'][s].copy_(torch.from_numpy(nv)); t['view_id'][s].copy_(torch.from_numpy(view_id))
+        t['view_alpha'][s].copy_(torch.from_numpy(valpha)); t['nclu'][s].copy_(torch.from_numpy(nclu))
+        t['live'][s].copy_(torch.from_numpy(live)); t['cid'][s].copy_(torch.from_numpy(cid))
+        t['nk'][s].copy_(torch.from_numpy(nk))
+        t['col_alpha'][s] = float(ch['col_alpha'])
+
+    def download_chain(self, s, with_stats=False):
+        t = self.t
+        out = {}
+        nv = t['nv'][s].cpu().numpy()
+        slots = [int(v) for v in np.nonzero(nv > 0)[0]]
+        out['view_slots'] = slots
+        out['nv'] = [int(nv[v]) for v in slots]
+        view_id = t['view_id'][s].cpu().numpy()
+        out['view_id'] = [int(view_id[v]) for v in slots]
+        valpha = t['view_alpha'][s].cpu().numpy()
+        out['view_alpha'] = [float(valpha[v]) for v in slots]
+        out['col_alpha'] = float(t['col_alpha'][s].item())
+        out['zv'] = t['zv'][s].cpu().numpy()
+        out['hyp'] = t['hyp'][s].cpu().numpy()
+        nclu = t['nclu'][s].cpu().numpy()
+        live = t['live'][s].cpu().numpy(); cid = t['cid'][s].cpu().numpy(); nk = t['nk'][s].cpu().numpy()
+        out['live'] = [live[v, :nclu[v]].copy() for v in slots]
+        out['cid'] = [cid[v][live[v, :nclu[v]]].copy() for v in slots]
+        out['nk'] = [nk[v][live[v, :nclu[v]]].copy() for v in slots]
+        out['zr'] = [t['zr'][s, v].cpu().numpy() for v in slots]         # cluster slots
+        out['cid_by_slot'] = [cid[v].copy() for v in slots]
+        out['order'] = [t['order'][s, v].cpu().numpy() for v in slots]
+        if with_stats:
+            out['stat'] = t['stat'][s].cpu().numpy()
+            out['cnt'] = t['cnt'][s].cpu().numpy()
+        return out
+
+    # ------------------------------------------------------------------ kernels
+    def rebuild(self, pairs=None):
+        """Recompute tables for (chain, view slot) pairs (None = everything)."""
+        if pairs is None:
+            rc = self.lib.cc_rebuild(C.byref(self.st), 0, None, None, self.stream_ptr())
+        else:
+            if len(pairs) == 0:
+                return
+            ch = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int32)
+            vw = np.ascontiguousarray([p[1] for p in pairs], dtype=np.int32)
+            rc = self.lib.cc_rebuild(C.byref(self.st), len(pairs), ch.ctypes.data_as(C.c_void_p),
+                                     vw.ctypes.data_as(C.c_void_p), self.stream_ptr())
+            self.sync()            # host work lists must outlive the async copy
+        L.check(rc, 'cc_rebuild')
+
+    def logpdf_score(self):
+        out = torch.empty((self.S,), dtype=torch.float64, device=self.device)
+        L.check(self.lib.cc_logpdf_score(C.byref(self.st), C.c_void_p(out.data_ptr()), self.stream_ptr()),
+                'cc_logpdf_score')
+        return out
+
+    def transition_rows(self, work, perm=None, u=None, trace=None, trace_stride=0, seed=0, counter=0):
+        """work: list of dicts(chain, view, n, perm_is_index, perm_off, u_off, trace_off)."""
+        n = len(work)
+        if n == 0:
+            return
+        arr = (L.cc_row_work * n)()
+        for i, w in enumerate(work):
+            arr[i].chain = w['chain']; arr[i].view = w['view']; arr[i].n = w['n']
+            arr[i].perm_is_index = w.get('perm_is_index', 1)
+            arr[i].perm_off = w.get('perm_off', -1)
+            arr[i].u_off = w.get('u_off', -1)
+            arr[i].trace_off = w.get('trace_off', -1)
+        rc = self.lib.cc_transition_rows(
+            C.byref(self.st), n, arr,
+            C.c_void_p(perm.data_ptr()) if perm is not None else None,
+            C.c_void_p(u.data_ptr()) if u is not None else None,
+            C.c_void_p(trace.data_ptr()) if trace is not None else None,
+            int(trace_stride), C.c_uint64(seed), C.c_uint64(counter), self.stream_ptr())
+        L.check(rc, 'cc_transition_rows')

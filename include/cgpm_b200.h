@@ -1,0 +1,129 @@
+/* cgpm_b200.h -- C ABI of the B200 CrossCat Gibbs hot path.
+ *
+ * Drop-in boundary.  The reference (probcomp/cgpm, pure Python) has exactly one
+ * precedent for handing `State.transition` to native code:
+ * `State.transition_lovecat` (src/crosscat/state.py:812-831) which exports the
+ * state to dense arrays (src/crosscat/lovecat.py:73-223), calls
+ * `LocalEngine.analyze(M_c, T, X_L, X_D, kernel_list, n_steps, ...)`
+ * (lovecat.py:377-391) and writes the partitions back (lovecat.py:226-290).
+ * The entry points below are that interface for a GPU: dense chain state in
+ * device memory + one call per CrossCat kernel.  No torch types appear here;
+ * every pointer inside `cc_state` is a plain CUDA device pointer owned by the
+ * caller (the Python host allocates them as torch tensors, a C++ host would
+ * use cudaMalloc).  All functions return 0 on success, CC_ERR_* otherwise;
+ * `cc_last_error()` gives the message.  They enqueue on `stream` (a
+ * cudaStream_t passed as void*) and do not synchronise unless stated.
+ *
+ * Array layout (S chains, R rows, C columns, Vcap view slots per chain, Kcap
+ * cluster slots per view, CT = sum of categories over categorical columns):
+ * see `cc_state` below.  "slot" = dense index; the reference's sparse ids
+ * (view ids, cluster ids: crp.py:58-59,142) are carried in `view_id`/`cid`.
+ */
+#ifndef CGPM_B200_H
+#define CGPM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CC_ABI_VERSION 1
+#define CC_NGRID 30          /* hyper-grid points, dim.py:176 n_grid=30        */
+#define CC_NFIELD 8          /* per (cluster, column) statistic fields          */
+
+/* column types (config.py:25-39; only the two named by the scope contract) */
+#define CC_NORMAL 0
+#define CC_CATEGORICAL 1
+
+/* statistic fields of `stat[S][CC_NFIELD][Kcap][C]`                         */
+#define CC_F_N    0   /* count of non-NaN members   (normal.py:51, categorical.py:47) */
+#define CC_F_SX   1   /* sum_x                      (normal.py:52)  */
+#define CC_F_SXX  2   /* sum_x_sq                   (normal.py:53)  */
+#define CC_F_MN   3   /* cached posterior mean      (normal.py:186) */
+#define CC_F_A    4   /* cached rn/((rn+1) sn)                      */
+#define CC_F_CST  5   /* cached constant: normal G(N) - log(sn)/2 ; categorical log(N + alpha k) */
+#define CC_F_GN   6   /* cached G(N)   = lgamma((nu+N+1)/2)-lgamma((nu+N)/2)+log((r+N)/(r+N+1))/2-log(pi)/2 */
+#define CC_F_GM1  7   /* cached G(N-1)                               */
+
+#define CC_OK            0
+#define CC_ERR_ARG       1   /* invalid argument -> Python ValueError           */
+#define CC_ERR_CUDA      2   /* CUDA failure     -> Python RuntimeError         */
+#define CC_ERR_CAPACITY  3   /* Vcap/Kcap exceeded in some chain                */
+
+typedef struct cc_state {
+    int32_t R, C, Cp, S, Vcap, Kcap, CT, _pad;
+    /* ---- the table (shared by all chains; read-only to kernels) ---------- */
+    const double*  Xrm;            /* [R][Cp] row-major, NaN = missing; Cp = C rounded up to even (16-byte rows) */
+    const double*  Xcm;            /* [C][R]  column-major copy                  */
+    const int32_t* ctype;          /* [C]   CC_NORMAL / CC_CATEGORICAL           */
+    const int32_t* ncat;           /* [C]   k of categorical(k), else 0          */
+    const int32_t* catoff;         /* [C]   offset of the column's counts in `cnt` rows */
+    const double*  grids;          /* [C][4][CC_NGRID] normal: m,r,s,nu ; categorical: alpha in row 0 */
+    const double*  row_alpha_grid; /* [CC_NGRID] crp.py:148-152 with n = R       */
+    const double*  col_alpha_grid; /* [CC_NGRID] with n = C                      */
+    /* ---- per chain -------------------------------------------------------- */
+    double*  hyp;        /* [S][C][4]   m,r,s,nu | alpha,-,-,-                    */
+    int32_t* zv;         /* [S][C]      view slot of each column                  */
+    int32_t* nv;         /* [S][Vcap]   number of columns per view slot (0 = free)*/
+    int32_t* view_id;    /* [S][Vcap]   reference view id, -1 = free slot         */
+    double*  col_alpha;  /* [S]         column-CRP alpha                          */
+    double*  view_alpha; /* [S][Vcap]   row-CRP alpha per view                    */
+    int32_t* nclu;       /* [S][Vcap]   live clusters K                           */
+    int32_t* live;       /* [S][Vcap][Kcap] cluster slots in ascending cluster-id order */
+    int32_t* cid;        /* [S][Vcap][Kcap] reference cluster id of a slot        */
+    int32_t* nk;         /* [S][Vcap][Kcap] members per cluster slot              */
+    int32_t* zr;         /* [S][Vcap][R]    cluster slot of each row              */
+    int32_t* order;      /* [S][Vcap][R]    member order of the view's CRP (crp.py:45-59) */
+    double*  stat;       /* [S][CC_NFIELD][Kcap][C]                               */
+    double*  cnt;        /* [S][Kcap][CT]   categorical counts                    */
+    int32_t* err;        /* [S]  sticky per-chain error code (CC_ERR_CAPACITY)    */
+    /* ---- scratch (caller-allocated, contents undefined between calls) ----- */
+    int32_t* seq;        /* [S][Vcap][R]  row visiting sequence of the current sweep */
+    int32_t* moved;      /* [S][Vcap][R]  rows re-seated in the current sweep, in order */
+    uint8_t* movedflag;  /* [S][Vcap][R]                                          */
+    double*  colL;       /* [S][C][Vcap+1] column marginal matrix (last = auxiliary view) */
+    int32_t* aux_zr;     /* [S][R]   auxiliary-view partition (one column step)   */
+    double*  aux_alpha;  /* [S][C]   alpha drawn for each column's auxiliary view */
+    void*    arena;      /* per-worker scratch for the auxiliary CRP simulation   */
+    int64_t  arena_bytes;
+} cc_state;
+
+/* One unit of work of the rows kernel: a (chain, view slot) pair and where its
+ * injected randomness lives.  perm/u offsets index `perm`/`u` of
+ * cc_transition_rows (element offsets), or -1 to use the device generator. */
+typedef struct cc_row_work {
+    int32_t chain, view;
+    int32_t n;            /* number of rows to visit                             */
+    int32_t perm_is_index;/* 1: perm[i] indexes `order` (rows=None, view.py:249-250); 0: perm[i] is a rowid */
+    int64_t perm_off;     /* into `perm`, or -1: device pseudo-random permutation of `order` */
+    int64_t u_off;        /* into `u`,    or -1: Philox uniforms                  */
+    int64_t trace_off;    /* into `trace`, or -1                                  */
+} cc_row_work;
+
+const char* cc_last_error(void);
+int cc_abi_version(void);
+
+/* Recompute every cached field of `stat` and the counts from (X, zr, order,
+ * hyp) for the listed (chain, view slot) pairs, summing each cluster in the
+ * view's member order -- the device form of View._bulk_incorporate
+ * (src/mixtures/view.py:483-494).  views == NULL: all live views of all chains. */
+int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains,
+               const int32_t* views, void* stream);
+
+/* State.logpdf_score (src/crosscat/state.py:384-387): column-CRP marginal +
+ * per view [row-CRP marginal + sum of cluster marginals].  out: device [S]. */
+int cc_logpdf_score(const cc_state* st, double* out, void* stream);
+
+/* View.transition_rows for every work item (src/mixtures/view.py:247-252,
+ * 393-429).  `perm`, `u`, `trace` are device buffers (may be NULL when no work
+ * item refers to them).  seed/counter key the device generator. */
+int cc_transition_rows(const cc_state* st, int n_work, const cc_row_work* work /*host*/,
+                       const int32_t* perm, const double* u, double* trace,
+                       int trace_stride, uint64_t seed, uint64_t counter,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGPM_B200_H */

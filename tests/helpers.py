@@ -1,0 +1,80 @@
+"""Shared test helpers (oracle <-> device plumbing)."""
+from collections import OrderedDict
+
+import numpy as np
+
+import crosscat_oracle as co
+from cgpm_b200 import _lib as L
+from cgpm_b200 import codec
+
+CT = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL}
+
+
+def small_table(n_rows=60, seed=0, nan=True):
+    from cgpm_b200.synth import gen_table
+    cct = ['normal', 'categorical', 'normal', 'categorical', 'normal', 'normal']
+    da = [None, {'k': 4}, None, {'k': 3}, None, None]
+    X, _, _ = gen_table(n_rows, cct, da, n_views=2, clusters_per_view=3, seed=seed)
+    if nan:
+        rng = np.random.RandomState(seed + 1)
+        for _ in range(max(3, n_rows // 15)):
+            X[rng.randint(n_rows), rng.randint(len(cct))] = np.nan
+    return X, cct, da
+
+
+def ctype_arrays(cct, da):
+    ctype = np.array([CT[c] for c in cct], dtype=np.int32)
+    ncat = np.array([int(d['k']) if d and 'k' in d else 0 for d in da], dtype=np.int32)
+    return ctype, ncat
+
+
+def oracle_spec(o):
+    """OState -> codec spec (views in the oracle's insertion order)."""
+    ctype = np.array([CT[o.dim_for(c).cctype] for c in o.outputs], dtype=np.int32)
+    views = OrderedDict()
+    for v, view in o.views.items():
+        views[v] = {'alpha': float(view.crp.alpha),
+                    'Zr': np.array([view.Zr[i] for i in range(o.n_rows)]),
+                    'order': np.array(list(view.Zr.keys()))}
+    hyp = codec.hypers_to_array([o.dim_for(c).hypers for c in o.outputs], ctype)
+    return {'Zv': [o.Zv[c] for c in o.outputs], 'views': views,
+            'alpha': float(o.crp.alpha), 'hyp': hyp}
+
+
+def oracle_suffstats(o):
+    """{(col index, cluster id): stats} from the oracle."""
+    out = {}
+    for ci, c in enumerate(o.outputs):
+        dim = o.dim_for(c)
+        for k, st in dim.clusters.items():
+            out[(ci, int(k))] = st
+    return out
+
+
+def device_suffstats(dev, s, ctype):
+    """{(col index, cluster id): stats} from the device tables of chain s."""
+    dl = dev.download_chain(s, with_stats=True)
+    out = {}
+    for j, v in enumerate(dl['view_slots']):
+        cols = np.nonzero(dl['zv'] == v)[0]
+        for pos, k in enumerate(dl['live'][j]):
+            cid = int(dl['cid'][j][pos])
+            for c in cols:
+                N = dl['stat'][L.F_N, k, c]
+                if ctype[c] == L.NORMAL:
+                    out[(int(c), cid)] = [N, dl['stat'][L.F_SX, k, c], dl['stat'][L.F_SXX, k, c]]
+                else:
+                    o0 = dev.catoff_h[c]
+                    out[(int(c), cid)] = [N, dl['cnt'][k, o0:o0 + dev.ncat_h[c]].copy()]
+    return out, dl
+
+
+def assert_suffstats_equal(a, b):
+    assert set(a.keys()) == set(b.keys()), (sorted(a.keys())[:10], sorted(b.keys())[:10])
+    for key in a:
+        sa, sb = a[key], b[key]
+        assert float(sa[0]) == float(sb[0]), (key, sa, sb)
+        if len(sa) == 3:
+            assert float(sa[1]) == float(sb[1]) and float(sa[2]) == float(sb[2]), (key, sa, sb)
+        else:
+            assert np.array_equal(np.asarray(sa[1], float), np.asarray(sb[1], float)), (key, sa, sb)

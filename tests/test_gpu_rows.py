@@ -1,0 +1,107 @@
+"""GPU parity of the rows kernel and the table rebuild against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import crosscat_oracle as co
+from helpers import (small_table, ctype_arrays, oracle_spec, oracle_suffstats,
+                     device_suffstats, assert_suffstats_equal)
+
+pytestmark = pytest.mark.gpu
+
+
+def make_pair(n_rows, seed, S=1, **kw):
+    from cgpm_b200.device import DeviceChains
+    from cgpm_b200 import codec
+    X, cct, da = small_table(n_rows, seed)
+    ctype, ncat = ctype_arrays(cct, da)
+    dev = DeviceChains(X, ctype, ncat, S, **kw)
+    oracles = []
+    for s in range(S):
+        o = co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed * 100 + s))
+        dev.upload_chain(s, codec.pack_chain(oracle_spec(o), X.shape[0], X.shape[1]))
+        oracles.append(o)
+    dev.rebuild()
+    dev.sync()
+    return X, ctype, dev, oracles
+
+
+@pytest.mark.parametrize('n_rows,seed', [(40, 1), (150, 2)])
+def test_rebuild_and_score_match_oracle(n_rows, seed):
+    X, ctype, dev, oracles = make_pair(n_rows, seed, S=2)
+    scores = dev.logpdf_score().cpu().numpy()
+    for s, o in enumerate(oracles):
+        got, _ = device_suffstats(dev, s, ctype)
+        assert_suffstats_equal(oracle_suffstats(o), got)        # bit-exact
+        ref = o.logpdf_score()
+        assert abs(scores[s] - ref) <= 1e-10 * abs(ref), (scores[s], ref)
+
+
+def rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=False):
+    """One 'rows' kernel call with the host numpy stream injected, mirroring the
+    draw order of View.transition_rows (one permutation + one uniform per row)."""
+    R = dev.R
+    TS = 3 + dev.Kcap
+    work, perms, us = [], [], []
+    off = 0
+    for s, o in enumerate(oracles):
+        for v in views_order[s]:
+            perms.append(rngs[s].permutation(R).astype(np.int32))
+            us.append(rngs[s].random_sample(R))
+            work.append(dict(chain=s, view=v, n=R, perm_is_index=1, perm_off=off, u_off=off,
+                             trace_off=(len(work) * R * TS if trace else -1)))
+            off += R
+    perm = torch.from_numpy(np.concatenate(perms)).to(dev.device)
+    u = torch.from_numpy(np.concatenate(us)).to(dev.device)
+    tr = torch.zeros(len(work) * R * TS, dtype=torch.float64, device=dev.device) if trace else None
+    dev.transition_rows(work, perm=perm, u=u, trace=tr, trace_stride=TS)
+    dev.sync()
+    dev.check_errors()
+    return work, (tr.cpu().numpy().reshape(len(work), R, TS) if trace else None)
+
+
+@pytest.mark.parametrize('n_rows,seed,kw', [(40, 1, {}), (150, 2, {}), (300, 3, {})])
+def test_rows_trajectory_matches_oracle(n_rows, seed, kw):
+    """Injected shared stream: identical partitions, bit-identical sufficient
+    statistics, conditional log-probabilities within 1e-5 relative."""
+    X, ctype, dev, oracles = make_pair(n_rows, seed, S=2, **kw)
+    # the oracle draws from its own RandomState; the device gets the same stream
+    rngs = [np.random.RandomState(7 + s) for s in range(len(oracles))]
+    for s, o in enumerate(oracles):
+        o.rng.set_state(rngs[s].get_state())
+        for view in o.views.values():
+            view.rng = o.rng
+    views_order = [list(range(len(o.views))) for o in oracles]
+    for sweep in range(4):
+        otr = [dict() for _ in oracles]
+        for s, o in enumerate(oracles):
+            o.transition_view_rows(trace=otr[s])
+        work, tr = rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=True)
+        for s, o in enumerate(oracles):
+            assert rngs[s].random_sample() == o.rng.random_sample()
+            got, dl = device_suffstats(dev, s, ctype)
+            # partitions and member order
+            for j, (vid, view) in enumerate(o.views.items()):
+                zr_dev = dl['cid_by_slot'][j][dl['zr'][j]]
+                zr_ref = np.array([view.Zr[i] for i in range(n_rows)])
+                assert np.array_equal(zr_dev, zr_ref), (sweep, s, vid)
+                assert np.array_equal(dl['order'][j], np.array(list(view.Zr.keys())))
+            assert_suffstats_equal(oracle_suffstats(o), got)
+        # per-step conditionals
+        wi = 0
+        for s, o in enumerate(oracles):
+            for vid in o.views:
+                steps = otr[s][vid]
+                for i, (rowid, K, logp, zb) in enumerate(steps):
+                    rec = tr[wi, i]
+                    assert int(rec[0]) == rowid and int(rec[1]) == len(K) and int(rec[2]) == zb
+                    got = rec[3:3 + len(K)]
+                    ref = np.asarray(logp)
+                    fin = np.isfinite(ref)
+                    assert np.array_equal(np.isfinite(got), fin)
+                    assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-5 * np.maximum(1.0, np.abs(ref[fin])))
+                wi += 1
+    scores = dev.logpdf_score().cpu().numpy()
+    for s, o in enumerate(oracles):
+        ref = o.logpdf_score()
+        assert abs(scores[s] - ref) <= 1e-10 * abs(ref)
