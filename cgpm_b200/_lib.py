@@ -31,7 +31,8 @@ class cc_state(C.Structure):
         ('zr', C.c_void_p), ('order', C.c_void_p), ('stat', C.c_void_p), ('cnt', C.c_void_p),
         ('err', C.c_void_p),
         ('seq', C.c_void_p), ('moved', C.c_void_p), ('movedflag', C.c_void_p),
-        ('colL', C.c_void_p), ('aux_zr', C.c_void_p), ('aux_alpha', C.c_void_p),
+        ('colL', C.c_void_p), ('aux_zr', C.c_void_p), ('aux_nk', C.c_void_p), ('aux_K', C.c_void_p),
+        ('aux_alpha', C.c_void_p),
         ('arena', C.c_void_p), ('arena_bytes', C.c_int64),
     ]
 
@@ -58,12 +59,24 @@ def _declare(lib):
     lib.cc_abi_version.restype = I
     lib.cc_abi_version.argtypes = []
     lib.cc_rebuild.restype = I
-    lib.cc_rebuild.argtypes = [C.POINTER(cc_state), I, P, P, P]
+    lib.cc_rebuild.argtypes = [C.POINTER(cc_state), I, P, P, P, P]
     lib.cc_logpdf_score.restype = I
     lib.cc_logpdf_score.argtypes = [C.POINTER(cc_state), P, P]
     lib.cc_transition_rows.restype = I
     lib.cc_transition_rows.argtypes = [C.POINTER(cc_state), I, C.POINTER(cc_row_work),
                                        P, P, P, I, U64, U64, P]
+    lib.cc_col_aux.restype = I
+    lib.cc_col_aux.argtypes = [C.POINTER(cc_state), I, P, P, P, P, I, U64, U64, P]
+    lib.cc_col_marginals.restype = I
+    lib.cc_col_marginals.argtypes = [C.POINTER(cc_state), I, P, P, P, P, P, I, P]
+    lib.cc_col_scan.restype = I
+    lib.cc_col_scan.argtypes = [C.POINTER(cc_state), I, P, P, I, P, P, P, U64, U64, P, P, P, I, P]
+    lib.cc_col_install.restype = I
+    lib.cc_col_install.argtypes = [C.POINTER(cc_state), I, P, P, P]
+    lib.cc_transition_col_hypers.restype = I
+    lib.cc_transition_col_hypers.argtypes = [C.POINTER(cc_state), I, P, P, P, P, U64, U64, P]
+    lib.cc_transition_alphas.restype = I
+    lib.cc_transition_alphas.argtypes = [C.POINTER(cc_state), I, P, P, P, I, U64, U64, P]
     for name, argtypes in OPTIONAL.items():
         if hasattr(lib, name):
             f = getattr(lib, name)
@@ -76,7 +89,8 @@ OPTIONAL = {}
 
 # every symbol include/cgpm_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_logpdf_score',
-           'cc_transition_rows']
+           'cc_transition_rows', 'cc_col_aux', 'cc_col_marginals', 'cc_col_scan', 'cc_col_install',
+           'cc_transition_col_hypers', 'cc_transition_alphas']
 
 
 def load():

@@ -1,0 +1,555 @@
+"""Host orchestration of S CrossCat chains on one GPU.
+
+`Chains` owns a DeviceChains (device memory + C ABI) and the small host-side
+mirrors the reference keeps implicitly in its object graph: each chain's
+numpy RandomState, the insertion order of its views (State.views is an
+OrderedDict, src/crosscat/state.py:141-159), the order of hyper names, and the
+diagnostics counters (state.py:907-914).  It runs the kernel scheduler of
+State.transition / _transition_generic (state.py:727-761,866-905) for all
+selected chains in lock-step, one CUDA launch per CrossCat kernel.
+
+Two random-stream modes:
+  stream='numpy'   every draw comes from the chain's RandomState in exactly the
+                   order the reference consumes it and is
+                   injected into the kernels; chains then follow the reference's
+                   trajectories for the same seeds.  The column kernel needs a
+                   host round-trip per column in this mode (its stream use is
+                   data dependent, src/primitives/crp.py:141).
+  stream='philox'  counter-based device generator; nothing crosses PCIe inside
+                   a sweep.  Same kernels, same conditional distributions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import codec
+from . import hostmath as hm
+from .device import DeviceChains
+
+CCTYPES = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL}
+KERNELS = ['alpha', 'view_alphas', 'column_params', 'column_hypers', 'rows', 'columns']
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _dp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Chains(object):
+    def __init__(self, X, outputs=None, cctypes=None, distargs=None, Cd=None, Ci=None,
+                 S=1, stream='philox', device=None, Vcap=None, Kcap=None, seed=0):
+        X = np.asarray(X, dtype=np.float64)
+        if X.ndim != 2:
+            raise ValueError('X must be a 2-D table.')
+        R, Cn = X.shape
+        self.outputs = list(outputs) if outputs else list(range(Cn))
+        if len(self.outputs) != Cn or any(o < 0 for o in self.outputs):
+            raise ValueError('outputs must be %d non-negative ids' % Cn)
+        cctypes = list(cctypes) if cctypes else ['normal'] * Cn
+        distargs = [dict(d) if d else {} for d in (distargs or [None] * Cn)]
+        bad = [c for c in cctypes if c not in CCTYPES]
+        if bad:                                           # same rule as state.py:817-820
+            raise ValueError('Only normal and categorical cgpms supported by cgpm_b200: %s' % (cctypes,))
+        for ct, d in zip(cctypes, distargs):
+            if ct == 'categorical' and 'k' not in d:
+                raise ValueError('Categorical requires distarg `k`.')
+        self.cctypes, self.distargs = cctypes, distargs
+        self.ctype = np.array([CCTYPES[c] for c in cctypes], dtype=np.int32)
+        self.ncat = np.array([int(d['k']) if ct == 'categorical' else 0
+                              for ct, d in zip(cctypes, distargs)], dtype=np.int32)
+        self.Cd = list(Cd) if Cd else []
+        self.Ci = list(Ci) if Ci else []
+        if stream not in ('numpy', 'philox'):
+            raise ValueError("stream must be 'numpy' or 'philox'")
+        self.stream = stream
+        self.col_index = {c: i for i, c in enumerate(self.outputs)}
+        if Vcap is None:
+            Vcap = min(Cn, 32) if R * min(Cn, 32) <= (1 << 24) else min(Cn, 16)
+        self.dev = DeviceChains(X, self.ctype, self.ncat, S, Vcap=Vcap, Kcap=Kcap, device=device)
+        self.R, self.C, self.S = R, Cn, S
+        self.rngs = [None] * S
+        self.views_order = [[] for _ in range(S)]
+        self.hyper_order = [[list(codec.HYPER_NAMES[int(t)]) for t in self.ctype] for _ in range(S)]
+        self.diagnostics = [self._fresh_diag() for _ in range(S)]
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.counter = 1
+        self._ci_dev = None
+        self._mirror = None
+        if self.Ci:
+            self._build_ci()
+
+    # ------------------------------------------------------------------ set-up
+    @staticmethod
+    def _fresh_diag():
+        return {'iterations': {}, 'logscore': [], 'column_crp_alpha': [], 'column_partition': []}
+
+    def _build_ci(self):
+        adj = [[] for _ in range(self.C)]
+        for pair in self.Ci:
+            for a in pair:
+                for b in pair:
+                    if a != b:
+                        adj[self.col_index[a]].append(self.col_index[b])
+        off = np.zeros(self.C + 1, np.int32)
+        off[1:] = np.cumsum([len(a) for a in adj])
+        flat = np.array([x for a in adj for x in a] or [0], np.int32)
+        self._ci_dev = (torch.from_numpy(off).to(self.dev.device), torch.from_numpy(flat).to(self.dev.device))
+
+    def init_chain(self, s, rng, Zv=None, Zrv=None, alpha=None, view_alphas=None, hypers=None,
+                   diagnostics=None):
+        """State.__init__ (src/crosscat/state.py:47-182) for chain s, consuming
+        `rng` in the reference's order: column-CRP alpha, column partition, then
+        per view (in `set(Zv.values())` order) its alpha, row partition and the
+        hypers of its columns."""
+        dev, R, Cn = self.dev, self.R, self.C
+        exact = self.stream == 'numpy'
+        sim = hm.crp_simulate_exact if exact else hm.crp_simulate_fast
+        self.rngs[s] = rng
+        if alpha is None:
+            alpha = rng.choice(dev.col_alpha_grid_h)
+        if Zv is None:
+            if self.Ci or self.Cd:
+                raise ValueError('cgpm_b200: supply Zv when using Cd/Ci constraints.')
+            zv_ids = sim(Cn, alpha, rng)
+            Zv_od = OrderedDict((c, int(z)) for c, z in zip(self.outputs, zv_ids))
+        else:
+            Zv_od = OrderedDict((c, int(z)) for c, z in dict(Zv).items())
+            if set(Zv_od.keys()) != set(self.outputs):
+                raise ValueError('Zv must assign every output.')
+        view_alphas = dict(view_alphas) if view_alphas else {}
+        Zrv = dict(Zrv) if Zrv else {}
+        if Zrv and set(Zrv.keys()) != set(Zv_od.values()):
+            raise ValueError('Zrv keys must match the views of Zv.')
+        hyp = np.zeros((Cn, 4))
+        names_all = [None] * Cn
+        views = OrderedDict()
+        for v in set(Zv_od.values()):
+            va = view_alphas.get(v)
+            if va is None:
+                va = rng.choice(dev.row_alpha_grid_h)
+            zr = Zrv.get(v)
+            zr = sim(R, va, rng) if zr is None else np.asarray(zr, dtype=np.int64)
+            if zr.shape != (R,):
+                raise ValueError('Zrv[%s] must have one entry per row.' % (v,))
+            views[v] = {'alpha': float(va), 'Zr': zr, 'order': None}
+            for c in [o for o in self.outputs if Zv_od[o] == v]:
+                i = self.col_index[c]
+                names = list(codec.HYPER_NAMES[int(self.ctype[i])])
+                given = hypers[i] if hypers else None
+                if given:
+                    names_all[i] = list(given.keys())
+                    for n in names:
+                        hyp[i, names.index(n)] = float(given[n])
+                else:
+                    names_all[i] = names
+                    for hi, n in enumerate(names):              # dim.py:180-183
+                        hyp[i, hi] = rng.choice(dev.grids_h[i][hi])
+        spec = {'Zv': [Zv_od[c] for c in self.outputs], 'views': views, 'alpha': float(alpha), 'hyp': hyp}
+        dev.upload_chain(s, codec.pack_chain(spec, R, Cn))
+        self.views_order[s] = list(range(len(views)))
+        self.hyper_order[s] = names_all
+        self.diagnostics[s] = self._fresh_diag() if diagnostics is None else self._load_diag(diagnostics)
+        self._mirror = None
+
+    @staticmethod
+    def _load_diag(d):
+        out = Chains._fresh_diag()
+        for k, v in dict(d).items():
+            out[k] = v
+        out['iterations'] = dict(out.get('iterations', {}))
+        return out
+
+    def finish_init(self, chains=None):
+        if chains is None:
+            self.dev.rebuild()
+        else:
+            nv = self.dev.t['nv'].cpu().numpy()
+            self.dev.rebuild([(s, int(v)) for s in chains for v in np.nonzero(nv[s] > 0)[0]])
+        self._mirror = None
+
+    # ------------------------------------------------------------------ mirror
+    def mirror(self):
+        """Small per-chain structure read back from the device: zv, nv, view_id."""
+        if self._mirror is None:
+            t = self.dev.t
+            self._mirror = {'zv': t['zv'].cpu().numpy(), 'nv': t['nv'].cpu().numpy(),
+                            'view_id': t['view_id'].cpu().numpy()}
+        return self._mirror
+
+    def _refresh_views_order(self, chains):
+        m = self.mirror()
+        for s in chains:
+            live = [int(v) for v in np.nonzero(m['nv'][s] > 0)[0]]
+            keep = [v for v in self.views_order[s] if v in live]
+            new = sorted([v for v in live if v not in keep], key=lambda v: m['view_id'][s][v])
+            self.views_order[s] = keep + new
+
+    # ------------------------------------------------------------- transitions
+    def transition(self, N=None, S=None, kernels=None, rowids=None, cols=None, views=None,
+                   progress=True, checkpoint=None, chains=None):
+        """State.transition (state.py:727-761) + _transition_generic (:866-905) for
+        the selected chains in lock-step."""
+        chains = list(range(self.S)) if chains is None else list(chains)
+        if cols and any(c not in self.col_index for c in cols):
+            raise ValueError('Only CrossCat columns may be transitioned.')
+        if kernels is None:
+            kernels = list(KERNELS)
+        for k in kernels:
+            if k not in KERNELS:
+                raise KeyError(k)
+        if 'columns' in kernels and self.Cd:
+            raise ValueError('Cannot transition columns with dependence constraint, '
+                             'use State.transition_lovecat.')
+        table = {
+            'alpha': lambda: self.transition_crp_alpha(chains),
+            'view_alphas': lambda: self.transition_view_alphas(chains, views=views, cols=cols),
+            'column_params': lambda: self._count(chains, 'column_params'),
+            'column_hypers': lambda: self.transition_dim_hypers(chains, cols=cols),
+            'rows': lambda: self.transition_view_rows(chains, views=views, cols=cols, rows=rowids),
+            'columns': lambda: self.transition_dims(chains, cols=cols),
+        }
+        funcs = [table[k] for k in kernels]
+        if N is None and S is None:
+            N = 1
+        if progress is None:
+            progress = True
+        iters, start = 0, time.time()
+
+        def done():
+            p_sec = 0 if S is None else (time.time() - start) / S
+            p_it = 0 if N is None else float(iters) / N
+            return max(p_it, p_sec)
+        while funcs:
+            broke = False
+            for f in funcs:
+                p = done()
+                if progress:
+                    self._progress(p)
+                if p >= 1.:
+                    broke = True
+                    break
+                f()
+            if broke:
+                break
+            iters += 1
+            if checkpoint and iters % checkpoint == 0:
+                self._increment_diagnostics(chains)
+        self.dev.sync()
+        self.dev.check_errors()
+        if progress:
+            print('\rCompleted: %d iterations in %f seconds.' % (iters, time.time() - start))
+        return iters
+
+    @staticmethod
+    def _progress(p):
+        width = 30
+        k = int(min(max(p, 0), 1) * width)
+        sys.stdout.write('\r[%s%s] %.2f%%' % ('#' * k, '-' * (width - k), 100 * min(p, 1)))
+        sys.stdout.flush()
+
+    def _count(self, chains, name):
+        for s in chains:
+            it = self.diagnostics[s]['iterations']
+            it[name] = it.get(name, 0) + 1
+
+    def _increment_diagnostics(self, chains):
+        """state.py:911-914."""
+        scores = self.logpdf_score()
+        alphas = self.dev.t['col_alpha'].cpu().numpy()
+        for s in chains:
+            d = self.diagnostics[s]
+            d['logscore'].append(float(scores[s]))
+            d['column_crp_alpha'].append(float(alphas[s]))
+            d['column_partition'].append(self.Zv_items(s))
+
+    def _next_counter(self):
+        self.counter += 1
+        return self.counter
+
+    # -- alpha ---------------------------------------------------------------
+    def transition_crp_alpha(self, chains):
+        ch = np.ascontiguousarray(chains, dtype=np.int32)
+        u = None
+        if self.stream == 'numpy':
+            u = np.ascontiguousarray([self.rngs[s].random_sample() for s in chains])
+        L.check(self.dev.lib.cc_transition_alphas(C.byref(self.dev.st), len(ch), _p(ch), None, _p(u), 1,
+                                                  C.c_uint64(self.seed), C.c_uint64(self._next_counter()),
+                                                  self.dev.stream_ptr()), 'cc_transition_alphas')
+        self._count(chains, 'alpha')
+
+    def _views_for(self, s, views, cols):
+        """Selection rule of state.py:768-769 / 798-799 (view slots)."""
+        m = self.mirror()
+        if views is not None:
+            ids = list(views)
+        elif cols:
+            ids = list(set(int(m['view_id'][s][m['zv'][s][self.col_index[c]]]) for c in cols))
+        else:
+            return list(self.views_order[s])
+        slot_of = {int(m['view_id'][s][v]): v for v in range(self.dev.Vcap) if m['nv'][s][v] > 0}
+        return [slot_of[i] for i in ids]
+
+    def transition_view_alphas(self, chains, views=None, cols=None):
+        ch, vw, us = [], [], []
+        for s in chains:
+            for v in self._views_for(s, views, cols):
+                ch.append(s)
+                vw.append(v)
+                if self.stream == 'numpy':
+                    us.append([self.rngs[s].random_sample(), self.rngs[s].random_sample()])
+        ch = np.ascontiguousarray(ch, dtype=np.int32)
+        vw = np.ascontiguousarray(vw, dtype=np.int32)
+        u = np.ascontiguousarray(us, dtype=np.float64) if self.stream == 'numpy' else None
+        L.check(self.dev.lib.cc_transition_alphas(C.byref(self.dev.st), len(ch), _p(ch), _p(vw), _p(u), 2,
+                                                  C.c_uint64(self.seed), C.c_uint64(self._next_counter()),
+                                                  self.dev.stream_ptr()), 'cc_transition_alphas')
+        self._count(chains, 'view_alphas')
+
+    # -- column hypers -------------------------------------------------------
+    def transition_dim_hypers(self, chains, cols=None):
+        cidx = [self.col_index[c] for c in cols] if cols is not None else list(range(self.C))
+        ch, co, hord, us = [], [], [], []
+        for s in chains:
+            for i in cidx:
+                ch.append(s)
+                co.append(i)
+                if self.stream == 'numpy':
+                    names = list(self.hyper_order[s][i])
+                    self.rngs[s].shuffle(names)                           # dim.py:154-155
+                    canon = codec.HYPER_NAMES[int(self.ctype[i])]
+                    o = [canon.index(n) for n in names]
+                    hord.append(o + [-1] * (4 - len(o)))
+                    uu = [self.rngs[s].random_sample() for _ in names]
+                    us.append(uu + [0.0] * (4 - len(uu)))
+        ch = np.ascontiguousarray(ch, dtype=np.int32)
+        co = np.ascontiguousarray(co, dtype=np.int32)
+        ho = np.ascontiguousarray(hord, dtype=np.int32) if self.stream == 'numpy' else None
+        u = np.ascontiguousarray(us, dtype=np.float64) if self.stream == 'numpy' else None
+        L.check(self.dev.lib.cc_transition_col_hypers(C.byref(self.dev.st), len(ch), _p(ch), _p(co), _p(ho), _p(u),
+                                                      C.c_uint64(self.seed), C.c_uint64(self._next_counter()),
+                                                      self.dev.stream_ptr()), 'cc_transition_col_hypers')
+        self._count(chains, 'column_hypers')
+
+    # -- rows ------------------------------------------------------------------
+    def transition_view_rows(self, chains, views=None, cols=None, rows=None, trace=None):
+        """State.transition_view_rows (state.py:795-802) -> View.transition_rows."""
+        if self.R == 1:
+            return
+        R, dev = self.R, self.dev
+        n = R if rows is None else len(rows)
+        work, perms, us = [], [], []
+        off = 0
+        for s in chains:
+            for v in self._views_for(s, views, cols):
+                w = dict(chain=s, view=v, n=n, perm_is_index=1 if rows is None else 0)
+                if self.stream == 'numpy':
+                    rng = self.rngs[s]
+                    perms.append(np.asarray(rng.permutation(R if rows is None else rows), dtype=np.int32))
+                    us.append(rng.random_sample(n))
+                    w['perm_off'] = off
+                    w['u_off'] = off
+                    off += n
+                elif rows is not None:
+                    perms.append(np.asarray(np.random.RandomState((self.seed + self.counter + 7919 * s + v) % (2 ** 32))
+                                            .permutation(rows), dtype=np.int32))
+                    w['perm_off'] = off
+                    off += n
+                if trace is not None:
+                    w['trace_off'] = len(work) * n * trace['stride']
+                work.append(w)
+        perm = torch.from_numpy(np.concatenate(perms)).to(dev.device) if perms else None
+        u = torch.from_numpy(np.concatenate(us)).to(dev.device) if us else None
+        tr = None
+        if trace is not None:
+            tr = torch.zeros(max(len(work) * n * trace['stride'], 1), dtype=torch.float64, device=dev.device)
+        dev.transition_rows(work, perm=perm, u=u, trace=tr, trace_stride=trace['stride'] if trace else 0,
+                            seed=self.seed, counter=self._next_counter())
+        if trace is not None:
+            dev.sync()
+            trace['work'] = work
+            trace['data'] = tr.cpu().numpy()[:len(work) * n * trace['stride']].reshape(len(work), n, trace['stride'])
+        self._count(chains, 'rows')
+
+    # -- columns ---------------------------------------------------------------
+    def _ensure_arena(self, n_pairs):
+        dev = self.dev
+        R = self.R
+        n1 = (R + 31) >> 5
+        n2 = (n1 + 31) >> 5
+        per = (R + (R + n1 + n2 + 32) + (R + 1) + R + R + 3) & ~3
+        want = min(max(n_pairs, 1), 148 * 16)
+        free, _total = torch.cuda.mem_get_info(dev.device)
+        budget = max(int(free * 0.5), per * 4)
+        workers = max(1, min(want, budget // (per * 4)))
+        need = workers * per
+        if dev.arena is None or dev.arena.numel() < need:
+            dev.arena = None
+            dev.arena = torch.empty(need, dtype=torch.int32, device=dev.device)
+            dev.st.arena = dev.arena.data_ptr()
+            dev.st.arena_bytes = need * 4
+
+    def transition_dims(self, chains, cols=None, trace=None):
+        """State.transition_dims (state.py:804-810) for the selected chains."""
+        dev, lib, st = self.dev, self.dev.lib, C.byref(self.dev.st)
+        sp = dev.stream_ptr
+        cidx = [self.col_index[c] for c in cols] if cols is not None else list(range(self.C))
+        ncols = len(cidx)
+        nch = len(chains)
+        if ncols == 0 or nch == 0:
+            return
+        counter = self._next_counter()
+        seed = C.c_uint64(self.seed)
+        ci_off, ci_adj = (self._ci_dev if self._ci_dev else (None, None))
+        # column visiting order: rng.permutation(cols) (state.py:807)
+        perm = np.zeros((nch, ncols), np.int32)
+        for i, s in enumerate(chains):
+            if self.stream == 'numpy':
+                perm[i] = np.asarray(self.rngs[s].permutation(cidx), dtype=np.int32)
+            else:
+                perm[i] = np.asarray(np.random.RandomState((self.seed * 31 + counter * 1009 + s) % (2 ** 32))
+                                     .permutation(cidx), dtype=np.int32)
+        ch_h = np.ascontiguousarray(chains, dtype=np.int32)
+        ch_d = torch.from_numpy(ch_h).to(dev.device)
+        ts = trace['stride'] if trace is not None else 0
+        tr_d = torch.zeros(max(nch * ncols * ts, 1), dtype=torch.float64, device=dev.device) if trace is not None else None
+        self._mirror = None
+        if self.stream == 'philox':
+            self._ensure_arena(nch * ncols)
+            cols_d = torch.from_numpy(perm).to(dev.device)
+            pos_d = torch.zeros(nch, dtype=torch.int32, device=dev.device)
+            pend_d = torch.full((nch,), -1, dtype=torch.int32, device=dev.device)
+            # auxiliary views of every (chain, column) and marginals under every live view
+            a_ch = np.repeat(ch_h, ncols).astype(np.int32)
+            a_co = perm.reshape(-1).astype(np.int32)
+            L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), None, None, 0, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
+            m = self.mirror()
+            w_ch = np.ascontiguousarray([s for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
+            w_vw = np.ascontiguousarray([v for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
+            if cols is None:
+                L.check(lib.cc_col_marginals(st, len(w_ch), _p(w_ch), _p(w_vw), None, None, None, self.C, sp()), 'cc_col_marginals')
+            else:
+                row_of = {s: i for i, s in enumerate(chains)}
+                off = np.ascontiguousarray([row_of[s] * ncols for s in w_ch], dtype=np.int32)
+                cnt = np.full(len(w_ch), ncols, np.int32)
+                L.check(lib.cc_col_marginals(st, len(w_ch), _p(w_ch), _p(w_vw), _dp(cols_d), _p(off), _p(cnt), ncols, sp()), 'cc_col_marginals')
+            self._mirror = None
+            while True:
+                L.check(lib.cc_col_scan(st, nch, _dp(ch_d), _dp(cols_d), ncols, _dp(pos_d), _dp(pend_d), None,
+                                        seed, C.c_uint64(counter), _dp(ci_off), _dp(ci_adj), _dp(tr_d), ts, sp()), 'cc_col_scan')
+                pend = pend_d.cpu().numpy()
+                idx = np.nonzero(pend >= 0)[0]
+                if len(idx) == 0:
+                    break
+                b_ch = np.ascontiguousarray(ch_h[idx], dtype=np.int32)
+                b_co = np.ascontiguousarray(perm[idx, pend[idx]], dtype=np.int32)
+                # regenerate the same auxiliary partitions (same key), keep them, install
+                L.check(lib.cc_col_aux(st, len(b_ch), _p(b_ch), _p(b_co), None, None, 1, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
+                nv_before = dev.t['nv'].cpu().numpy()
+                L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), sp()), 'cc_col_install')
+                new_slots = np.array([int(np.nonzero(nv_before[s] == 0)[0][0]) if np.any(nv_before[s] == 0) else 0
+                                      for s in b_ch], dtype=np.int32)
+                rem_off = np.ascontiguousarray([i * ncols + pend[i] + 1 for i in idx], dtype=np.int32)
+                rem_cnt = np.ascontiguousarray([ncols - pend[i] - 1 for i in idx], dtype=np.int32)
+                keep = rem_cnt > 0
+                if np.any(keep):
+                    L.check(lib.cc_col_marginals(st, int(keep.sum()), _p(np.ascontiguousarray(b_ch[keep])),
+                                                 _p(np.ascontiguousarray(new_slots[keep])), _dp(cols_d),
+                                                 _p(np.ascontiguousarray(rem_off[keep])), _p(np.ascontiguousarray(rem_cnt[keep])),
+                                                 int(rem_cnt.max()), sp()), 'cc_col_marginals')
+                pos_d += (pend_d >= 0).to(torch.int32)
+                dev.sync()
+                dev.check_errors()
+        else:
+            self._ensure_arena(nch)
+            R = self.R
+            for j in range(ncols):
+                m = self.mirror()
+                a_ch, a_co, a_ai, a_u, draws = [], [], [], [], np.zeros((nch, 1))
+                for i, s in enumerate(chains):
+                    c = int(perm[i, j])
+                    own = m['zv'][s][c]
+                    singleton = m['nv'][s][own] == 1
+                    nviews = int(np.sum(m['nv'][s] > 0))
+                    rng = self.rngs[s]
+                    if not singleton:
+                        a_ch.append(s); a_co.append(c)
+                        a_ai.append(int(rng.randint(0, L.NGRID)))          # rng.choice(grid), dim.py:183
+                        a_u.append(rng.random_sample(R - 1) if R > 1 else np.zeros(0))
+                    if nviews + (0 if singleton else 1) > 1:
+                        draws[i, 0] = rng.random_sample()                   # state.py:1106
+                a_ch = np.ascontiguousarray(a_ch, dtype=np.int32); a_co = np.ascontiguousarray(a_co, dtype=np.int32)
+                a_ai = np.ascontiguousarray(a_ai, dtype=np.int32)
+                if len(a_ch):
+                    u_d = torch.from_numpy(np.ascontiguousarray(np.concatenate(a_u) if R > 1 else np.zeros(1))).to(dev.device)
+                    L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), _p(a_ai), _dp(u_d), 1, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
+                w_ch = np.ascontiguousarray([s for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
+                w_vw = np.ascontiguousarray([v for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
+                row_of = {s: i for i, s in enumerate(chains)}
+                colj_d = torch.from_numpy(np.ascontiguousarray(perm[:, j])).to(dev.device)
+                off = np.ascontiguousarray([row_of[s] for s in w_ch], dtype=np.int32)
+                cnt = np.ones(len(w_ch), np.int32)
+                L.check(lib.cc_col_marginals(st, len(w_ch), _p(w_ch), _p(w_vw), _dp(colj_d), _p(off), _p(cnt), 1, sp()), 'cc_col_marginals')
+                pos_d = torch.zeros(nch, dtype=torch.int32, device=dev.device)
+                pend_d = torch.full((nch,), -1, dtype=torch.int32, device=dev.device)
+                u_draw = torch.from_numpy(draws).to(dev.device)
+                trj = None
+                if tr_d is not None:
+                    trj = torch.zeros(nch * ts, dtype=torch.float64, device=dev.device)
+                L.check(lib.cc_col_scan(st, nch, _dp(ch_d), _dp(colj_d), 1, _dp(pos_d), _dp(pend_d), _dp(u_draw),
+                                        seed, C.c_uint64(counter), _dp(ci_off), _dp(ci_adj), _dp(trj), ts, sp()), 'cc_col_scan')
+                if trj is not None:
+                    tr_d.view(nch, ncols, ts)[:, j, :] = trj.view(nch, ts)
+                pend = pend_d.cpu().numpy()
+                idx = np.nonzero(pend >= 0)[0]
+                if len(idx):
+                    b_ch = np.ascontiguousarray(ch_h[idx], dtype=np.int32)
+                    b_co = np.ascontiguousarray(perm[idx, j], dtype=np.int32)
+                    L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), sp()), 'cc_col_install')
+                self._mirror = None
+                self._refresh_views_order(chains)
+            dev.sync()
+            dev.check_errors()
+        # re-incorporate every visited column under its final view (state.py:1110-1121)
+        mask = torch.zeros((self.S, self.C), dtype=torch.uint8, device=dev.device)
+        mask[ch_d.long().unsqueeze(1), torch.from_numpy(np.ascontiguousarray(cidx, dtype=np.int64)).to(dev.device).unsqueeze(0)] = 1
+        self._mirror = None
+        m = self.mirror()
+        pairs = [(s, int(v)) for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]]
+        dev.rebuild(pairs, mask=mask)
+        self._refresh_views_order(chains)
+        if trace is not None:
+            dev.sync()
+            trace['perm'] = perm
+            trace['data'] = tr_d.cpu().numpy()[:nch * ncols * ts].reshape(nch, ncols, ts)
+        self._count(chains, 'columns')
+
+    # ------------------------------------------------------------------ queries
+    def logpdf_score(self):
+        out = self.dev.logpdf_score()
+        return out.cpu().numpy()
+
+    def Zv_items(self, s):
+        m = self.mirror()
+        return [(self.outputs[i], int(m['view_id'][s][m['zv'][s][i]])) for i in range(self.C)]
+
+    def chain_spec(self, s, with_stats=False):
+        dl = self.dev.download_chain(s, with_stats=with_stats)
+        return codec.unpack_chain(dl, self.views_order[s]), dl
+
+    def logpdf_bulk(self, chains, rowids, targets_list, constraints_list=None):
+        from . import query
+        return query.logpdf_bulk(self, chains, rowids, targets_list, constraints_list)
+
+    def simulate_bulk(self, chains, rowids, targets_list, constraints_list=None, Ns=None):
+        from . import query
+        return query.simulate_bulk(self, chains, rowids, targets_list, constraints_list, Ns)

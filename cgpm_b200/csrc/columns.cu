@@ -1,0 +1,492 @@
+// Column (view) reassignment: State.transition_dims / _gibbs_transition_dim
+// (src/crosscat/state.py:804-810,1050-1123).
+//
+//   aux_kernel      the auxiliary view of a column: alpha ~ grid, a CRP-prior
+//                   partition of all rows (state.py:1078-1081 -> view.py:99-103 ->
+//                   crp.py:71-81, a strictly sequential draw), then the column's
+//                   marginal likelihood under it.  One warp per (chain, column):
+//                   the first 32 tables live in registers as running prefix sums
+//                   (one ballot per draw), later tables in a 32-ary count tree.
+//   (stats_kernel, MARGINAL mode, gives the marginals under the existing views.)
+//   scan_kernel     the sequential part: per column, CRP weights (crp.py:111-146)
+//                   + Ci mask (state.py:1098-1102) + log_pflip draw + bookkeeping
+//                   (state.py:1125-1154).  One warp per chain.  A move into the
+//                   auxiliary view pauses the chain; the host installs the view
+//                   (install_kernel) and resumes.
+#include "cc_common.cuh"
+
+#define CC_MAXCAT 256
+
+int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, const int32_t* d_views,
+                    int marginal, const int32_t* d_cols, const int32_t* d_coloff, const int32_t* d_colcnt,
+                    int max_cols, const uint8_t* d_mask, cudaStream_t stream);
+
+namespace {
+
+__device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+struct AuxParams {
+    cc_state st;
+    int n;
+    const int32_t* chains;
+    const int32_t* cols;
+    const int32_t* aidx;     // injected grid index per work item, or NULL
+    const double* u;         // injected uniforms [n][R-1], or NULL
+    int write_zr;
+    uint64_t seed, counter;
+    int32_t* arena;
+    size_t worker_stride;    // int32 units
+};
+
+__global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
+    const cc_state& st = p.st;
+    const int lane = threadIdx.x & 31;
+    const int worker = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nworkers = gridDim.x * (blockDim.x >> 5);
+    const int R = st.R;
+    const int n1 = (R + 31) >> 5, n2 = (n1 + 31) >> 5;
+    int32_t* base = p.arena + (size_t)worker * p.worker_stride;
+    int32_t* z = base;                      // [R] table of each row
+    int32_t* Lv[4];
+    Lv[0] = z + R;                          // [R]   counts of tables >= 32
+    Lv[1] = Lv[0] + R;                      // [n1]
+    Lv[2] = Lv[1] + n1;                     // [n2]
+    Lv[3] = Lv[2] + n2;                     // [32]
+    int32_t* start = Lv[3] + 32;            // [R+1]
+    int32_t* cursor = start + (R + 1);      // [R]
+    int32_t* grouped = cursor + R;          // [R]
+    const int ntree = R + n1 + n2 + 32;
+    const Philox rng(p.seed);
+
+    for (int w = worker; w < p.n; w += nworkers) {
+        const int s = p.chains[w], c = p.cols[w];
+        // ---- alpha of the fresh view: rng.choice(grid) (view.py:99, dim.py:181-183)
+        int ai;
+        if (p.aidx) ai = p.aidx[w];
+        else { const uint4 r4 = rng(p.counter, stream_id(4, s, c)); ai = (int)(((uint64_t)r4.x * CC_NGRID) >> 32); }
+        const double alpha = st.row_alpha_grid[ai];
+        // ---- pass 1: sequential CRP-prior seating (crp.py:71-81) -------------------
+        for (int i = lane; i < ntree; i += 32) Lv[0][i] = 0;
+        __syncwarp();
+        int K = 1;              // tables so far
+        int P = 1;              // this lane's inclusive prefix of the counts of tables 0..31 (lane 0: table 0 has row 0)
+        int reg_total = 1, mem_total = 0;
+        if (lane == 0) z[0] = 0;
+        const uint64_t ustream = stream_id(3, s, c);
+        double ucache = 0.0;
+        for (int i = 1; i < R; ++i) {
+            // uniforms in batches of 32 (lane l holds the one for row i0 + l)
+            if (((i - 1) & 31) == 0) {
+                const int ii = i + lane;
+                if (p.u) ucache = (ii < R) ? p.u[(size_t)w * (R - 1) + (ii - 1)] : 0.0;
+                else { const uint4 r4 = rng(p.counter * 0x100000000ull + (uint64_t)ii, ustream); ucache = u01_from_words(r4.x, r4.y); }
+            }
+            const double uu = __shfl_sync(0xffffffffu, ucache, (i - 1) & 31);
+            const double t = uu * ((double)i + alpha);
+            int j;
+            if (t >= (double)i) {
+                // new table (index K)
+                j = K;
+                if (K < 32) { if (lane >= K) P += 1; reg_total += 1; }
+                else {
+                    const int jp = K - 32;
+                    if (lane == 0) {
+                        if (jp == 32) Lv[1][0] = mem_total;
+                        if (jp == 1024) { Lv[2][0] = mem_total; }
+                        if (jp == 32768) { Lv[3][0] = mem_total; }
+                        Lv[0][jp] = 1;
+                        if (jp >= 32) Lv[1][jp >> 5] += 1;
+                        if (jp >= 1024) Lv[2][jp >> 10] += 1;
+                        if (jp >= 32768) Lv[3][jp >> 15] += 1;
+                    }
+                    mem_total += 1;
+                    __syncwarp();
+                }
+                K += 1;
+            } else if (t < (double)reg_total) {
+                const unsigned hit = __ballot_sync(0xffffffffu, (double)P > t);
+                j = __ffs(hit) - 1;
+                if (lane >= j) P += 1;
+                reg_total += 1;
+            } else {
+                double tr = t - (double)reg_total;
+                const int Kp = K - 32;
+                const int top = (Kp <= 32) ? 0 : (Kp <= 1024) ? 1 : (Kp <= 32768) ? 2 : 3;
+                int idx = 0;
+                for (int lev = top; lev >= 0; --lev) {
+                    const int size = (lev == 0) ? Kp : (lev == 1) ? ((Kp + 31) >> 5) : (lev == 2) ? ((Kp + 1023) >> 10) : ((Kp + 32767) >> 15);
+                    const int e = idx * 32 + lane;
+                    const int val = (e < size) ? Lv[lev][e] : 0;
+                    const int inc = warp_incl_scan_i(val, lane);
+                    unsigned hit = __ballot_sync(0xffffffffu, (double)inc > tr);
+                    if (!hit) {             // unreachable in exact arithmetic; fall on the last occupied entry
+                        const unsigned nz = __ballot_sync(0xffffffffu, val > 0);
+                        hit = nz ? (1u << (31 - __clz(nz))) : 1u;
+                    }
+                    const int h = __ffs(hit) - 1;
+                    const int excl = __shfl_sync(0xffffffffu, inc - val, h);
+                    tr -= (double)excl;
+                    if (lane == h) Lv[lev][e] = val + 1;
+                    idx = idx * 32 + h;
+                }
+                __syncwarp();
+                j = idx + 32;
+                mem_total += 1;
+            }
+            if (lane == 0) z[i] = j;
+        }
+        __syncwarp();
+        // ---- pass 2: ordered per-table statistics of column c, marginal ------------
+        // counts -> start offsets
+        {
+            const int pm1 = __shfl_up_sync(0xffffffffu, P, 1);
+            const int myc = (lane == 0) ? P : P - pm1;          // count of table `lane`
+            int carry = 0;
+            for (int b0 = 0; b0 < K; b0 += 32) {
+                const int j = b0 + lane;
+                int cn = 0;
+                if (j < K) cn = (b0 == 0) ? myc : Lv[0][j - 32];
+                const int inc = warp_incl_scan_i(cn, lane);
+                if (j < K) { start[j] = carry + inc - cn; cursor[j] = carry + inc - cn; }
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (lane == 0) start[K] = carry;
+            if (p.write_zr) {
+                int32_t* anke = st.aux_nk + (size_t)s * R;
+                for (int b0 = 0; b0 < K; b0 += 32) {
+                    const int j = b0 + lane;
+                    if (j < K) anke[j] = (b0 == 0) ? myc : Lv[0][j - 32];
+                }
+                if (lane == 0) st.aux_K[s] = K;
+            }
+        }
+        __syncwarp();
+        for (int b0 = 0; b0 < R; b0 += 32) {
+            const int i = b0 + lane;
+            const bool act = i < R;
+            const int k = act ? z[i] : -1;
+            const unsigned peers = __match_any_sync(0xffffffffu, k);
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            int pos = 0;
+            if (act) pos = cursor[k] + rank;
+            __syncwarp();
+            if (act && rank == __popc(peers) - 1) cursor[k] = pos + 1;
+            if (act) grouped[pos] = i;
+            if (act && p.write_zr) st.aux_zr[(size_t)s * R + i] = k;
+            __syncwarp();
+        }
+        const double* hyp = st.hyp + ((size_t)s * st.C + c) * 4;
+        const double h0 = hyp[0], h1 = hyp[1], h2 = hyp[2], h3 = hyp[3];
+        const int ctype = st.ctype[c], kc = st.ncat[c];
+        const double* xc = st.Xcm + (size_t)c * R;
+        double lsum = 0.0;
+        for (int b0 = 0; b0 < K; b0 += 32) {
+            const int j = b0 + lane;
+            if (j >= K) continue;
+            const int beg = start[j], end = start[j + 1];
+            double N = 0.0, sx = 0.0, sxx = 0.0;
+            if (ctype == CC_NORMAL) {
+                int i = beg;
+                for (; i + 4 <= end; i += 4) {
+                    const double x0 = xc[grouped[i]], x1 = xc[grouped[i + 1]], x2 = xc[grouped[i + 2]], x3 = xc[grouped[i + 3]];
+                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                    if (!isnan(x1)) { N += 1.0; sx = __dadd_rn(sx, x1); sxx = __dadd_rn(sxx, __dmul_rn(x1, x1)); }
+                    if (!isnan(x2)) { N += 1.0; sx = __dadd_rn(sx, x2); sxx = __dadd_rn(sxx, __dmul_rn(x2, x2)); }
+                    if (!isnan(x3)) { N += 1.0; sx = __dadd_rn(sx, x3); sxx = __dadd_rn(sxx, __dmul_rn(x3, x3)); }
+                }
+                for (; i < end; ++i) {
+                    const double x0 = xc[grouped[i]];
+                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                }
+                lsum += normal_marginal(N, sx, sxx, h0, h1, h2, h3);
+            } else {
+                uint32_t lc[CC_MAXCAT];
+                for (int q = 0; q < kc; ++q) lc[q] = 0;
+                for (int i = beg; i < end; ++i) {
+                    const double x0 = xc[grouped[i]];
+                    if (!isnan(x0)) { N += 1.0; lc[(int)x0]++; }
+                }
+                const double A = kc * h0;
+                double lg = 0.0;
+                for (int q = 0; q < kc; ++q) lg += lgamma((double)lc[q] + h0);
+                lsum += lgamma(A) - lgamma(A + N) + lg - kc * lgamma(h0);
+            }
+        }
+        lsum = warp_sum(lsum);
+        if (lane == 0) {
+            st.colL[((size_t)s * st.C + c) * (st.Vcap + 1) + st.Vcap] = lsum;
+            st.aux_alpha[(size_t)s * st.C + c] = alpha;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+struct ScanParams {
+    cc_state st;
+    int n_chains;
+    const int32_t* chains;
+    const int32_t* cols;     // [n_chains][ncols]
+    int ncols;
+    int32_t* pos;            // [n_chains] in/out: next list position
+    int32_t* pending;        // [n_chains] out: -1 finished, else the list position that moves to its auxiliary view
+    const double* u;         // [n_chains][ncols] injected uniforms or NULL
+    uint64_t seed, counter;
+    const int32_t* ci_off;   // [C+1] independence constraints (CSR) or NULL
+    const int32_t* ci_adj;
+    double* trace;           // [n_chains][ncols][trace_stride] or NULL
+    int trace_stride;
+};
+
+__global__ void __launch_bounds__(32) scan_kernel(const ScanParams p) {
+    const cc_state& st = p.st;
+    const int w = blockIdx.x, lane = threadIdx.x;
+    const int s = p.chains[w];
+    const int C = st.C, Vcap = st.Vcap;
+    int32_t* zv = st.zv + (size_t)s * C;
+    int32_t* nv = st.nv + (size_t)s * Vcap;
+    int32_t* view_id = st.view_id + (size_t)s * Vcap;
+    extern __shared__ double s_mem[];
+    double* lp = s_mem;                                   // [Vcap+1]
+    int* cand = reinterpret_cast<int*>(lp + Vcap + 1);    // [Vcap+1] view slot per candidate (-1 = aux)
+    const double alpha = st.col_alpha[s];
+    const Philox rng(p.seed);
+    const int32_t* cols = p.cols + (size_t)w * p.ncols;
+    int j = p.pos[w];
+    for (; j < p.ncols; ++j) {
+        const int c = cols[j];
+        const int own = zv[c];
+        const bool singleton = nv[own] == 1;
+        // candidates: live views in ascending view id (crp.py:139), then the auxiliary view
+        int V = 0;
+        for (int v0 = 0; v0 < Vcap; v0 += 32) {
+            const int v = v0 + lane;
+            const bool livev = v < Vcap && nv[v] > 0;
+            if (livev) {
+                int rank = 0;
+                const int myid = view_id[v];
+                for (int q = 0; q < Vcap; ++q) if (nv[q] > 0 && view_id[q] < myid) ++rank;
+                cand[rank] = v;
+            }
+            V += __popc(__ballot_sync(0xffffffffu, livev));
+        }
+        __syncwarp();
+        const int ncand = V + (singleton ? 0 : 1);
+        if (lane == 0 && !singleton) cand[V] = -1;
+        __syncwarp();
+        const double* Lrow = st.colL + ((size_t)s * C + c) * (Vcap + 1);
+        for (int q = lane; q < ncand; q += 32) {
+            const int v = cand[q];
+            double wgt, ld;
+            if (v < 0) { wgt = alpha; ld = Lrow[Vcap]; }
+            else { ld = Lrow[v]; wgt = (v == own) ? (singleton ? alpha : (double)(nv[own] - 1)) : (double)nv[v]; }
+            double val = ld + log(wgt);
+            if (p.ci_off && v >= 0) {
+                for (int e = p.ci_off[c]; e < p.ci_off[c + 1]; ++e)
+                    if (zv[p.ci_adj[e]] == v) val = -INFINITY;              // state.py:1098-1102
+            }
+            lp[q] = val;
+        }
+        __syncwarp();
+        int choice = 0;
+        if (ncand > 1) {
+            double uu;
+            if (p.u) uu = p.u[(size_t)w * p.ncols + j];
+            else { const uint4 r4 = rng(p.counter, stream_id(5, s, c)); uu = u01_from_words(r4.x, r4.y); }
+            double mx = -INFINITY;
+            for (int q = lane; q < ncand; q += 32) mx = fmax(mx, lp[q]);
+            mx = warp_max(mx);
+            double carry = 0.0;
+            for (int b0 = 0; b0 < ncand; b0 += 32) {
+                const int q = b0 + lane;
+                const double e = (q < ncand) ? exp(lp[q] - mx) : 0.0;
+                carry += __shfl_sync(0xffffffffu, warp_incl_scan(e, lane), 31);
+            }
+            const double tot = carry;
+            carry = 0.0;
+            choice = -1;
+            for (int b0 = 0; b0 < ncand && choice < 0; b0 += 32) {
+                const int q = b0 + lane;
+                const double e = (q < ncand) ? exp(lp[q] - mx) : 0.0;
+                const double inc = warp_incl_scan(e, lane) + carry;
+                const unsigned hit = __ballot_sync(0xffffffffu, q < ncand && inc > uu * tot);
+                if (hit) choice = b0 + __ffs(hit) - 1;
+                carry = __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (choice < 0) {                 // NaN / all -inf: stay, flag
+                if (lane == 0) st.err[s] = CC_ERR_ARG;
+                for (int q = 0; q < ncand; ++q) if (cand[q] == own) choice = q;
+            }
+        }
+        const int vnew = cand[choice];
+        if (p.trace && lane == 0) {
+            double* tr = p.trace + ((size_t)w * p.ncols + j) * p.trace_stride;
+            int maxid = -1;
+            for (int q = 0; q < Vcap; ++q) if (nv[q] > 0) maxid = max(maxid, view_id[q]);
+            tr[0] = (double)c; tr[1] = (double)ncand;
+            tr[2] = (double)(vnew < 0 ? maxid + 1 : view_id[vnew]);
+            for (int q = 0; q < ncand && q + 3 < p.trace_stride; ++q) tr[3 + q] = lp[q];
+        }
+        if (vnew < 0) {                       // into the auxiliary view: host installs it
+            if (lane == 0) { p.pending[w] = j; p.pos[w] = j; }
+            return;
+        }
+        if (vnew != own && lane == 0) {       // state.py:1125-1145
+            zv[c] = vnew;
+            nv[vnew] += 1;
+            nv[own] -= 1;
+            if (nv[own] == 0) { view_id[own] = -1; st.nclu[sv_index(st, s, own)] = 0; }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) { p.pending[w] = -1; p.pos[w] = p.ncols; }
+}
+
+// install the auxiliary partition held in aux_zr / aux_nk / aux_K as a new view
+// and move the pending column into it (state.py:1110-1116, 1147-1154)
+__global__ void __launch_bounds__(256) install_kernel(const cc_state st, int n, const int32_t* chains,
+                                                      const int32_t* cols) {
+    const int w = blockIdx.x;
+    if (w >= n) return;
+    const int s = chains[w], c = cols[w];
+    const int R = st.R, C = st.C, Vcap = st.Vcap, Kcap = st.Kcap;
+    int32_t* nv = st.nv + (size_t)s * Vcap;
+    int32_t* view_id = st.view_id + (size_t)s * Vcap;
+    __shared__ int s_slot, s_newid;
+    if (threadIdx.x == 0) {
+        int slot = -1, maxid = -1;
+        for (int v = 0; v < Vcap; ++v) {
+            if (nv[v] > 0) maxid = max(maxid, view_id[v]);
+            else if (slot < 0) slot = v;
+        }
+        if (st.aux_K[s] > Kcap - 1) slot = -1;
+        s_slot = slot;
+        s_newid = maxid + 1;
+        if (slot < 0) st.err[s] = CC_ERR_CAPACITY;
+    }
+    __syncthreads();
+    const int slot = s_slot;
+    if (slot < 0) return;
+    const size_t sv = sv_index(st, s, slot);
+    const int K = st.aux_K[s];
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        st.zr[sv * R + i] = st.aux_zr[(size_t)s * R + i];
+        st.order[sv * R + i] = i;
+    }
+    for (int k = threadIdx.x; k < Kcap; k += blockDim.x) {
+        st.live[sv * Kcap + k] = (k < K) ? k : -1;
+        st.cid[sv * Kcap + k] = (k < K) ? k : 0;
+        st.nk[sv * Kcap + k] = (k < K) ? st.aux_nk[(size_t)s * R + k] : 0;
+    }
+    if (threadIdx.x == 0) {
+        const int own = st.zv[(size_t)s * C + c];
+        st.nclu[sv] = K;
+        st.view_alpha[sv] = st.aux_alpha[(size_t)s * C + c];
+        view_id[slot] = s_newid;
+        nv[slot] = 1;
+        st.zv[(size_t)s * C + c] = slot;
+        nv[own] -= 1;
+        if (nv[own] == 0) { view_id[own] = -1; st.nclu[sv_index(st, s, own)] = 0; }
+    }
+}
+
+template <typename T>
+int to_device(T** out, const T* host, size_t n, cudaStream_t stream) {
+    *out = nullptr;
+    if (n == 0 || !host) return CC_OK;
+    CC_CUDA(cudaMallocAsync(out, sizeof(T) * n, stream));
+    CC_CUDA(cudaMemcpyAsync(*out, host, sizeof(T) * n, cudaMemcpyHostToDevice, stream));
+    return CC_OK;
+}
+
+}  // namespace
+
+extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, const int32_t* cols,
+                          const int32_t* aidx, const double* u_dev, int write_zr, uint64_t seed,
+                          uint64_t counter, void* stream_) {
+    if (!st || n < 0) { cc_set_error("cc_col_aux: bad arguments"); return CC_ERR_ARG; }
+    if (n == 0) return CC_OK;
+    if (st->R > (1 << 20) + 32) { cc_set_error("cc_col_aux: R > 2^20 not supported by the count tree"); return CC_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int R = st->R;
+    const size_t n1 = (R + 31) >> 5, n2 = (n1 + 31) >> 5;
+    size_t per = (size_t)R + (R + n1 + n2 + 32) + (R + 1) + R + R;
+    per = (per + 3) & ~(size_t)3;
+    const size_t avail = (size_t)st->arena_bytes / sizeof(int32_t);
+    if (!st->arena || avail < per) { cc_set_error("cc_col_aux: arena too small (%lld bytes, need %lld per worker)", (long long)st->arena_bytes, (long long)(per * 4)); return CC_ERR_ARG; }
+    int nworkers = (int)(avail / per);
+    if (nworkers > n) nworkers = n;
+    int dev = 0, nsm = 148;
+    CC_CUDA(cudaGetDevice(&dev));
+    CC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    const int wpb = 4;
+    int blocks = (nworkers + wpb - 1) / wpb;
+    if (blocks > nsm * 4) blocks = nsm * 4;
+    if (blocks * wpb > nworkers) blocks = nworkers / wpb > 0 ? nworkers / wpb : 1;
+    int tpb = (blocks == 1 && nworkers < wpb) ? nworkers * 32 : wpb * 32;
+    AuxParams p;
+    p.st = *st; p.n = n; p.aidx = nullptr; p.u = u_dev; p.write_zr = write_zr; p.seed = seed; p.counter = counter;
+    p.arena = (int32_t*)st->arena; p.worker_stride = per;
+    int32_t *dch = nullptr, *dco = nullptr, *dai = nullptr;
+    if (to_device(&dch, chains, n, stream) || to_device(&dco, cols, n, stream) || to_device(&dai, aidx, aidx ? n : 0, stream)) return CC_ERR_CUDA;
+    p.chains = dch; p.cols = dco; p.aidx = dai;
+    aux_kernel<<<blocks, tpb, 0, stream>>>(p);
+    CC_CUDA(cudaGetLastError());
+    cudaFreeAsync(dch, stream); cudaFreeAsync(dco, stream);
+    if (dai) cudaFreeAsync(dai, stream);
+    return CC_OK;
+}
+
+extern "C" int cc_col_marginals(const cc_state* st, int n_work, const int32_t* chains, const int32_t* views,
+                                const int32_t* cols_dev, const int32_t* coloff, const int32_t* colcnt,
+                                int max_cols, void* stream_) {
+    if (!st || n_work < 0) { cc_set_error("cc_col_marginals: bad arguments"); return CC_ERR_ARG; }
+    if (n_work == 0) return CC_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t *dch = nullptr, *dvw = nullptr, *dof = nullptr, *dcn = nullptr;
+    if (to_device(&dch, chains, n_work, stream) || to_device(&dvw, views, n_work, stream)) return CC_ERR_CUDA;
+    if (cols_dev) {
+        if (!coloff || !colcnt) { cc_set_error("cc_col_marginals: column lists need offsets and counts"); return CC_ERR_ARG; }
+        if (to_device(&dof, coloff, n_work, stream) || to_device(&dcn, colcnt, n_work, stream)) return CC_ERR_CUDA;
+    }
+    const int rc = cc_launch_stats(st, n_work, dch, dvw, 1, cols_dev, dof, dcn, max_cols, nullptr, stream);
+    cudaFreeAsync(dch, stream); cudaFreeAsync(dvw, stream);
+    if (dof) cudaFreeAsync(dof, stream);
+    if (dcn) cudaFreeAsync(dcn, stream);
+    return rc;
+}
+
+extern "C" int cc_col_scan(const cc_state* st, int n_chains, const int32_t* chains_dev, const int32_t* cols_dev,
+                           int ncols, int32_t* pos_dev, int32_t* pending_dev, const double* u_dev,
+                           uint64_t seed, uint64_t counter, const int32_t* ci_off_dev, const int32_t* ci_adj_dev,
+                           double* trace_dev, int trace_stride, void* stream_) {
+    if (!st || n_chains < 0 || !chains_dev || !cols_dev || !pos_dev || !pending_dev) { cc_set_error("cc_col_scan: bad arguments"); return CC_ERR_ARG; }
+    if (n_chains == 0) return CC_OK;
+    ScanParams p;
+    p.st = *st; p.n_chains = n_chains; p.chains = chains_dev; p.cols = cols_dev; p.ncols = ncols;
+    p.pos = pos_dev; p.pending = pending_dev; p.u = u_dev; p.seed = seed; p.counter = counter;
+    p.ci_off = ci_off_dev; p.ci_adj = ci_adj_dev; p.trace = trace_dev; p.trace_stride = trace_stride;
+    const size_t smem = (size_t)(st->Vcap + 1) * (sizeof(double) + sizeof(int)) + 16;
+    scan_kernel<<<n_chains, 32, smem, (cudaStream_t)stream_>>>(p);
+    CC_CUDA(cudaGetLastError());
+    return CC_OK;
+}
+
+extern "C" int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols, void* stream_) {
+    if (!st || n < 0) { cc_set_error("cc_col_install: bad arguments"); return CC_ERR_ARG; }
+    if (n == 0) return CC_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int32_t *dch = nullptr, *dco = nullptr;
+    if (to_device(&dch, chains, n, stream) || to_device(&dco, cols, n, stream)) return CC_ERR_CUDA;
+    install_kernel<<<n, 256, 0, stream>>>(*st, n, dch, dco);
+    CC_CUDA(cudaGetLastError());
+    cudaFreeAsync(dch, stream); cudaFreeAsync(dco, stream);
+    return CC_OK;
+}

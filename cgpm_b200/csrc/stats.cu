@@ -77,10 +77,11 @@ struct StatsParams {
     const int32_t* chains;
     const int32_t* views;
     const int32_t* gstart;   // [n_work][Kcap+1]
-    int marginal;            // 0: TABLE mode (the view's own columns), 1: MARGINAL mode (columns `cols`)
-    const int32_t* cols;     // MARGINAL: [n_cols] column list (NULL = all)
-    int n_cols;
-    double* scratch;         // MARGINAL: [n_work][Kcap] x [n_cols] per-cluster marginals
+    int marginal;            // 0: TABLE mode (the view's own columns), 1: MARGINAL mode (listed columns)
+    const int32_t* cols;     // MARGINAL: flat column lists (NULL = all columns for every work item)
+    const int32_t* coloff;   // MARGINAL: [n_work] offset of the work item's list in `cols`
+    const int32_t* colcnt;   // MARGINAL: [n_work] length of the list
+    const uint8_t* mask;     // TABLE: optional [S][C]; only columns with mask != 0 are rebuilt
 };
 
 // grid: (n_work, column tiles of 32).  block: NW warps; warp w owns clusters
@@ -102,12 +103,13 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
         int cnt = 0;
         const int first = blockIdx.y * 32;
         if (p.marginal) {
-            const int total = p.cols ? p.n_cols : C;
-            for (int j = first; j < total && cnt < 32; ++j) s_cols[cnt++] = p.cols ? p.cols[j] : j;
+            const int total = p.cols ? p.colcnt[w] : C;
+            const int32_t* list = p.cols ? p.cols + p.coloff[w] : nullptr;
+            for (int j = first; j < total && cnt < 32; ++j) s_cols[cnt++] = list ? list[j] : j;
         } else {
             int seen = 0;
             for (int c = 0; c < C && cnt < 32; ++c)
-                if (zv[c] == v) { if (seen >= first) s_cols[cnt++] = c; ++seen; }
+                if (zv[c] == v && (!p.mask || p.mask[(size_t)s * C + c])) { if (seen >= first) s_cols[cnt++] = c; ++seen; }
         }
         s_ncols = cnt;
     }
@@ -296,7 +298,8 @@ __global__ void list_views_kernel(const cc_state st, int32_t* chains, int32_t* v
 
 // Host-side launcher shared by cc_rebuild and the column kernel.
 int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, const int32_t* d_views,
-                    int marginal, const int32_t* d_cols, int n_cols, cudaStream_t stream) {
+                    int marginal, const int32_t* d_cols, const int32_t* d_coloff, const int32_t* d_colcnt,
+                    int max_cols, const uint8_t* d_mask, cudaStream_t stream) {
     if (n_work == 0) return CC_OK;
     int32_t* gstart = nullptr;
     CC_CUDA(cudaMallocAsync(&gstart, sizeof(int32_t) * (size_t)n_work * (st->Kcap + 1), stream));
@@ -304,8 +307,8 @@ int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, con
     CC_CUDA(cudaGetLastError());
     StatsParams p;
     p.st = *st; p.n_work = n_work; p.chains = d_chains; p.views = d_views; p.gstart = gstart;
-    p.marginal = marginal; p.cols = d_cols; p.n_cols = n_cols; p.scratch = nullptr;
-    const int maxcols = marginal ? (d_cols ? n_cols : st->C) : st->C;
+    p.marginal = marginal; p.cols = d_cols; p.coloff = d_coloff; p.colcnt = d_colcnt; p.mask = d_mask;
+    const int maxcols = marginal ? (d_cols ? max_cols : st->C) : st->C;
     dim3 grid(n_work, (maxcols + 31) / 32);
     stats_kernel<8><<<grid, 8 * 32, 0, stream>>>(p);
     CC_CUDA(cudaGetLastError());
@@ -314,7 +317,7 @@ int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, con
 }
 
 extern "C" int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains, const int32_t* views,
-                          void* stream_) {
+                          const uint8_t* d_mask, void* stream_) {
     if (!st) { cc_set_error("cc_rebuild: null state"); return CC_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
     int32_t *dch = nullptr, *dvw = nullptr, *dcount = nullptr;
@@ -336,7 +339,7 @@ extern "C" int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains,
         CC_CUDA(cudaMemcpyAsync(dch, chains, sizeof(int32_t) * n_work, cudaMemcpyHostToDevice, stream));
         CC_CUDA(cudaMemcpyAsync(dvw, views, sizeof(int32_t) * n_work, cudaMemcpyHostToDevice, stream));
     }
-    rc = cc_launch_stats(st, n_work, dch, dvw, 0, nullptr, 0, stream);
+    rc = cc_launch_stats(st, n_work, dch, dvw, 0, nullptr, nullptr, nullptr, 0, d_mask, stream);
     if (dch) cudaFreeAsync(dch, stream);
     if (dvw) cudaFreeAsync(dvw, stream);
     if (dcount) cudaFreeAsync(dcount, stream);

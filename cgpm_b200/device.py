@@ -117,6 +117,8 @@ class DeviceChains(object):
         t['movedflag'] = z((S_, V, R), torch.uint8)
         t['colL'] = z((S_, Cn, V + 1), f64)
         t['aux_zr'] = z((S_, R), i32)
+        t['aux_nk'] = z((S_, R), i32)
+        t['aux_K'] = z((S_,), i32)
         t['aux_alpha'] = z((S_, Cn), f64)
         self.t = t
         self.arena = None
@@ -126,7 +128,7 @@ class DeviceChains(object):
         for name in ('Xrm', 'Xcm', 'ctype', 'ncat', 'catoff', 'grids', 'row_alpha_grid',
                      'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha',
                      'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'seq',
-                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_alpha'):
+                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_nk', 'aux_K', 'aux_alpha'):
             setattr(st, name, t[name].data_ptr())
         st.arena = None
         st.arena_bytes = 0
@@ -210,18 +212,19 @@ class DeviceChains(object):
         return out
 
     # ------------------------------------------------------------------ kernels
-    def rebuild(self, pairs=None):
-        """Recompute tables for (chain, view slot) pairs (None = everything)."""
+    def rebuild(self, pairs=None, mask=None):
+        """Recompute tables for (chain, view slot) pairs (None = everything);
+        mask: optional uint8 device tensor [S][C] restricting the columns."""
+        mp = C.c_void_p(mask.data_ptr()) if mask is not None else None
         if pairs is None:
-            rc = self.lib.cc_rebuild(C.byref(self.st), 0, None, None, self.stream_ptr())
+            rc = self.lib.cc_rebuild(C.byref(self.st), 0, None, None, mp, self.stream_ptr())
         else:
             if len(pairs) == 0:
                 return
             ch = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int32)
             vw = np.ascontiguousarray([p[1] for p in pairs], dtype=np.int32)
             rc = self.lib.cc_rebuild(C.byref(self.st), len(pairs), ch.ctypes.data_as(C.c_void_p),
-                                     vw.ctypes.data_as(C.c_void_p), self.stream_ptr())
-            self.sync()            # host work lists must outlive the async copy
+                                     vw.ctypes.data_as(C.c_void_p), mp, self.stream_ptr())
         L.check(rc, 'cc_rebuild')
 
     def logpdf_score(self):

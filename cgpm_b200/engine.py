@@ -1,0 +1,506 @@
+"""`Engine` and `State`: the reference's public API for the CrossCat path, GPU-backed.
+
+Mirrors cgpm.crosscat.engine.Engine (src/crosscat/engine.py:61-435) and
+cgpm.crosscat.state.State (src/crosscat/state.py:44-1284) for the inference hot
+path: construction ("initialize"), transition(N, S, kernels, rowids, cols,
+views, progress, checkpoint, statenos), logpdf_score, dependence probability,
+logpdf / simulate (bulk), and the metadata / pickle round trip ("serialize").
+Same names, argument meaning and error behaviour; only `normal` and
+`categorical` columns are accepted (the rule lovecat applies, state.py:817-822).
+The reference's process fan-out (utils/parallel_map.py) is replaced by one CUDA
+launch over all chains; `multiprocess` is accepted and ignored.
+
+Extra keyword arguments (not in the reference): stream ('philox' | 'numpy',
+see core.py), device, Vcap, Kcap.
+"""
+from __future__ import annotations
+
+import pickle
+from collections import OrderedDict
+
+import numpy as np
+
+from . import _lib as L
+from . import codec
+from . import hostmath as hm
+from .core import Chains, KERNELS
+
+STATE_KW = ('outputs', 'inputs', 'cctypes', 'distargs', 'Zv', 'Zrv', 'alpha', 'view_alphas',
+            'hypers', 'Cd', 'Ci', 'Rd', 'Ri', 'diagnostics', 'loom_path')
+OPT_KW = ('stream', 'device', 'Vcap', 'Kcap')
+
+
+def gen_rng(seed=None):
+    """src/utils/general.py:37-40."""
+    if seed is None:
+        seed = np.random.randint(low=1, high=2 ** 31)
+    return np.random.RandomState(seed)
+
+
+def _check_state_kwargs(kw):
+    if kw.get('inputs'):
+        raise ValueError('State does not accept inputs.')
+    if kw.get('Rd') is not None:
+        raise ValueError('Row dependence constraints not implemented.')
+    if kw.get('Ri') is not None:
+        raise ValueError('Row independence constraints not implemented.')
+    unknown = [k for k in kw if k not in STATE_KW]
+    if unknown:
+        raise TypeError('unexpected keyword arguments: %s' % (unknown,))
+
+
+def _chain_metadata(ch, s, X_list=None):
+    """State.to_metadata (src/crosscat/state.py:1189-1240) for chain s."""
+    spec, dl = ch.chain_spec(s, with_stats=True)
+    md = dict()
+    if X_list is not None:
+        md['X'] = X_list
+    md['outputs'] = list(ch.outputs)
+    md['alpha'] = float(spec['alpha'])
+    md['Zv'] = [(ch.outputs[i], int(v)) for i, v in enumerate(spec['Zv'])]
+    md['cctypes'] = list(ch.cctypes)
+    hyp = spec['hyp']
+    md['hypers'] = []
+    for i in range(ch.C):
+        canon = codec.HYPER_NAMES[int(ch.ctype[i])]
+        md['hypers'].append(OrderedDict((n, float(hyp[i, canon.index(n)])) for n in ch.hyper_order[s][i]))
+    md['distargs'] = [dict(d) for d in ch.distargs]
+    # suffstats: list per column of (cluster id, stats) + the empty aux model at max+1 (dim.py:212-217)
+    md['suffstats'] = []
+    view_of_col = {i: v for i, v in enumerate(spec['Zv'])}
+    for i in range(ch.C):
+        vw = spec['views'][view_of_col[i]]
+        items = []
+        for pos, k in enumerate(vw['live']):
+            cid = int(vw['cid'][pos])
+            N = float(dl['stat'][L.F_N, k, i])
+            if ch.ctype[i] == L.NORMAL:
+                items.append((cid, {'N': N, 'sum_x': float(dl['stat'][L.F_SX, k, i]),
+                                    'sum_x_sq': float(dl['stat'][L.F_SXX, k, i])}))
+            else:
+                o0 = ch.dev.catoff_h[i]
+                items.append((cid, {'N': int(N), 'counts': [float(x) for x in dl['cnt'][k, o0:o0 + ch.ncat[i]]]}))
+        top = max(int(c) for c in vw['cid']) + 1
+        if ch.ctype[i] == L.NORMAL:
+            items.append((top, {'N': 0, 'sum_x': 0, 'sum_x_sq': 0}))
+        else:
+            items.append((top, {'N': 0, 'counts': [0.0] * int(ch.ncat[i])}))
+        md['suffstats'].append(items)
+    md['Cd'] = ch.Cd
+    md['Ci'] = ch.Ci
+    md['Zrv'] = [(int(v), [int(z) for z in vw['Zr']]) for v, vw in spec['views'].items()]
+    md['view_alphas'] = [(int(v), float(vw['alpha'])) for v, vw in spec['views'].items()]
+    md['diagnostics'] = ch.diagnostics[s]
+    md['hooked_cgpms'] = dict()
+    md['loom_path'] = None
+    md['factory'] = ('cgpm.crosscat.state', 'State')
+    return md
+
+
+class _ViewInfo(object):
+    """Read-only stand-in for cgpm.mixtures.view.View (Zr / Nk / alpha / dims)."""
+
+    def __init__(self, vid, vw, cols):
+        self.vid = vid
+        self._zr = vw['Zr']
+        self._alpha = vw['alpha']
+        self._order = vw['order']
+        self.dims = OrderedDict((c, None) for c in cols)
+        self.outputs = [10 ** 7 + vid] + list(cols)
+
+    def Zr(self, rowid=None):
+        if rowid is not None:
+            return int(self._zr[rowid])
+        return OrderedDict((int(r), int(self._zr[r])) for r in self._order)
+
+    def Nk(self, k=None):
+        ids, counts = np.unique(self._zr, return_counts=True)
+        d = OrderedDict((int(i), int(c)) for i, c in zip(ids, counts))
+        return d[k] if k is not None else d
+
+    def alpha(self):
+        return self._alpha
+
+
+class _Api(object):
+    """Behaviour shared by Engine (S chains) and State (1 chain)."""
+
+    _ch = None
+
+    # ---- per-chain accessors -------------------------------------------------
+    def _Zv(self, s):
+        return OrderedDict(self._ch.Zv_items(s))
+
+    def _views(self, s):
+        spec, _ = self._ch.chain_spec(s)
+        out = OrderedDict()
+        for vid, vw in spec['views'].items():
+            cols = [self._ch.outputs[i] for i, v in enumerate(spec['Zv']) if v == vid]
+            out[vid] = _ViewInfo(vid, vw, cols)
+        return out
+
+    def _dependence_probability(self, s, col0, col1):
+        zv = self._Zv(s)
+        if col0 not in zv or col1 not in zv:
+            raise ValueError('Unknown columns: %s, %s' % (col0, col1))
+        return float(zv[col0] == zv[col1])
+
+    def _dependence_probability_pairwise(self, s, colnos=None):
+        """state.py:546-554."""
+        if colnos is None:
+            colnos = self._ch.outputs
+        zv = self._Zv(s)
+        z = np.array([zv[c] for c in colnos])
+        return (z[:, None] == z[None, :]).astype(float)
+
+
+class State(_Api):
+    """cgpm.crosscat.state.State for one chain (src/crosscat/state.py:44-1284)."""
+
+    def __init__(self, X, outputs=None, inputs=None, cctypes=None, distargs=None, Zv=None, Zrv=None,
+                 alpha=None, view_alphas=None, hypers=None, Cd=None, Ci=None, Rd=None, Ri=None,
+                 diagnostics=None, loom_path=None, rng=None, **opts):
+        _check_state_kwargs(dict(inputs=inputs, Rd=Rd, Ri=Ri))
+        bad = [k for k in opts if k not in OPT_KW]
+        if bad:
+            raise TypeError('unexpected keyword arguments: %s' % (bad,))
+        self.rng = gen_rng() if rng is None else rng
+        X = np.asarray(X)
+        opts.setdefault('stream', 'numpy')
+        self._ch = Chains(X, outputs=outputs, cctypes=cctypes, distargs=distargs, Cd=Cd, Ci=Ci, S=1,
+                          seed=int(self.rng.get_state()[1][0]), **opts)
+        self._ch.init_chain(0, self.rng, Zv=Zv, Zrv=Zrv, alpha=alpha, view_alphas=view_alphas,
+                            hypers=hypers, diagnostics=diagnostics)
+        self._ch.finish_init()
+        self.outputs = list(self._ch.outputs)
+        self.inputs = []
+        self.Cd, self.Ci = self._ch.Cd, self._ch.Ci
+
+    # ---- structure ---------------------------------------------------------------
+    @property
+    def diagnostics(self):
+        return self._ch.diagnostics[0]
+
+    @property
+    def views(self):
+        return self._views(0)
+
+    def n_rows(self):
+        return self._ch.R
+
+    def n_cols(self):
+        return self._ch.C
+
+    def cctypes(self):
+        return list(self._ch.cctypes)
+
+    def distargs(self):
+        return [dict(d) for d in self._ch.distargs]
+
+    def data_array(self):
+        return self._ch.dev.X_h.copy()
+
+    def alpha(self):
+        return float(self._ch.dev.t['col_alpha'][0].item())
+
+    def Zv(self, col=None):
+        zv = self._Zv(0)
+        return zv[col] if col is not None else zv
+
+    def Nv(self, v=None):
+        zv = self._Zv(0)
+        out = OrderedDict()
+        for c, w in zv.items():
+            out[w] = out.get(w, 0) + 1
+        return out[v] if v is not None else out
+
+    def Zrv(self):
+        return OrderedDict((vid, [vw.Zr(i) for i in range(self.n_rows())]) for vid, vw in self.views.items())
+
+    def hypers(self):
+        return _chain_metadata(self._ch, 0)['hypers']
+
+    def is_composite(self):
+        return False
+
+    def hypothetical(self, rowid):
+        return rowid is None or not 0 <= rowid < self.n_rows()
+
+    # ---- inference -------------------------------------------------------------
+    def transition(self, N=None, S=None, kernels=None, rowids=None, cols=None, views=None,
+                   progress=True, checkpoint=None):
+        self._ch.transition(N=N, S=S, kernels=kernels, rowids=rowids, cols=cols, views=views,
+                            progress=progress, checkpoint=checkpoint, chains=[0])
+
+    def transition_crp_alpha(self):
+        self._ch.transition_crp_alpha([0])
+
+    def transition_view_alphas(self, views=None, cols=None):
+        self._ch.transition_view_alphas([0], views=views, cols=cols)
+
+    def transition_dim_hypers(self, cols=None):
+        self._ch.transition_dim_hypers([0], cols=cols)
+
+    def transition_view_rows(self, views=None, rows=None, cols=None):
+        self._ch.transition_view_rows([0], views=views, cols=cols, rows=rows)
+
+    def transition_dims(self, cols=None):
+        self._ch.transition_dims([0], cols=cols)
+        self._ch.dev.sync()
+        self._ch.dev.check_errors()
+
+    # ---- queries -----------------------------------------------------------------
+    def logpdf_score(self):
+        return float(self._ch.logpdf_score()[0])
+
+    def dependence_probability(self, col0, col1):
+        return self._dependence_probability(0, col0, col1)
+
+    def dependence_probability_pairwise(self, colnos=None):
+        return self._dependence_probability_pairwise(0, colnos)
+
+    def logpdf(self, rowid, targets, constraints=None, inputs=None, accuracy=None):
+        return self._ch.logpdf_bulk([0], [rowid], [targets], [constraints or {}])[0][0]
+
+    def logpdf_bulk(self, rowids, targets_list, constraints_list=None, inputs_list=None):
+        return self._ch.logpdf_bulk([0], rowids, targets_list, constraints_list)[0]
+
+    def simulate(self, rowid, targets, constraints=None, inputs=None, N=None, accuracy=None):
+        out = self._ch.simulate_bulk([0], [rowid], [targets], [constraints or {}], [N if N is not None else 1])[0][0]
+        return out if N is not None else out[0]
+
+    def simulate_bulk(self, rowids, targets_list, constraints_list=None, inputs_list=None, Ns=None):
+        return self._ch.simulate_bulk([0], rowids, targets_list, constraints_list, Ns)[0]
+
+    # ---- serialise ---------------------------------------------------------------
+    def to_metadata(self):
+        return _chain_metadata(self._ch, 0, X_list=self._ch.dev.X_h.tolist())
+
+    def to_pickle(self, fileptr):
+        pickle.dump(self.to_metadata(), fileptr)
+
+    @classmethod
+    def from_metadata(cls, metadata, rng=None, **opts):
+        """state.py:1246-1267: suffstats are ignored and rebuilt from X, Zv, Zrv."""
+        if rng is None:
+            rng = gen_rng(0)
+        if metadata.get('hooked_cgpms'):
+            raise ValueError('cgpm_b200: composite states (hooked cgpms) are out of scope.')
+        to_dict = lambda val: None if val is None else OrderedDict(val)
+        return cls(
+            np.asarray(metadata['X']), outputs=metadata.get('outputs'), cctypes=metadata.get('cctypes'),
+            distargs=metadata.get('distargs'), alpha=metadata.get('alpha'), Zv=to_dict(metadata.get('Zv')),
+            Zrv=to_dict(metadata.get('Zrv')), view_alphas=to_dict(metadata.get('view_alphas')),
+            hypers=metadata.get('hypers'), Cd=metadata.get('Cd'), Ci=metadata.get('Ci'),
+            diagnostics=metadata.get('diagnostics'), loom_path=metadata.get('loom_path'), rng=rng, **opts)
+
+    @classmethod
+    def from_pickle(cls, fileptr, rng=None, **opts):
+        if isinstance(fileptr, str):
+            with open(fileptr, 'rb') as f:
+                metadata = pickle.load(f)
+        else:
+            metadata = pickle.load(fileptr)
+        return cls.from_metadata(metadata, rng=rng, **opts)
+
+
+class Engine(_Api):
+    """cgpm.crosscat.engine.Engine (src/crosscat/engine.py:61-435)."""
+
+    def __init__(self, X, num_states=1, rng=None, multiprocess=1, **kwargs):
+        self.rng = gen_rng(1) if rng is None else rng
+        self._opts = {k: kwargs.pop(k) for k in OPT_KW if k in kwargs}
+        self._opts.setdefault('stream', 'philox')
+        _check_state_kwargs(kwargs)
+        self.X = np.asarray(X, dtype=float)
+        self._state_kwargs = kwargs
+        seeds = self._get_seeds(num_states)
+        self._make_chains(num_states, seeds[0] if num_states else 0)
+        for s, seed in enumerate(seeds):                       # engine.py:36-38
+            self._init_from_kwargs(s, gen_rng(seed), kwargs)
+        if num_states:
+            self._ch.finish_init()
+
+    def _make_chains(self, S, seed):
+        kw = self._state_kwargs
+        self._ch = Chains(self.X, outputs=kw.get('outputs'), cctypes=kw.get('cctypes'), distargs=kw.get('distargs'),
+                          Cd=kw.get('Cd'), Ci=kw.get('Ci'), S=S, seed=int(seed), **self._opts)
+
+    def _init_from_kwargs(self, s, rng, kw):
+        self._ch.init_chain(s, rng, Zv=kw.get('Zv'), Zrv=kw.get('Zrv'), alpha=kw.get('alpha'),
+                            view_alphas=kw.get('view_alphas'), hypers=kw.get('hypers'),
+                            diagnostics=kw.get('diagnostics'))
+
+    # ---- inference -------------------------------------------------------------
+    def transition(self, N=None, S=None, kernels=None, rowids=None, cols=None, views=None,
+                   progress=True, checkpoint=None, statenos=None, multiprocess=1):
+        statenos = list(statenos) if statenos else list(range(self.num_states()))
+        self._ch.transition(N=N, S=S, kernels=kernels, rowids=rowids, cols=cols, views=views,
+                            progress=progress, checkpoint=checkpoint, chains=statenos)
+
+    # ---- queries -----------------------------------------------------------------
+    def logpdf_score(self, statenos=None, multiprocess=1):
+        statenos = statenos or range(self.num_states())
+        scores = self._ch.logpdf_score()
+        return [float(scores[s]) for s in statenos]
+
+    def logpdf(self, rowid, targets, constraints=None, inputs=None, accuracy=None, statenos=None,
+               multiprocess=1):
+        statenos = list(statenos or range(self.num_states()))
+        out = self._ch.logpdf_bulk(statenos, [rowid], [targets], [constraints or {}])
+        return [o[0] for o in out]
+
+    def logpdf_bulk(self, rowids, targets_list, constraints_list=None, inputs_list=None, statenos=None,
+                    multiprocess=1):
+        statenos = list(statenos or range(self.num_states()))
+        return self._ch.logpdf_bulk(statenos, rowids, targets_list, constraints_list)
+
+    def simulate(self, rowid, targets, constraints=None, inputs=None, N=None, accuracy=None,
+                 statenos=None, multiprocess=1):
+        self._seed_states()
+        statenos = list(statenos or range(self.num_states()))
+        out = self._ch.simulate_bulk(statenos, [rowid], [targets], [constraints or {}], [N if N is not None else 1])
+        return [o[0] if N is not None else o[0][0] for o in out]
+
+    def simulate_bulk(self, rowids, targets_list, constraints_list=None, inputs_list=None, Ns=None,
+                      statenos=None, multiprocess=1):
+        self._seed_states()
+        statenos = list(statenos or range(self.num_states()))
+        return self._ch.simulate_bulk(statenos, rowids, targets_list, constraints_list, Ns)
+
+    def dependence_probability(self, col0, col1, statenos=None, multiprocess=1):
+        statenos = statenos or range(self.num_states())
+        return [self._dependence_probability(s, col0, col1) for s in statenos]
+
+    def dependence_probability_pairwise(self, colnos=None, statenos=None, multiprocess=1):
+        statenos = statenos or range(self.num_states())
+        return [self._dependence_probability_pairwise(s, colnos) for s in statenos]
+
+    def _likelihood_weighted_integrate(self, logpdfs, rowid, constraints=None, inputs=None, statenos=None,
+                                       multiprocess=1):
+        """engine.py:361-371."""
+        if constraints:
+            weights = self.logpdf(rowid, constraints, inputs, statenos=statenos)
+            return hm.logmeanexp_weighted(logpdfs, weights)
+        return hm.logmeanexp(logpdfs)
+
+    # ---- states ------------------------------------------------------------------
+    def num_states(self):
+        return self._ch.S if self._ch is not None else 0
+
+    def get_state(self, index):
+        md = _chain_metadata(self._ch, index, X_list=self.X.tolist())
+        st = State.from_metadata(md, rng=self._ch.rngs[index], **self._opts_for_state())
+        return st
+
+    def _opts_for_state(self):
+        o = dict(self._opts)
+        return o
+
+    @property
+    def states(self):
+        return [self.get_state(i) for i in range(self.num_states())]
+
+    def _all_metadata(self):
+        return [_chain_metadata(self._ch, s) for s in range(self.num_states())]
+
+    def _reload(self, mds, rngs):
+        kw = self._state_kwargs
+        if mds:
+            kw = dict(kw, outputs=mds[0]['outputs'], cctypes=mds[0]['cctypes'], distargs=mds[0]['distargs'],
+                      Cd=mds[0].get('Cd'), Ci=mds[0].get('Ci'))
+            self._state_kwargs = {k: v for k, v in kw.items() if k in ('outputs', 'cctypes', 'distargs', 'Cd', 'Ci')}
+        self._make_chains(len(mds), self._ch.seed if self._ch is not None else 0)
+        for s, (md, rng) in enumerate(zip(mds, rngs)):
+            self._ch.init_chain(s, rng, Zv=OrderedDict(md['Zv']), Zrv=OrderedDict(md['Zrv']), alpha=md['alpha'],
+                                view_alphas=OrderedDict(md['view_alphas']), hypers=md['hypers'],
+                                diagnostics=md.get('diagnostics'))
+        if mds:
+            self._ch.finish_init()
+
+    def drop_state(self, index):
+        mds, rngs = self._all_metadata(), list(self._ch.rngs)
+        del mds[index]
+        del rngs[index]
+        self._reload(mds, rngs)
+
+    def add_state(self, count=1, multiprocess=1, **kwargs):
+        """engine.py:331-346."""
+        forbidden = ['X', 'outputs', 'cctypes', 'distargs']
+        if [f for f in forbidden if f in kwargs]:
+            raise ValueError('Cannot specify arguments for: %s.' % (forbidden,))
+        _check_state_kwargs(kwargs)
+        mds, rngs = self._all_metadata(), list(self._ch.rngs)
+        old = len(mds)
+        seeds = self._get_seeds(count)
+        tmp_kw = dict(self._state_kwargs)
+        self._state_kwargs = dict(outputs=self._ch.outputs, cctypes=self._ch.cctypes, distargs=self._ch.distargs,
+                                  Cd=kwargs.get('Cd', self._ch.Cd), Ci=kwargs.get('Ci', self._ch.Ci))
+        self._make_chains(old + count, self._ch.seed)
+        for s, (md, rng) in enumerate(zip(mds, rngs)):
+            self._ch.init_chain(s, rng, Zv=OrderedDict(md['Zv']), Zrv=OrderedDict(md['Zrv']), alpha=md['alpha'],
+                                view_alphas=OrderedDict(md['view_alphas']), hypers=md['hypers'],
+                                diagnostics=md.get('diagnostics'))
+        for j, seed in enumerate(seeds):
+            self._init_from_kwargs(old + j, gen_rng(seed), kwargs)
+        self._ch.finish_init()
+        del tmp_kw
+
+    # ---- internal ------------------------------------------------------------------
+    def _seed_states(self):
+        """engine.py:352-355."""
+        seeds = self._get_seeds()
+        for seed, rng in zip(seeds, self._ch.rngs):
+            rng.seed(seed)
+
+    def _get_seeds(self, N=None):
+        """engine.py:357-359."""
+        num_draws = N if N is not None else self.num_states()
+        return self.rng.randint(low=1, high=2 ** 32 - 1, size=num_draws)
+
+    # ---- serialise -------------------------------------------------------------------
+    def to_metadata(self):
+        """engine.py:394-401."""
+        return {'X': self.X.tolist(), 'states': self._all_metadata(),
+                'factory': ('cgpm.crosscat.engine', 'Engine')}
+
+    @classmethod
+    def from_metadata(cls, metadata, rng=None, multiprocess=1, **opts):
+        """engine.py:403-424."""
+        if rng is None:
+            rng = gen_rng(0)
+        states = metadata['states']
+        if any(m.get('hooked_cgpms') for m in states):
+            raise ValueError('cgpm_b200: composite states (hooked cgpms) are out of scope.')
+        eng = cls.__new__(cls)
+        eng.rng = rng
+        eng._opts = {k: opts[k] for k in OPT_KW if k in opts}
+        eng._opts.setdefault('stream', 'philox')
+        eng.X = np.asarray(metadata['X'], dtype=float)
+        eng._state_kwargs = {}
+        eng._ch = None
+        seeds = eng.rng.randint(low=1, high=2 ** 32 - 1, size=len(states))
+        eng._ch = None
+        if states:
+            eng._state_kwargs = dict(outputs=states[0]['outputs'], cctypes=states[0]['cctypes'],
+                                     distargs=states[0]['distargs'], Cd=states[0].get('Cd'), Ci=states[0].get('Ci'))
+        eng._make_chains(len(states), seeds[0] if len(states) else 0)
+        for s, (md, seed) in enumerate(zip(states, seeds)):
+            eng._ch.init_chain(s, gen_rng(seed), Zv=OrderedDict(md['Zv']), Zrv=OrderedDict(md['Zrv']),
+                               alpha=md['alpha'], view_alphas=OrderedDict(md['view_alphas']),
+                               hypers=md['hypers'], diagnostics=md.get('diagnostics'))
+        if states:
+            eng._ch.finish_init()
+        return eng
+
+    def to_pickle(self, fileptr):
+        pickle.dump(self.to_metadata(), fileptr)
+
+    @classmethod
+    def from_pickle(cls, fileptr, rng=None, **opts):
+        if isinstance(fileptr, str):
+            with open(fileptr, 'rb') as f:
+                metadata = pickle.load(f)
+        else:
+            metadata = pickle.load(fileptr)
+        return cls.from_metadata(metadata, rng=rng, **opts)

@@ -84,6 +84,8 @@ typedef struct cc_state {
     uint8_t* movedflag;  /* [S][Vcap][R]                                          */
     double*  colL;       /* [S][C][Vcap+1] column marginal matrix (last = auxiliary view) */
     int32_t* aux_zr;     /* [S][R]   auxiliary-view partition (one column step)   */
+    int32_t* aux_nk;     /* [S][R]   table sizes of that partition                */
+    int32_t* aux_K;      /* [S]      number of tables                             */
     double*  aux_alpha;  /* [S][C]   alpha drawn for each column's auxiliary view */
     void*    arena;      /* per-worker scratch for the auxiliary CRP simulation   */
     int64_t  arena_bytes;
@@ -107,9 +109,12 @@ int cc_abi_version(void);
 /* Recompute every cached field of `stat` and the counts from (X, zr, order,
  * hyp) for the listed (chain, view slot) pairs, summing each cluster in the
  * view's member order -- the device form of View._bulk_incorporate
- * (src/mixtures/view.py:483-494).  views == NULL: all live views of all chains. */
-int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains,
-               const int32_t* views, void* stream);
+ * (src/mixtures/view.py:483-494).  views == NULL: all live views of all chains
+ * (synchronises the stream once to size the launch). */
+int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains /*host*/,
+               const int32_t* views /*host*/, const uint8_t* mask /*device [S][C] or NULL:
+               rebuild only these columns, state.py:1117-1121 re-incorporates only the
+               visited column*/, void* stream);
 
 /* State.logpdf_score (src/crosscat/state.py:384-387): column-CRP marginal +
  * per view [row-CRP marginal + sum of cluster marginals].  out: device [S]. */
@@ -122,6 +127,62 @@ int cc_transition_rows(const cc_state* st, int n_work, const cc_row_work* work /
                        const int32_t* perm, const double* u, double* trace,
                        int trace_stride, uint64_t seed, uint64_t counter,
                        void* stream);
+
+/* ---- State.transition_dims (src/crosscat/state.py:804-810,1050-1154) --------
+ * The column sweep is exposed as its four stages; the host runs
+ *   cc_col_aux -> cc_col_marginals -> { cc_col_scan -> [cc_col_aux(write_zr) ->
+ *   cc_col_install -> cc_col_marginals(new view)] }* -> cc_rebuild(mask)
+ * (cgpm_b200/core.py: transition_columns).  Arguments named *_dev are device
+ * pointers; the others are host arrays copied on `stream`. */
+
+/* Auxiliary view of each listed (chain, column): alpha = row_alpha_grid[aidx]
+ * (view.py:99; aidx == NULL: device generator), CRP-prior partition of all rows
+ * (view.py:100-103, crp.py:71-81; uniforms u_dev[n][R-1] or device generator),
+ * the column's marginal under it -> colL[chain][col][Vcap], aux_alpha.  With
+ * write_zr the partition is kept in aux_zr/aux_nk/aux_K of the chain (one
+ * column per chain per call).  Needs st->arena. */
+int cc_col_aux(const cc_state* st, int n, const int32_t* chains, const int32_t* cols,
+               const int32_t* aidx, const double* u_dev, int write_zr, uint64_t seed,
+               uint64_t counter, void* stream);
+
+/* Marginal likelihood of columns under existing views (state.py:1065-1072 ->
+ * view.py:483-494 -> dim.py:121-122): for work item i, every column of its list
+ * cols_dev[coloff[i] .. coloff[i]+colcnt[i]) (cols_dev == NULL: all columns)
+ * under view views[i] of chain chains[i] -> colL[chain][col][view]. */
+int cc_col_marginals(const cc_state* st, int n_work, const int32_t* chains, const int32_t* views,
+                     const int32_t* cols_dev, const int32_t* coloff, const int32_t* colcnt,
+                     int max_cols, void* stream);
+
+/* The sequential scan (state.py:1087-1121): for chain chains_dev[i], columns
+ * cols_dev[i][pos_dev[i] .. ncols) in order.  A move into the auxiliary view
+ * stops the chain: pending_dev[i] = list position (else -1 when finished).
+ * u_dev[n_chains][ncols]: injected uniforms, or NULL for the device generator.
+ * ci_off/ci_adj: CSR of the independence constraints Ci (state.py:1098-1102). */
+int cc_col_scan(const cc_state* st, int n_chains, const int32_t* chains_dev, const int32_t* cols_dev,
+                int ncols, int32_t* pos_dev, int32_t* pending_dev, const double* u_dev,
+                uint64_t seed, uint64_t counter, const int32_t* ci_off_dev, const int32_t* ci_adj_dev,
+                double* trace_dev, int trace_stride, void* stream);
+
+/* Install aux_zr/aux_nk/aux_K of each listed chain as a new view and move the
+ * column into it (state.py:1110-1116,1125-1154). */
+int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols, void* stream);
+
+/* ---- grid Gibbs on hyperparameters (src/mixtures/dim.py:152-174) ------------ */
+
+/* 'column_hypers' (state.py:781-786) for each listed (chain, column).  hord[n][4]:
+ * hyper indices (0..3 = m,r,s,nu | 0 = alpha) in visiting order, -1 padded --
+ * the host's rng.shuffle of the names (dim.py:154-155) -- or NULL for a device
+ * shuffle; u[n][4]: one uniform per visited hyper, or NULL.  Host arrays. */
+int cc_transition_col_hypers(const cc_state* st, int n, const int32_t* chains, const int32_t* cols,
+                             const int32_t* hord, const double* u, uint64_t seed, uint64_t counter,
+                             void* stream);
+
+/* 'alpha' (views == NULL, ndraw = 1; state.py:763-765) and 'view_alphas'
+ * (views[n], ndraw = 2; state.py:767-772, view.py:231-233).  u[n][ndraw] host
+ * uniforms or NULL.  The grid scores do not depend on the current alpha, so the
+ * value kept is the one selected by the last uniform. */
+int cc_transition_alphas(const cc_state* st, int n, const int32_t* chains, const int32_t* views,
+                         const double* u, int ndraw, uint64_t seed, uint64_t counter, void* stream);
 
 #ifdef __cplusplus
 }
