@@ -85,6 +85,7 @@ class Chains(object):
         self.counter = 1
         self._ci_dev = None
         self._mirror = None
+        self.events = None          # bench instrumentation: list of (kernel name, start event, end event)
         if self.Ci:
             self._build_ci()
 
@@ -218,7 +219,7 @@ class Chains(object):
             'rows': lambda: self.transition_view_rows(chains, views=views, cols=cols, rows=rowids),
             'columns': lambda: self.transition_dims(chains, cols=cols),
         }
-        funcs = [table[k] for k in kernels]
+        funcs = [self._timed(k, table[k]) for k in kernels]
         if N is None and S is None:
             N = 1
         if progress is None:
@@ -249,6 +250,18 @@ class Chains(object):
         if progress:
             print('\rCompleted: %d iterations in %f seconds.' % (iters, time.time() - start))
         return iters
+
+    def _timed(self, name, f):
+        def run():
+            if self.events is None:
+                return f()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            self.events.append((name, e0, e1))
+        return run
 
     @staticmethod
     def _progress(p):
@@ -553,3 +566,45 @@ class Chains(object):
     def simulate_bulk(self, chains, rowids, targets_list, constraints_list=None, Ns=None):
         from . import query
         return query.simulate_bulk(self, chains, rowids, targets_list, constraints_list, Ns)
+
+    # ------------------------------------------------- dense host <-> device state
+    SMALL = ('hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha', 'nclu', 'live', 'cid', 'nk')
+
+    def export_dense(self, pinned=None):
+        """Device -> host copy of the chain state in dense slot form (the
+        write-back half of the lovecat-style bridge, lovecat.py:226-290).
+        Returns pinned CPU tensors; zr/order only for live (chain, view) slots."""
+        t = self.dev.t
+        out = pinned if pinned is not None else {}
+        for k in self.SMALL:
+            if k not in out:
+                out[k] = torch.empty(t[k].shape, dtype=t[k].dtype).pin_memory()
+            out[k].copy_(t[k], non_blocking=True)
+        self.dev.sync()
+        live = torch.nonzero(out['nv'] > 0)
+        idx = (live[:, 0] * self.dev.Vcap + live[:, 1]).to(self.dev.device)
+        n = int(idx.numel())
+        for k in ('zr', 'order'):
+            if k not in out or out[k].shape[0] != n:
+                out[k] = torch.empty((n, self.R), dtype=torch.int32).pin_memory()
+            out[k].copy_(t[k].view(-1, self.R).index_select(0, idx), non_blocking=True)
+        out['live_index'] = live
+        self.dev.sync()
+        return out
+
+    def import_dense(self, d, X=None):
+        """Host -> device copy of a dense chain state (+ optionally the table),
+        then the ordered rebuild of all tables: the export half of the bridge
+        (lovecat.py:73-223)."""
+        t = self.dev.t
+        if X is not None:
+            t['Xrm'][:, :self.C].copy_(X, non_blocking=True)
+            t['Xcm'].copy_(t['Xrm'][:, :self.C].t())
+        for k in self.SMALL:
+            t[k].copy_(d[k], non_blocking=True)
+        live = d['live_index']
+        idx = (live[:, 0] * self.dev.Vcap + live[:, 1]).to(self.dev.device)
+        for k in ('zr', 'order'):
+            t[k].view(-1, self.R).index_copy_(0, idx, d[k].to(self.dev.device, non_blocking=True))
+        self._mirror = None
+        self.dev.rebuild()

@@ -6,6 +6,7 @@ tensors is done by the CUDA kernels of libcgpm_b200.so through the C ABI
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 
@@ -43,6 +44,32 @@ def hyper_grids(xcol, ctype, n_grid=L.NGRID):
 def crp_grid(n, n_grid=L.NGRID):
     """src/primitives/crp.py:148-152 with n members."""
     return log_linspace(1. / n, n, n_grid)
+
+
+# CUDA kernels launched per C-ABI call (for the bench's gpu_launches count)
+KERNELS_PER_CALL = {'cc_rebuild': 2, 'cc_logpdf_score': 1, 'cc_transition_rows': 1, 'cc_col_aux': 1,
+                    'cc_col_marginals': 2, 'cc_col_scan': 1, 'cc_col_install': 1,
+                    'cc_transition_col_hypers': 1, 'cc_transition_alphas': 1, 'cc_logpdf_bulk': 1,
+                    'cc_simulate_bulk': 1}
+
+
+class _CountingLib(object):
+    """Forwards to the ctypes library and counts the kernels each call launches."""
+
+    def __init__(self, lib, counts):
+        self._lib, self._counts = lib, counts
+
+    def __getattr__(self, name):
+        f = getattr(self._lib, name)
+        n = KERNELS_PER_CALL.get(name)
+        if n is None:
+            return f
+        counts = self._counts
+
+        def call(*args):
+            counts[name] += n
+            return f(*args)
+        return call
 
 
 class DeviceChains(object):
@@ -133,7 +160,8 @@ class DeviceChains(object):
         st.arena = None
         st.arena_bytes = 0
         self.st = st
-        self.lib = L.load()
+        self.lib_calls = collections.Counter()
+        self.lib = _CountingLib(L.load(), self.lib_calls)
 
     # ------------------------------------------------------------------ helpers
     def stream_ptr(self):
