@@ -77,6 +77,10 @@ def _declare(lib):
     lib.cc_transition_col_hypers.argtypes = [C.POINTER(cc_state), I, P, P, P, P, U64, U64, P]
     lib.cc_transition_alphas.restype = I
     lib.cc_transition_alphas.argtypes = [C.POINTER(cc_state), I, P, P, P, I, U64, U64, P]
+    lib.cc_logpdf_bulk.restype = I
+    lib.cc_logpdf_bulk.argtypes = [C.POINTER(cc_state), I, P, I, P, P, P, P, P, P, P, P]
+    lib.cc_simulate_bulk.restype = I
+    lib.cc_simulate_bulk.argtypes = [C.POINTER(cc_state), I, P, I, P, P, P, P, P, P, I, I, P, P, U64, U64, P]
     for name, argtypes in OPTIONAL.items():
         if hasattr(lib, name):
             f = getattr(lib, name)
@@ -90,7 +94,7 @@ OPTIONAL = {}
 # every symbol include/cgpm_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_logpdf_score',
            'cc_transition_rows', 'cc_col_aux', 'cc_col_marginals', 'cc_col_scan', 'cc_col_install',
-           'cc_transition_col_hypers', 'cc_transition_alphas']
+           'cc_transition_col_hypers', 'cc_transition_alphas', 'cc_logpdf_bulk', 'cc_simulate_bulk']
 
 
 def load():

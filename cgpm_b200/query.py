@@ -1,0 +1,147 @@
+"""Host side of the batched queries: encode the reference's dict-style queries
+(State.logpdf_bulk / simulate_bulk, src/crosscat/state.py:479-523) as CSR
+arrays, run the CUDA kernels, decode.  Validation follows
+State._validate_cgpm_query (state.py:447-476)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def _dp(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _validate(ch, rowid, targets, constraints, simulate):
+    fresh = rowid is None or not (0 <= rowid < ch.R)
+    tcols = list(targets)
+    if simulate and len(set(tcols)) != len(tcols):
+        raise ValueError('Columns in targets must be unique.')
+    for c in list(tcols) + list(constraints):
+        if c not in ch.col_index:
+            raise ValueError('Unknown column: %s' % (c,))
+    X = ch.dev.X_h
+    if not fresh and not simulate and any(not np.isnan(X[rowid, ch.col_index[q]]) for q in tcols):
+        raise ValueError('Cannot constrain observed cell.')
+    if constraints:
+        if set(tcols) & set(constraints):
+            raise ValueError('Targets and constraints must be disjoint.')
+        if not fresh:
+            for e, val in constraints.items():
+                x = X[rowid, ch.col_index[e]]
+                if not (np.isnan(x) or np.allclose(x, val)):
+                    raise ValueError('Cannot use observed cell in constraints.')
+    return fresh
+
+
+def _encode(ch, rowids, targets_list, constraints_list, simulate):
+    Q = len(rowids)
+    if constraints_list is None:
+        constraints_list = [{} for _ in range(Q)]
+    assert len(targets_list) == Q and len(constraints_list) == Q
+    rid = np.full(Q, -1, np.int32)
+    off = np.zeros(Q + 1, np.int32)
+    cols, vals, roles = [], [], []
+    for q in range(Q):
+        t = targets_list[q]
+        cns = constraints_list[q] or {}
+        fresh = _validate(ch, rowids[q], t, cns, simulate)
+        rid[q] = -1 if fresh else int(rowids[q])
+        if simulate:
+            for c in t:
+                cols.append(ch.col_index[c]); vals.append(0.0); roles.append(0)
+        else:
+            for c, x in t.items():
+                cols.append(ch.col_index[c]); vals.append(float(x)); roles.append(0)
+        for c, x in cns.items():
+            cols.append(ch.col_index[c]); vals.append(float(x)); roles.append(1)
+        off[q + 1] = len(cols)
+    dev = ch.dev.device
+    enc = {
+        'Q': Q, 'rowid': torch.from_numpy(rid).to(dev), 'off': torch.from_numpy(off).to(dev),
+        'col': torch.from_numpy(np.asarray(cols or [0], np.int32)).to(dev),
+        'val': torch.from_numpy(np.asarray(vals or [0.0], np.float64)).to(dev),
+        'role': torch.from_numpy(np.asarray(roles or [0], np.uint8)).to(dev),
+        'constraints': constraints_list,
+    }
+    return enc
+
+
+def logpdf_bulk(ch, chains, rowids, targets_list, constraints_list=None):
+    """Returns [len(chains)][Q] floats (Engine.logpdf_bulk, engine.py:202-210)."""
+    for t in targets_list:
+        assert isinstance(t, dict)
+    enc = _encode(ch, rowids, targets_list, constraints_list, simulate=False)
+    out = logpdf_bulk_encoded(ch, chains, enc)
+    return [[float(x) for x in row] for row in out]
+
+
+def logpdf_bulk_encoded(ch, chains, enc):
+    dev = ch.dev
+    n, Q = len(chains), enc['Q']
+    out = torch.empty((n, Q), dtype=torch.float64, device=dev.device)
+    flag = torch.zeros((n, Q), dtype=torch.int32, device=dev.device)
+    chs = np.ascontiguousarray(chains, dtype=np.int32)
+    L.check(dev.lib.cc_logpdf_bulk(C.byref(dev.st), n, chs.ctypes.data_as(C.c_void_p), Q, _dp(enc['rowid']),
+                                   _dp(enc['off']), _dp(enc['col']), _dp(enc['val']), _dp(enc['role']),
+                                   _dp(out), _dp(flag), dev.stream_ptr()), 'cc_logpdf_bulk')
+    res = out.cpu().numpy()
+    bad = flag.cpu().numpy()
+    if bad.any():
+        q = int(np.nonzero(bad.any(axis=0))[0][0])
+        raise ValueError('Zero density constraints: %s' % (enc['constraints'][q],))   # sampling.py:78-79
+    return res
+
+
+def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=None):
+    """Returns [len(chains)][Q] lists of N sample dicts (Engine.simulate_bulk,
+    engine.py:241-251)."""
+    Q = len(rowids)
+    if Ns is None:
+        Ns = [1] * Q
+    for t in targets_list:
+        assert isinstance(t, (list, tuple))
+    enc = _encode(ch, rowids, targets_list, constraints_list, simulate=True)
+    soff = np.zeros(Q + 1, np.int32)
+    soff[1:] = np.cumsum([int(n if n is not None else 1) for n in Ns])
+    total = int(soff[-1])
+    maxt = max(1, max(len(t) for t in targets_list)) if Q else 1
+    dev = ch.dev
+    n = len(chains)
+    out = torch.zeros((2, n, total, maxt), dtype=torch.float64, device=dev.device)
+    flag = torch.zeros((n, Q), dtype=torch.int32, device=dev.device)
+    chs = np.ascontiguousarray(chains, dtype=np.int32)
+    soff_d = torch.from_numpy(soff).to(dev.device)
+    # fold the chains' RandomStates into the device key so that Engine.simulate never
+    # repeats itself (engine.py:232,352-355 reseeds every state first)
+    salt = 0
+    for s in chains:
+        if ch.rngs[s] is not None:
+            salt = (salt * 1000003 + int(ch.rngs[s].randint(0, 2 ** 31 - 1))) & 0xFFFFFFFFFFFFFFFF
+    L.check(dev.lib.cc_simulate_bulk(C.byref(dev.st), n, chs.ctypes.data_as(C.c_void_p), Q, _dp(enc['rowid']),
+                                     _dp(enc['off']), _dp(enc['col']), _dp(enc['val']), _dp(enc['role']),
+                                     _dp(soff_d), total, maxt, _dp(out), _dp(flag),
+                                     C.c_uint64(ch.seed ^ salt), C.c_uint64(ch._next_counter()), dev.stream_ptr()),
+            'cc_simulate_bulk')
+    vals = out[0].cpu().numpy()
+    bad = flag.cpu().numpy()
+    if bad.any():
+        q = int(np.nonzero(bad.any(axis=0))[0][0])
+        raise ValueError('Zero density constraints: %s' % (enc['constraints'][q],))
+    res = []
+    for i in range(n):
+        per_chain = []
+        for q in range(Q):
+            tcols = list(targets_list[q])
+            is_cat = [ch.ctype[ch.col_index[c]] == L.CATEGORICAL for c in tcols]
+            samples = []
+            for r in range(soff[q], soff[q + 1]):
+                samples.append({c: (int(vals[i, r, j]) if is_cat[j] else float(vals[i, r, j]))
+                                for j, c in enumerate(tcols)})
+            per_chain.append(samples)
+        res.append(per_chain)
+    return res

@@ -184,6 +184,28 @@ int cc_transition_col_hypers(const cc_state* st, int n, const int32_t* chains, c
 int cc_transition_alphas(const cc_state* st, int n, const int32_t* chains, const int32_t* views,
                          const double* u, int ndraw, uint64_t seed, uint64_t counter, void* stream);
 
+/* ---- batched queries (src/crosscat/sampling.py:37-116) ------------------------
+ * Queries are CSR: cells qoff[q]..qoff[q+1] of query q have column qcol, value
+ * qval and role qrole (0 target, 1 constraint); rowid[q] is an observed rowid
+ * or -1 for a hypothetical row.  Every listed chain answers every query
+ * (Engine.logpdf_bulk / simulate_bulk, src/crosscat/engine.py:202-210,241-251). */
+
+/* out_dev[n_chains][Q] = State.logpdf; flag_dev[n_chains][Q] = 1 where every
+ * cluster gives the constraints zero density (ValueError, sampling.py:78-79). */
+int cc_logpdf_bulk(const cc_state* st, int n_chains, const int32_t* chains /*host*/, int Q,
+                   const int32_t* rowid_dev, const int32_t* qoff_dev, const int32_t* qcol_dev,
+                   const double* qval_dev, const uint8_t* qrole_dev, double* out_dev,
+                   int32_t* flag_dev, void* stream);
+
+/* soff_dev[Q+1]: sample offsets (N samples per query).  out_dev is
+ * [2][n_chains][total_samples][max_targets]: plane 0 the sampled values in the
+ * query's target order, plane 1 the cluster slot each was drawn from. */
+int cc_simulate_bulk(const cc_state* st, int n_chains, const int32_t* chains /*host*/, int Q,
+                     const int32_t* rowid_dev, const int32_t* qoff_dev, const int32_t* qcol_dev,
+                     const double* qval_dev, const uint8_t* qrole_dev, const int32_t* soff_dev,
+                     int total_samples, int max_targets, double* out_dev, int32_t* flag_dev,
+                     uint64_t seed, uint64_t counter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
