@@ -78,3 +78,81 @@ def assert_suffstats_equal(a, b):
             assert float(sa[1]) == float(sb[1]) and float(sa[2]) == float(sb[2]), (key, sa, sb)
         else:
             assert np.array_equal(np.asarray(sa[1], float), np.asarray(sb[1], float)), (key, sa, sb)
+
+
+# ---------------------------------------------------------------------------- golden snapshots
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load_golden(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def golden_table(g):
+    X = np.array([[np.nan if v is None else v for v in row] for row in g['X']], dtype=float)
+    da = [d if d else None for d in g['distargs']]
+    return X, g['cctypes'], da
+
+
+def hx(x):
+    return float(x).hex()
+
+
+def _pack_stats(st):
+    if len(st) == 3:
+        return {'N': hx(st[0]), 'sum_x': hx(st[1]), 'sum_x_sq': hx(st[2])}
+    return {'N': hx(st[0]), 'counts': [hx(c) for c in st[1]]}
+
+
+def snapshot_oracle(o):
+    md = o.to_metadata()
+    out = {
+        'Zv': sorted([int(c), int(v)] for c, v in md['Zv']),
+        'Zrv': [[int(v), [int(z) for z in zr]] for v, zr in md['Zrv']],
+        'row_order': [[int(v), [int(r) for r in order]] for v, order in md['row_order']],
+        'alpha': hx(md['alpha']),
+        'view_alphas': [[int(v), hx(a)] for v, a in md['view_alphas']],
+        'hypers': [{k: hx(v) for k, v in h.items()} for h in md['hypers']],
+        'suffstats': [],
+    }
+    for c in o.outputs:
+        dim = o.dim_for(c)
+        items = [[int(k), _pack_stats(st)] for k, st in dim.clusters.items()]
+        items.append([max(dim.clusters) + 1, _pack_stats(dim._empty())])
+        out['suffstats'].append(sorted(items))
+    return out
+
+
+def snapshot_engine(eng, s):
+    """Same structure from the GPU engine (chain s)."""
+    from cgpm_b200.engine import _chain_metadata
+    ch = eng._ch
+    md = _chain_metadata(ch, s)
+    spec, _ = ch.chain_spec(s)
+    out = {
+        'Zv': sorted([int(c), int(v)] for c, v in md['Zv']),
+        'Zrv': [[int(v), [int(z) for z in zr]] for v, zr in md['Zrv']],
+        'row_order': [[int(v), [int(r) for r in vw['order']]] for v, vw in spec['views'].items()],
+        'alpha': hx(md['alpha']),
+        'view_alphas': [[int(v), hx(a)] for v, a in md['view_alphas']],
+        'hypers': [{k: hx(v) for k, v in h.items()} for h in md['hypers']],
+        'suffstats': [],
+    }
+    for col in md['suffstats']:
+        items = []
+        for k, st in col:
+            if 'counts' in st:
+                items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
+            else:
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
+        out['suffstats'].append(sorted(items))
+    return out
+
+
+def assert_snapshot_equal(got, ref, tag=''):
+    for key in ('Zv', 'Zrv', 'row_order', 'alpha', 'view_alphas', 'hypers', 'suffstats'):
+        assert got[key] == ref[key], (tag, key, got[key], ref[key])

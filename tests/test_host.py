@@ -1,0 +1,121 @@
+"""CPU: host-side logic (codec, exact host maths, synthetic data, chain sharding)."""
+import os
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import crosscat_oracle as co
+from cgpm_b200 import codec, hostmath as hm, synth
+from cgpm_b200.parallel import shard_range, shard_sizes
+
+
+def test_codec_pack_unpack_round_trip():
+    R, C = 12, 4
+    views = OrderedDict()
+    views[3] = {'alpha': 0.5, 'Zr': np.array([0, 0, 7, 7, 2, 2, 2, 0, 7, 9, 9, 0]), 'order': None}
+    views[0] = {'alpha': 2.0, 'Zr': np.zeros(R, dtype=int), 'order': np.arange(R)[::-1].copy()}
+    spec = {'Zv': [3, 0, 3, 0], 'views': views, 'alpha': 1.5, 'hyp': np.arange(16.).reshape(4, 4)}
+    ch = codec.pack_chain(spec, R, C)
+    assert ch['view_id'] == [3, 0] and ch['nv'] == [2, 2]
+    assert list(ch['cid'][0]) == [0, 2, 7, 9] and list(ch['nk'][0]) == [4, 3, 3, 2]
+    dl = dict(ch)
+    dl['live'] = [np.arange(len(c)) for c in ch['cid']]
+    dl['cid_by_slot'] = ch['cid']
+    back = codec.unpack_chain(dl, views_order=[0, 1])
+    assert back['Zv'] == spec['Zv']
+    for v in views:
+        assert np.array_equal(back['views'][v]['Zr'], views[v]['Zr'])
+    assert list(back['views'].keys()) == [3, 0]
+    h = codec.hypers_from_array(np.arange(8.).reshape(2, 4), [0, 1])
+    assert list(h[0].keys()) == ['m', 'r', 's', 'nu'] and list(h[1].keys()) == ['alpha']
+    assert np.array_equal(codec.hypers_to_array(h, [0, 1])[0], [0, 1, 2, 3])
+
+
+def test_hostmath_matches_oracle_and_reference_kats():
+    rng = np.random.RandomState(42)
+    assert [int(hm.log_pflip([-1, -2, -.5], array=[5, 7, 9], rng=rng)) for _ in range(8)] == [7, 9, 9, 9, 5, 5, 5, 9]
+    assert hm.logsumexp(range(1000)) == co.logsumexp(range(1000))
+    assert hm.logmeanexp([0., -1.]) == co.logmeanexp([0., -1.])
+    # exact CRP prior simulation consumes the stream like the oracle's view constructor
+    a, b = np.random.RandomState(9), np.random.RandomState(9)
+    z = hm.crp_simulate_exact(60, 1.3, a)
+    crp = co.OCrp(60, 1.3, b)
+    ref = []
+    for i in range(60):
+        x = crp.simulate_fresh(b)
+        crp.incorporate(i, x)
+        ref.append(int(x))
+    assert list(z) == ref and a.random_sample() == b.random_sample()
+    zf = hm.crp_simulate_fast(5000, 2.0, np.random.RandomState(1))
+    assert zf[0] == 0 and set(np.unique(zf)) == set(range(zf.max() + 1))
+    K = zf.max() + 1
+    assert 5 < K < 40                      # E[K] ~ alpha log(1 + n/alpha) ~ 15.6
+
+
+def test_hyper_grids_match_oracle():
+    from cgpm_b200.device import hyper_grids, crp_grid
+    x = np.array([1.0, np.nan, 2.5, -0.5, 4.0])
+    g = hyper_grids(x, 0)
+    ref = co.normal_grids([1.0, 2.5, -0.5, 4.0])
+    for i, n in enumerate(['m', 'r', 's', 'nu']):
+        assert np.array_equal(g[i], ref[n])
+    assert np.array_equal(hyper_grids(np.array([0., 1., 2., np.nan]), 1)[0], co.categorical_grids([0., 1., 2.])['alpha'])
+    assert np.array_equal(crp_grid(7), co.crp_grids(7))
+
+
+def test_synth_table_shapes_and_types():
+    cct = ['normal', 'categorical', 'normal']
+    X, Zv, Zrv = synth.gen_table(200, cct, [None, {'k': 5}, None], n_views=2, clusters_per_view=3, seed=3,
+                                 quantize_bits=12, nan_frac=0.05)
+    assert X.shape == (200, 3) and len(Zv) == 3 and len(Zrv) == 2
+    col = X[:, 1][~np.isnan(X[:, 1])]
+    assert np.all(col % 1 == 0) and col.min() >= 0 and col.max() <= 4
+    q = X[:, 0][~np.isnan(X[:, 0])] * 4096
+    assert np.all(q == np.round(q))
+    assert 0 < np.isnan(X).mean() < 0.15
+
+
+def test_shard_ranges_partition_all_chains():
+    for n in (1, 7, 64, 512):
+        for w in (1, 2, 3, 8):
+            got = [shard_range(n, w, r) for r in range(w)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            assert max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from cgpm_b200.parallel import all_gather_chains, all_reduce_sum, shard_range
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    n = 7
+    lo, hi = shard_range(n, world, rank)
+    local = torch.arange(lo, hi, dtype=torch.float64) * 1.5
+    full = all_gather_chains(local, n)
+    mat = torch.stack([torch.full((3,), float(i)) for i in range(lo, hi)])
+    full2 = all_gather_chains(mat, n)
+    acc = all_reduce_sum(torch.ones(2, 2, dtype=torch.float64) * (rank + 1))
+    q.put((rank, full.tolist(), full2[:, 0].tolist(), acc[0, 0].item()))
+    dist.destroy_process_group()
+
+
+def test_gather_over_two_gloo_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, full, full2, acc in res:
+        assert full == [i * 1.5 for i in range(7)]
+        assert full2 == [float(i) for i in range(7)]
+        assert acc == 3.0

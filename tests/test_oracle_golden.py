@@ -1,0 +1,129 @@
+"""CPU: the oracle restatement is pinned against (1) vectors generated from the
+reference itself (tests/golden/make_golden.py) and (2) the known-answer values
+held by the reference's own tests."""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+import crosscat_oracle as co
+from helpers import load_golden, golden_table, snapshot_oracle, assert_snapshot_equal
+
+
+def test_oracle_reproduces_reference_trajectory_bit_for_bit():
+    g = load_golden('trajectory_40x6.json')
+    X, cct, da = golden_table(g)
+    seeds = np.random.RandomState(g['engine_seed']).randint(low=1, high=2 ** 32 - 1, size=g['num_states'])
+    states = [co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(sd)) for sd in seeds]
+    for s, o in enumerate(states):
+        assert_snapshot_equal(snapshot_oracle(o), g['init'][s], ('init', s))
+        assert o.logpdf_score() == g['init'][s]['logpdf_score']
+    for it in range(g['iterations']):
+        for s, o in enumerate(states):
+            o.transition(N=1, kernels=g['kernels'])
+            assert_snapshot_equal(snapshot_oracle(o), g['after'][it][s], (it, s))
+            assert o.logpdf_score() == g['after'][it][s]['logpdf_score']
+    for q in g['queries']:
+        t = {int(k): v for k, v in q['targets'].items()}
+        c = {int(k): v for k, v in q['constraints'].items()}
+        for s, o in enumerate(states):
+            assert o.logpdf(q['rowid'], t, c) == q['logpdf'][s]
+    for s, o in enumerate(states):
+        assert o.rng.random_sample() == g['stream_check'][s]
+
+
+def test_primitive_known_answers():
+    k = load_golden('primitive_kats.json')
+    for args, ref in k['normal_predictive']:
+        assert co.normal_predictive(*args) == ref
+    for args, ref in k['normal_marginal']:
+        assert co.normal_marginal(*args) == ref
+    for args, ref in k['normal_posterior']:
+        assert list(co.normal_posterior(*args)) == ref
+    for (x, N, counts, a), ref in k['categorical_predictive']:
+        assert co.categorical_predictive(x, N, np.array(counts, float), a) == ref
+    for (N, counts, a), ref in k['categorical_marginal']:
+        assert float(co.categorical_marginal(N, np.array(counts, float), a)) == ref
+    counts = OrderedDict([(0, 2), (2, 3), (6, 1)])
+    for (x, N, a), ref in k['crp_predictive']:
+        assert co.crp_predictive(x, N, counts, a) == ref
+    for (N, a), ref in k['crp_marginal']:
+        assert float(co.crp_marginal(N, counts, a)) == ref
+    rng = np.random.RandomState(42)
+    assert [int(co.log_pflip([-1, -2, -.5], array=[5, 7, 9], rng=rng)) for _ in range(8)] == k['log_pflip']
+    for args, ref in k['logsumexp']:
+        assert co.logsumexp(args) == ref
+    grids = co.normal_grids([1.0, 2.5, -0.5, 4.0])
+    for n, v in k['normal_grids'].items():
+        assert [float(x) for x in grids[n]] == v
+    assert [float(x) for x in co.crp_grids(7)] == k['crp_grid']
+
+
+def relerr(expected, actual):
+    return abs((actual - expected) / expected)
+
+
+def test_reference_test_logsumexp_known_answers():
+    """/root/reference/tests/test_logsumexp.py:26-60."""
+    inf, nan = float('inf'), float('nan')
+    assert co.logsumexp([]) == -inf
+    assert co.logsumexp([-1000.]) == -1000.
+    assert co.logsumexp([-1000., -1000.]) == -1000. + math.log(2.)
+    assert relerr(math.log(2.), co.logsumexp([0., 0.])) < 1e-15
+    assert co.logsumexp([-inf, 1]) == 1
+    assert co.logsumexp([-inf, -inf]) == -inf
+    assert co.logsumexp([+inf, +inf]) == +inf
+    assert math.isnan(co.logsumexp([-inf, +inf]))
+    assert math.isnan(co.logsumexp([nan, inf]))
+    assert math.isnan(co.logsumexp([nan, -3]))
+    assert relerr(999.4586751453871, co.logsumexp(range(1000))) < 1e-15
+    assert co.logmeanexp([]) == -inf
+    assert relerr(992.550919866405, co.logmeanexp(range(1000))) < 1e-15
+    assert co.logmeanexp([-1000., -1000.]) == -1000.
+    assert relerr(math.log(0.5 * (1 + math.exp(-1.))), co.logmeanexp([0., -1.])) < 1e-15
+    assert relerr(math.log(0.5), co.logmeanexp([0., -1000.])) < 1e-15
+    assert relerr(-3 - math.log(2.), co.logmeanexp([-inf, -3])) < 1e-15
+    assert relerr(-3 - math.log(2.), co.logmeanexp([-3, -inf])) < 1e-15
+    assert co.logmeanexp([+inf, -3]) == +inf
+    assert co.logmeanexp([-inf, 0, +inf]) == +inf
+    assert math.isnan(co.logmeanexp([nan, -3]))
+    assert math.isnan(co.logmeanexp([nan]))
+
+
+def test_reference_test_crp_gibbs_tables():
+    """/root/reference/tests/test_crp.py:117-177: counts {0:2, 2:3, 6:1}, alpha 1.5."""
+    counts = OrderedDict([(0, 2), (2, 3), (6, 1)])
+    K, lp = co.crp_gibbs_logps(counts, 0, 1.5)
+    assert K == [0, 2, 6, 7] and np.allclose(np.exp(lp), [1, 3, 1, 1.5])
+    K, lp = co.crp_gibbs_logps(counts, 2, 1.5)
+    assert K == [0, 2, 6, 7] and np.allclose(np.exp(lp), [2, 2, 1, 1.5])
+    K, lp = co.crp_gibbs_logps(counts, 6, 1.5)                # the singleton: no auxiliary table
+    assert K == [0, 2, 6] and np.allclose(np.exp(lp), [2, 3, 1.5])
+    # marginal = sum of sequential predictives (tests/test_crp.py:180-212)
+    data, seen, N, acc = [0, 0, 2, 2, 2, 6], OrderedDict(), 0, 0.0
+    for x in data:
+        acc += co.crp_predictive(x, N, seen, 1.5)
+        seen[x] = seen.get(x, 0) + 1
+        N += 1
+    assert abs(acc - co.crp_marginal(6, counts, 1.5)) < 1e-12
+
+
+def test_reference_view_logpdf_cluster_identities():
+    """/root/reference/tests/test_view_logpdf_cluster.py:25-92: 5x3 view with NaNs,
+    alpha = 2, Zr = [0,0,0,1,1]: CRP prior 3/7, 2/7, 2/7 and sum_k p(k | x) = 1."""
+    X = np.array([[1, np.nan, 2, -1, np.nan], [1, 3, 2, -1, -5], [18, -7, -2, 11, -12]], dtype=float).T
+    o = co.OState(X, cctypes=['normal'] * 3, Zv={0: 0, 1: 0, 2: 0}, Zrv={0: [0, 0, 0, 1, 1]},
+                  view_alphas={0: 2.}, alpha=1., rng=np.random.RandomState(0))
+    view = o.views[0]
+    K = sorted(view.Nk) + [max(view.Nk) + 1]
+    prior = [math.exp(co.crp_predictive(k, 5, view.Nk, 2.)) for k in K]
+    assert np.allclose(prior, [3. / 7, 2. / 7, 2. / 7])
+    # Bayes rule over clusters for a hypothetical row with evidence on columns 0 and 2
+    ev = {0: 1., 2: 3.}
+    joint = [co.crp_predictive(k, 5, view.Nk, 2.) + co.OState._row_logpdf(view, ev, k) for k in K]
+    post = np.exp(np.asarray(joint) - co.logsumexp(joint))
+    assert abs(post.sum() - 1) < 1e-12
+    assert abs(o.logpdf(-1, ev) - co.logsumexp(joint)) < 1e-12
+    # chain rule p(x0, x2) = p(x0) p(x2 | x0)
+    assert abs(o.logpdf(-1, ev) - (o.logpdf(-1, {0: 1.}) + o.logpdf(-1, {2: 3.}, {0: 1.}))) < 1e-10

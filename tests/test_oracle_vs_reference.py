@@ -1,0 +1,55 @@
+"""CPU: live replay of the oracle restatement against the reference itself
+(oracle/_ref = the py3-shimmed /root/reference).  Skipped where the shimmed
+reference has not been built (it needs /root/reference)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import crosscat_oracle as co
+from helpers import small_table, snapshot_oracle
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'cgpm', '.built')),
+                                reason='oracle/_ref not built (reference tree absent)')
+
+
+def ref_snapshot(state):
+    sys.path.insert(0, os.path.join(os.path.dirname(REF), '..', 'tests', 'golden'))
+    md = state.to_metadata()
+    hx = lambda x: float(x).hex()
+    out = {
+        'Zv': sorted([int(c), int(v)] for c, v in md['Zv']),
+        'Zrv': [[int(v), [int(z) for z in zr]] for v, zr in md['Zrv']],
+        'row_order': [[int(v), [int(r) for r in view.Zr().keys()]] for v, view in state.views.items()],
+        'alpha': hx(md['alpha']), 'view_alphas': [[int(v), hx(a)] for v, a in md['view_alphas']],
+        'hypers': [{k: hx(v) for k, v in h.items()} for h in md['hypers']], 'suffstats': [],
+    }
+    for col in md['suffstats']:
+        items = []
+        for k, st in col:
+            if 'counts' in st:
+                items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
+            else:
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
+        out['suffstats'].append(sorted(items))
+    return out
+
+
+@pytest.mark.parametrize('seed', [3, 4])
+def test_oracle_equals_reference_over_transitions(seed):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from cgpm.crosscat.state import State
+    X, cct, da = small_table(50, seed)
+    ref = State(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed))
+    o = co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed))
+    kernels = ['alpha', 'view_alphas', 'column_hypers', 'rows', 'columns']
+    for it in range(3):
+        ref.transition(N=1, kernels=kernels, progress=False)
+        o.transition(N=1, kernels=kernels)
+        assert snapshot_oracle(o) == ref_snapshot(ref)
+        assert o.logpdf_score() == ref.logpdf_score()
+    assert o.logpdf(-1, {0: 1.0, 1: 2}, {2: 0.5}) == ref.logpdf(-1, {0: 1.0, 1: 2}, {2: 0.5})
+    assert o.rng.random_sample() == ref.rng.random_sample()
