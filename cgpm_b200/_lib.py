@@ -32,7 +32,7 @@ class cc_state(C.Structure):
         ('err', C.c_void_p),
         ('seq', C.c_void_p), ('moved', C.c_void_p), ('movedflag', C.c_void_p),
         ('colL', C.c_void_p), ('aux_zr', C.c_void_p), ('aux_nk', C.c_void_p), ('aux_K', C.c_void_p),
-        ('aux_alpha', C.c_void_p),
+        ('aux_alpha', C.c_void_p), ('aux_zr_all', C.c_void_p), ('aux_K_all', C.c_void_p),
         ('arena', C.c_void_p), ('arena_bytes', C.c_int64),
     ]
 
@@ -72,7 +72,7 @@ def _declare(lib):
     lib.cc_col_scan.restype = I
     lib.cc_col_scan.argtypes = [C.POINTER(cc_state), I, P, P, I, P, P, P, U64, U64, P, P, P, I, P]
     lib.cc_col_install.restype = I
-    lib.cc_col_install.argtypes = [C.POINTER(cc_state), I, P, P, P]
+    lib.cc_col_install.argtypes = [C.POINTER(cc_state), I, P, P, I, P]
     lib.cc_transition_col_hypers.restype = I
     lib.cc_transition_col_hypers.argtypes = [C.POINTER(cc_state), I, P, P, P, P, U64, U64, P]
     lib.cc_transition_alphas.restype = I

@@ -400,7 +400,7 @@ class Chains(object):
         n1 = (R + 31) >> 5
         n2 = (n1 + 31) >> 5
         per = (R + (R + n1 + n2 + 32) + (R + 1) + R + R + 3) & ~3
-        want = min(max(n_pairs, 1), 148 * 16)
+        want = min(max(n_pairs, 1), 148 * 32)
         free, _total = torch.cuda.mem_get_info(dev.device)
         budget = max(int(free * 0.5), per * 4)
         workers = max(1, min(want, budget // (per * 4)))
@@ -410,6 +410,20 @@ class Chains(object):
             dev.arena = torch.empty(need, dtype=torch.int32, device=dev.device)
             dev.st.arena = dev.arena.data_ptr()
             dev.st.arena_bytes = need * 4
+
+    def _ensure_aux_store(self):
+        """Room for every (chain, column) auxiliary partition, when it costs less than a
+        quarter of the free device memory; otherwise a birth regenerates its partition."""
+        dev = self.dev
+        if dev.aux_zr_all is not None:
+            return True
+        need = self.S * self.C * self.R * 4
+        free, _total = torch.cuda.mem_get_info(dev.device)
+        if need > free // 4:
+            return False
+        dev.aux_zr_all = torch.empty(self.S * self.C * self.R, dtype=torch.int32, device=dev.device)
+        dev.st.aux_zr_all = dev.aux_zr_all.data_ptr()
+        return True
 
     def transition_dims(self, chains, cols=None, trace=None):
         """State.transition_dims (state.py:804-810) for the selected chains."""
@@ -438,13 +452,15 @@ class Chains(object):
         self._mirror = None
         if self.stream == 'philox':
             self._ensure_arena(nch * ncols)
+            stored = self._ensure_aux_store()
             cols_d = torch.from_numpy(perm).to(dev.device)
             pos_d = torch.zeros(nch, dtype=torch.int32, device=dev.device)
             pend_d = torch.full((nch,), -1, dtype=torch.int32, device=dev.device)
             # auxiliary views of every (chain, column) and marginals under every live view
             a_ch = np.repeat(ch_h, ncols).astype(np.int32)
             a_co = perm.reshape(-1).astype(np.int32)
-            L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), None, None, 0, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
+            L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), None, None, 2 if stored else 0, seed,
+                                   C.c_uint64(counter), sp()), 'cc_col_aux')
             m = self.mirror()
             w_ch = np.ascontiguousarray([s for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
             w_vw = np.ascontiguousarray([v for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
@@ -465,10 +481,11 @@ class Chains(object):
                     break
                 b_ch = np.ascontiguousarray(ch_h[idx], dtype=np.int32)
                 b_co = np.ascontiguousarray(perm[idx, pend[idx]], dtype=np.int32)
-                # regenerate the same auxiliary partitions (same key), keep them, install
-                L.check(lib.cc_col_aux(st, len(b_ch), _p(b_ch), _p(b_co), None, None, 1, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
+                if not stored:
+                    # regenerate the same auxiliary partitions (same key) and keep them
+                    L.check(lib.cc_col_aux(st, len(b_ch), _p(b_ch), _p(b_co), None, None, 1, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
                 nv_before = dev.t['nv'].cpu().numpy()
-                L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), sp()), 'cc_col_install')
+                L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), 2 if stored else 1, sp()), 'cc_col_install')
                 new_slots = np.array([int(np.nonzero(nv_before[s] == 0)[0][0]) if np.any(nv_before[s] == 0) else 0
                                       for s in b_ch], dtype=np.int32)
                 rem_off = np.ascontiguousarray([i * ncols + pend[i] + 1 for i in idx], dtype=np.int32)
@@ -527,7 +544,7 @@ class Chains(object):
                 if len(idx):
                     b_ch = np.ascontiguousarray(ch_h[idx], dtype=np.int32)
                     b_co = np.ascontiguousarray(perm[idx, j], dtype=np.int32)
-                    L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), sp()), 'cc_col_install')
+                    L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), 1, sp()), 'cc_col_install')
                 self._mirror = None
                 self._refresh_views_order(chains)
             dev.sync()

@@ -76,71 +76,82 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         for (int i = lane; i < ntree; i += 32) Lv[0][i] = 0;
         __syncwarp();
         int K = 1;              // tables so far
-        int P = 1;              // this lane's inclusive prefix of the counts of tables 0..31 (lane 0: table 0 has row 0)
+        int P = 1;              // this lane's inclusive prefix of the counts of tables 0..31 (table 0 holds row 0)
         int reg_total = 1, mem_total = 0;
         if (lane == 0) z[0] = 0;
         const uint64_t ustream = stream_id(3, s, c);
-        double ucache = 0.0;
-        for (int i = 1; i < R; ++i) {
-            // uniforms in batches of 32 (lane l holds the one for row i0 + l)
-            if (((i - 1) & 31) == 0) {
-                const int ii = i + lane;
-                if (p.u) ucache = (ii < R) ? p.u[(size_t)w * (R - 1) + (ii - 1)] : 0.0;
-                else { const uint4 r4 = rng(p.counter * 0x100000000ull + (uint64_t)ii, ustream); ucache = u01_from_words(r4.x, r4.y); }
+        // Rows are seated in batches of 32: every lane first turns its row's uniform into
+        // t = u (i + alpha) (crp.py:178-182 normalised by N + alpha) and keeps floor(t) and
+        // the "new table" bit t >= i, which do not depend on the seating; the sequential part
+        // of a row is then one shuffle, one integer compare and one ballot (table counts are
+        // integers, so prefix > t  <=>  prefix > floor(t)).
+        for (int i0 = 1; i0 < R; i0 += 32) {
+            const int ii = i0 + lane;
+            double uu = 0.0;
+            if (ii < R) {
+                if (p.u) uu = p.u[(size_t)w * (R - 1) + (ii - 1)];
+                else { const uint4 r4 = rng(p.counter * 0x100000000ull + (uint64_t)ii, ustream); uu = u01_from_words(r4.x, r4.y); }
             }
-            const double uu = __shfl_sync(0xffffffffu, ucache, (i - 1) & 31);
-            const double t = uu * ((double)i + alpha);
-            int j;
-            if (t >= (double)i) {
-                // new table (index K)
-                j = K;
-                if (K < 32) { if (lane >= K) P += 1; reg_total += 1; }
-                else {
-                    const int jp = K - 32;
-                    if (lane == 0) {
-                        if (jp == 32) Lv[1][0] = mem_total;
-                        if (jp == 1024) { Lv[2][0] = mem_total; }
-                        if (jp == 32768) { Lv[3][0] = mem_total; }
-                        Lv[0][jp] = 1;
-                        if (jp >= 32) Lv[1][jp >> 5] += 1;
-                        if (jp >= 1024) Lv[2][jp >> 10] += 1;
-                        if (jp >= 32768) Lv[3][jp >> 15] += 1;
+            const double tt = uu * ((double)ii + alpha);
+            int packed = (int)fmin(tt, 2.0e9);                    // floor(t), t >= 0
+            if (tt >= (double)ii) packed |= 0x80000000;           // new table
+            int zreg = 0;
+            const int nb = min(32, R - i0);
+            for (int l = 0; l < nb; ++l) {
+                const int pk = __shfl_sync(0xffffffffu, packed, l);
+                const int tl = pk & 0x7fffffff;
+                int j;
+                if (pk < 0) {
+                    j = K;                                        // new table (index K)
+                    if (K < 32) { if (lane >= K) P += 1; reg_total += 1; }
+                    else {
+                        const int jp = K - 32;
+                        if (lane == 0) {
+                            if (jp == 32) Lv[1][0] = mem_total;
+                            if (jp == 1024) Lv[2][0] = mem_total;
+                            if (jp == 32768) Lv[3][0] = mem_total;
+                            Lv[0][jp] = 1;
+                            if (jp >= 32) Lv[1][jp >> 5] += 1;
+                            if (jp >= 1024) Lv[2][jp >> 10] += 1;
+                            if (jp >= 32768) Lv[3][jp >> 15] += 1;
+                        }
+                        mem_total += 1;
+                        __syncwarp();
                     }
-                    mem_total += 1;
+                    K += 1;
+                } else if (tl < reg_total) {
+                    const unsigned hit = __ballot_sync(0xffffffffu, P > tl);
+                    j = __ffs(hit) - 1;
+                    if (lane >= j) P += 1;
+                    reg_total += 1;
+                } else {
+                    int tr = tl - reg_total;
+                    const int Kp = K - 32;
+                    const int top = (Kp <= 32) ? 0 : (Kp <= 1024) ? 1 : (Kp <= 32768) ? 2 : 3;
+                    int idx = 0;
+                    for (int lev = top; lev >= 0; --lev) {
+                        const int size = (lev == 0) ? Kp : (lev == 1) ? ((Kp + 31) >> 5) : (lev == 2) ? ((Kp + 1023) >> 10) : ((Kp + 32767) >> 15);
+                        const int e = idx * 32 + lane;
+                        const int val = (e < size) ? Lv[lev][e] : 0;
+                        const int inc = warp_incl_scan_i(val, lane);
+                        unsigned hit = __ballot_sync(0xffffffffu, inc > tr);
+                        if (!hit) {             // unreachable in exact arithmetic; fall on the last occupied entry
+                            const unsigned nz = __ballot_sync(0xffffffffu, val > 0);
+                            hit = nz ? (1u << (31 - __clz(nz))) : 1u;
+                        }
+                        const int h = __ffs(hit) - 1;
+                        const int excl = __shfl_sync(0xffffffffu, inc - val, h);
+                        tr -= excl;
+                        if (lane == h) Lv[lev][e] = val + 1;
+                        idx = idx * 32 + h;
+                    }
                     __syncwarp();
+                    j = idx + 32;
+                    mem_total += 1;
                 }
-                K += 1;
-            } else if (t < (double)reg_total) {
-                const unsigned hit = __ballot_sync(0xffffffffu, (double)P > t);
-                j = __ffs(hit) - 1;
-                if (lane >= j) P += 1;
-                reg_total += 1;
-            } else {
-                double tr = t - (double)reg_total;
-                const int Kp = K - 32;
-                const int top = (Kp <= 32) ? 0 : (Kp <= 1024) ? 1 : (Kp <= 32768) ? 2 : 3;
-                int idx = 0;
-                for (int lev = top; lev >= 0; --lev) {
-                    const int size = (lev == 0) ? Kp : (lev == 1) ? ((Kp + 31) >> 5) : (lev == 2) ? ((Kp + 1023) >> 10) : ((Kp + 32767) >> 15);
-                    const int e = idx * 32 + lane;
-                    const int val = (e < size) ? Lv[lev][e] : 0;
-                    const int inc = warp_incl_scan_i(val, lane);
-                    unsigned hit = __ballot_sync(0xffffffffu, (double)inc > tr);
-                    if (!hit) {             // unreachable in exact arithmetic; fall on the last occupied entry
-                        const unsigned nz = __ballot_sync(0xffffffffu, val > 0);
-                        hit = nz ? (1u << (31 - __clz(nz))) : 1u;
-                    }
-                    const int h = __ffs(hit) - 1;
-                    const int excl = __shfl_sync(0xffffffffu, inc - val, h);
-                    tr -= (double)excl;
-                    if (lane == h) Lv[lev][e] = val + 1;
-                    idx = idx * 32 + h;
-                }
-                __syncwarp();
-                j = idx + 32;
-                mem_total += 1;
+                if (lane == l) zreg = j;
             }
-            if (lane == 0) z[i] = j;
+            if (ii < R) z[ii] = zreg;                             // coalesced store of the batch
         }
         __syncwarp();
         // ---- pass 2: ordered per-table statistics of column c, marginal ------------
@@ -158,14 +169,8 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                 carry += __shfl_sync(0xffffffffu, inc, 31);
             }
             if (lane == 0) start[K] = carry;
-            if (p.write_zr) {
-                int32_t* anke = st.aux_nk + (size_t)s * R;
-                for (int b0 = 0; b0 < K; b0 += 32) {
-                    const int j = b0 + lane;
-                    if (j < K) anke[j] = (b0 == 0) ? myc : Lv[0][j - 32];
-                }
-                if (lane == 0) st.aux_K[s] = K;
-            }
+            if (p.write_zr == 1 && lane == 0) st.aux_K[s] = K;
+            if (p.write_zr == 2 && lane == 0) st.aux_K_all[(size_t)s * st.C + c] = K;
         }
         __syncwarp();
         for (int b0 = 0; b0 < R; b0 += 32) {
@@ -179,7 +184,8 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             __syncwarp();
             if (act && rank == __popc(peers) - 1) cursor[k] = pos + 1;
             if (act) grouped[pos] = i;
-            if (act && p.write_zr) st.aux_zr[(size_t)s * R + i] = k;
+            if (act && p.write_zr == 1) st.aux_zr[(size_t)s * R + i] = k;
+            if (act && p.write_zr == 2) st.aux_zr_all[((size_t)s * st.C + c) * R + i] = k;
             __syncwarp();
         }
         const double* hyp = st.hyp + ((size_t)s * st.C + c) * 4;
@@ -349,16 +355,19 @@ __global__ void __launch_bounds__(32) scan_kernel(const ScanParams p) {
     if (lane == 0) { p.pending[w] = -1; p.pos[w] = p.ncols; }
 }
 
-// install the auxiliary partition held in aux_zr / aux_nk / aux_K as a new view
-// and move the pending column into it (state.py:1110-1116, 1147-1154)
+// install an auxiliary partition (mode 1: aux_zr / aux_K of the chain, mode 2: the stored
+// aux_zr_all / aux_K_all of the (chain, column)) as a new view and move the column into it
+// (state.py:1110-1116, 1147-1154).  Table sizes are recounted from the partition.
 __global__ void __launch_bounds__(256) install_kernel(const cc_state st, int n, const int32_t* chains,
-                                                      const int32_t* cols) {
+                                                      const int32_t* cols, int mode) {
     const int w = blockIdx.x;
     if (w >= n) return;
     const int s = chains[w], c = cols[w];
     const int R = st.R, C = st.C, Vcap = st.Vcap, Kcap = st.Kcap;
     int32_t* nv = st.nv + (size_t)s * Vcap;
     int32_t* view_id = st.view_id + (size_t)s * Vcap;
+    const int K = (mode == 2) ? st.aux_K_all[(size_t)s * C + c] : st.aux_K[s];
+    const int32_t* src = (mode == 2) ? st.aux_zr_all + ((size_t)s * C + c) * R : st.aux_zr + (size_t)s * R;
     __shared__ int s_slot, s_newid;
     if (threadIdx.x == 0) {
         int slot = -1, maxid = -1;
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__(256) install_kernel(const cc_state st, int n, 
             if (nv[v] > 0) maxid = max(maxid, view_id[v]);
             else if (slot < 0) slot = v;
         }
-        if (st.aux_K[s] > Kcap - 1) slot = -1;
+        if (K > Kcap - 1) slot = -1;
         s_slot = slot;
         s_newid = maxid + 1;
         if (slot < 0) st.err[s] = CC_ERR_CAPACITY;
@@ -375,15 +384,17 @@ __global__ void __launch_bounds__(256) install_kernel(const cc_state st, int n, 
     const int slot = s_slot;
     if (slot < 0) return;
     const size_t sv = sv_index(st, s, slot);
-    const int K = st.aux_K[s];
-    for (int i = threadIdx.x; i < R; i += blockDim.x) {
-        st.zr[sv * R + i] = st.aux_zr[(size_t)s * R + i];
-        st.order[sv * R + i] = i;
-    }
     for (int k = threadIdx.x; k < Kcap; k += blockDim.x) {
         st.live[sv * Kcap + k] = (k < K) ? k : -1;
         st.cid[sv * Kcap + k] = (k < K) ? k : 0;
-        st.nk[sv * Kcap + k] = (k < K) ? st.aux_nk[(size_t)s * R + k] : 0;
+        st.nk[sv * Kcap + k] = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        const int k = src[i];
+        st.zr[sv * R + i] = k;
+        st.order[sv * R + i] = i;
+        atomicAdd(&st.nk[sv * Kcap + k], 1);
     }
     if (threadIdx.x == 0) {
         const int own = st.zv[(size_t)s * C + c];
@@ -413,6 +424,7 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
                           uint64_t counter, void* stream_) {
     if (!st || n < 0) { cc_set_error("cc_col_aux: bad arguments"); return CC_ERR_ARG; }
     if (n == 0) return CC_OK;
+    if (write_zr == 2 && !st->aux_zr_all) { cc_set_error("cc_col_aux: write_zr=2 needs aux_zr_all"); return CC_ERR_ARG; }
     if (st->R > (1 << 20) + 32) { cc_set_error("cc_col_aux: R > 2^20 not supported by the count tree"); return CC_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
     const int R = st->R;
@@ -428,7 +440,7 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     CC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     const int wpb = 4;
     int blocks = (nworkers + wpb - 1) / wpb;
-    if (blocks > nsm * 4) blocks = nsm * 4;
+    if (blocks > nsm * 8) blocks = nsm * 8;
     if (blocks * wpb > nworkers) blocks = nworkers / wpb > 0 ? nworkers / wpb : 1;
     int tpb = (blocks == 1 && nworkers < wpb) ? nworkers * 32 : wpb * 32;
     AuxParams p;
@@ -479,13 +491,14 @@ extern "C" int cc_col_scan(const cc_state* st, int n_chains, const int32_t* chai
     return CC_OK;
 }
 
-extern "C" int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols, void* stream_) {
+extern "C" int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols, int mode, void* stream_) {
     if (!st || n < 0) { cc_set_error("cc_col_install: bad arguments"); return CC_ERR_ARG; }
     if (n == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     int32_t *dch = nullptr, *dco = nullptr;
     if (to_device(&dch, chains, n, stream) || to_device(&dco, cols, n, stream)) return CC_ERR_CUDA;
-    install_kernel<<<n, 256, 0, stream>>>(*st, n, dch, dco);
+    if (mode == 2 && !st->aux_zr_all) { cc_set_error("cc_col_install: no stored partitions"); return CC_ERR_ARG; }
+    install_kernel<<<n, 256, 0, stream>>>(*st, n, dch, dco, mode);
     CC_CUDA(cudaGetLastError());
     cudaFreeAsync(dch, stream); cudaFreeAsync(dco, stream);
     return CC_OK;

@@ -28,6 +28,7 @@
 // `+= x`, view.py:416-419), so they are bit-identical for the same sequence of
 // moves.  The predictive is evaluated in the algebraically equal Student-t form
 // (see cc_common.cuh) in fp64.
+#include <cstdlib>
 #include "cc_common.cuh"
 
 namespace {
@@ -53,8 +54,27 @@ struct Tab {            // table accessor (shared or global)
     int global;         // 0: shared-memory tables
 };
 
-__device__ __forceinline__ void consumer_sync(int nt) {
-    asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory");
+template <int NT>
+__device__ __forceinline__ void consumer_sync_t() {
+    if (NT == 32) __syncwarp();                       // single consumer warp: no block barrier at all
+    else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+#define consumer_sync(nt) consumer_sync_t<NT>()
+
+// cached predictive constants for the rows kernel: same formulas as normal_cache, with the two
+// divisions replaced by reciprocals (the values feed log-densities only, never the statistics)
+__device__ __forceinline__ NormalCache normal_cache_fast(double N, double sx, double sxx, double gN, double m,
+                                                         double r, double s, double nu) {
+    const double rn = r + N;
+    const double irn = __drcp_rn(rn);
+    const double mn = (r * m + sx) * irn;
+    double sn = __dsub_rn(__dadd_rn(__dadd_rn(s, sxx), __dmul_rn(__dmul_rn(r, m), m)), __dmul_rn(__dmul_rn(rn, mn), mn));
+    if (sn == 0.0) sn = s;
+    NormalCache c;
+    c.mn = mn;
+    c.a = rn * __drcp_rn((rn + 1.0) * sn);
+    c.cst = gN - 0.5 * log(sn);
+    return c;
 }
 
 // bijection on [0, 2^bits) from add / odd-multiply / xorshift rounds, walked
@@ -72,8 +92,8 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
     return x;
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p) {
     const cc_state& st = p.st;
     const cc_row_work wk = p.work[blockIdx.x];
     const int s = wk.chain, v = wk.view, n = wk.n;
@@ -113,6 +133,8 @@ __global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
     int* s_zrow = s_rowidx + 64;                                      // [2][32]
     size_t off = (size_t)((unsigned char*)(s_zrow + 64) - smem_raw);
     off = (off + 15) & ~(size_t)15;
+    double* s_u = reinterpret_cast<double*>(smem_raw + off);          // [2][32] the row's uniform
+    off += 64 * sizeof(double);
     const int xstride = p.bulk ? Cp : ((D + 1) & ~1);
     double* s_x = reinterpret_cast<double*>(smem_raw + off);          // [2][B][xstride]
     off += (size_t)2 * B * xstride * sizeof(double);
@@ -228,6 +250,10 @@ __global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
                 else idx = (int)keyed_perm((uint32_t)i, (uint32_t)n, bits, pkey);
                 r = wk.perm_is_index ? order[idx] : idx;
                 s_rowidx[buf * 32 + lane] = r;
+                double uu;
+                if (wk.u_off >= 0) uu = p.u[wk.u_off + i];
+                else { const uint4 w4 = rng(p.counter * 0x100000000ull + (uint64_t)i, stream_id(1, s, v)); uu = u01_from_words(w4.x, w4.y); }
+                s_u[buf * 32 + lane] = uu;
             }
             const int nrows = min(B, n - b * B);
             __syncwarp();
@@ -250,7 +276,6 @@ __global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
     int G = 1;
     while (G < D && G < 32) G <<= 1;
     const int gid = tid / G, gl = tid & (G - 1), ngroups = NT / G;
-    const uint64_t ustream = stream_id(1, s, v);
 
     for (int i = 0; i < n; ++i) {
         const int b = i / B, slot = i - b * B, buf = b & 1;
@@ -287,13 +312,13 @@ __global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
                         const double N0 = T.f[CC_F_N][e], sx0 = T.f[CC_F_SX][e], sxx0 = T.f[CC_F_SXX][e];
                         const double xx = __dmul_rn(x, x);
                         const double N1 = N0 - 1.0, sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
-                        const NormalCache c1 = normal_cache(N1, sx1, sxx1, T.f[CC_F_GM1][e], m, rr, ss, nu);
+                        const NormalCache c1 = normal_cache_fast(N1, sx1, sxx1, T.f[CC_F_GM1][e], m, rr, ss, nu);
                         acc += normal_predictive_cached(x, c1.mn, c1.a, c1.cst, N1, nu);
                         const double sx2 = __dadd_rn(sx1, x), sxx2 = __dadd_rn(sxx1, xx);
                         if (sx2 != sx0 || sxx2 != sxx0) {
                             T.f[CC_F_SX][e] = sx2;
                             T.f[CC_F_SXX][e] = sxx2;
-                            const NormalCache c2 = normal_cache(N0, sx2, sxx2, T.f[CC_F_GN][e], m, rr, ss, nu);
+                            const NormalCache c2 = normal_cache_fast(N0, sx2, sxx2, T.f[CC_F_GN][e], m, rr, ss, nu);
                             T.f[CC_F_MN][e] = c2.mn; T.f[CC_F_A][e] = c2.a; T.f[CC_F_CST][e] = c2.cst;
                         }
                     }
@@ -319,9 +344,7 @@ __global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
         consumer_sync(NT);
 
         // ---- draw (every warp redundantly; identical arithmetic) ------------------
-        double uu;
-        if (wk.u_off >= 0) uu = p.u[wk.u_off + i];
-        else { const uint4 w = rng(p.counter * 0x100000000ull + (uint64_t)i, ustream); uu = u01_from_words(w.x, w.y); }
+        const double uu = s_u[buf * 32 + slot];
         double mx = -INFINITY;
         for (int pc = lane; pc < ncand; pc += 32) mx = fmax(mx, s_lp[pc]);
         mx = warp_max(mx);
@@ -436,7 +459,7 @@ __global__ void __launch_bounds__(NT + 32, 1) rows_kernel(const RowsParams p) {
                         gM1 = T.f[CC_F_GN][e];
                         gN = normal_G(N, rr, nu);
                     }
-                    const NormalCache cc = normal_cache(N, sx, sxx, gN, m, rr, ss, nu);
+                    const NormalCache cc = normal_cache_fast(N, sx, sxx, gN, m, rr, ss, nu);
                     T.f[CC_F_N][e] = N; T.f[CC_F_SX][e] = sx; T.f[CC_F_SXX][e] = sxx;
                     T.f[CC_F_MN][e] = cc.mn; T.f[CC_F_A][e] = cc.a; T.f[CC_F_CST][e] = cc.cst;
                     T.f[CC_F_GN][e] = gN; T.f[CC_F_GM1][e] = gM1;
@@ -579,7 +602,6 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     CC_CUDA(cudaGetDevice(&dev));
     CC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     CC_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    constexpr int NT = 256;
     RowsParams p;
     p.st = *st; p.work = dwork; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
     p.seed = seed; p.counter = counter;
@@ -587,20 +609,30 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     const int rowbytes = st->Cp * 8;
     p.bulk = (rowbytes <= 4096) ? 1 : 0;
     p.B = 32;
-    if (p.bulk) while (p.B > 4 && 2 * p.B * rowbytes > 48 * 1024) p.B >>= 1;
-    // CTAs per SM wanted: enough to co-schedule all work items, at most 4
+    if (p.bulk) while (p.B > 4 && 2 * p.B * rowbytes > 32 * 1024) p.B >>= 1;
+    // consumer threads: one warp (no block barriers) for narrow views, four warps otherwise;
+    // override with CGPM_B200_ROWS_NT=32|128
+    int nt = 128;
+    if (const char* e = getenv("CGPM_B200_ROWS_NT")) nt = atoi(e) == 32 ? 32 : 128;
+    // CTAs per SM wanted: enough to co-schedule all work items
+    const int maxb = (nt == 32) ? 8 : 3;
     int per_sm = (n_work + nsm - 1) / nsm;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > maxb) per_sm = maxb;
     int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
     const int xbytes = 2 * p.B * (p.bulk ? st->Cp : ((st->C + 1) & ~1)) * 8;
-    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + st->C * 8 + 512 + 64 + xbytes;
+    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + st->C * 8 + 512 + 64 + 512 + xbytes;
     if (budget < fixed + 4096) budget = fixed + 4096;
     if (budget > max_smem) budget = max_smem;
     if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }
     p.smem_bytes = budget;
-    CC_CUDA(cudaFuncSetAttribute(rows_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-    rows_kernel<NT><<<n_work, NT + 32, budget, stream>>>(p);
+    if (nt == 32) {
+        CC_CUDA(cudaFuncSetAttribute(rows_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+        rows_kernel<32, 8><<<n_work, 64, budget, stream>>>(p);
+    } else {
+        CC_CUDA(cudaFuncSetAttribute(rows_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+        rows_kernel<128, 3><<<n_work, 160, budget, stream>>>(p);
+    }
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaFreeAsync(dwork, stream));
     return CC_OK;

@@ -147,6 +147,7 @@ class DeviceChains(object):
         t['aux_nk'] = z((S_, R), i32)
         t['aux_K'] = z((S_,), i32)
         t['aux_alpha'] = z((S_, Cn), f64)
+        t['aux_K_all'] = z((S_, Cn), i32)
         self.t = t
         self.arena = None
         st = L.cc_state()
@@ -155,10 +156,12 @@ class DeviceChains(object):
         for name in ('Xrm', 'Xcm', 'ctype', 'ncat', 'catoff', 'grids', 'row_alpha_grid',
                      'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha',
                      'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'seq',
-                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_nk', 'aux_K', 'aux_alpha'):
+                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_nk', 'aux_K', 'aux_alpha', 'aux_K_all'):
             setattr(st, name, t[name].data_ptr())
         st.arena = None
         st.arena_bytes = 0
+        st.aux_zr_all = None
+        self.aux_zr_all = None
         self.st = st
         self.lib_calls = collections.Counter()
         self.lib = _CountingLib(L.load(), self.lib_calls)

@@ -84,9 +84,11 @@ typedef struct cc_state {
     uint8_t* movedflag;  /* [S][Vcap][R]                                          */
     double*  colL;       /* [S][C][Vcap+1] column marginal matrix (last = auxiliary view) */
     int32_t* aux_zr;     /* [S][R]   auxiliary-view partition (one column step)   */
-    int32_t* aux_nk;     /* [S][R]   table sizes of that partition                */
+    int32_t* aux_nk;     /* [S][R]   (reserved)                                            */
     int32_t* aux_K;      /* [S]      number of tables                             */
     double*  aux_alpha;  /* [S][C]   alpha drawn for each column's auxiliary view */
+    int32_t* aux_zr_all; /* [S][C][R] every column's auxiliary partition, or NULL when it does not fit */
+    int32_t* aux_K_all;  /* [S][C]   number of tables of each stored partition    */
     void*    arena;      /* per-worker scratch for the auxiliary CRP simulation   */
     int64_t  arena_bytes;
 } cc_state;
@@ -139,8 +141,8 @@ int cc_transition_rows(const cc_state* st, int n_work, const cc_row_work* work /
  * (view.py:99; aidx == NULL: device generator), CRP-prior partition of all rows
  * (view.py:100-103, crp.py:71-81; uniforms u_dev[n][R-1] or device generator),
  * the column's marginal under it -> colL[chain][col][Vcap], aux_alpha.  With
- * write_zr the partition is kept in aux_zr/aux_nk/aux_K of the chain (one
- * column per chain per call).  Needs st->arena. */
+ * write_zr = 1 the partition is kept in aux_zr/aux_K of the chain (one column
+ * per chain per call), with write_zr = 2 in aux_zr_all/aux_K_all.  Needs st->arena. */
 int cc_col_aux(const cc_state* st, int n, const int32_t* chains, const int32_t* cols,
                const int32_t* aidx, const double* u_dev, int write_zr, uint64_t seed,
                uint64_t counter, void* stream);
@@ -165,7 +167,8 @@ int cc_col_scan(const cc_state* st, int n_chains, const int32_t* chains_dev, con
 
 /* Install aux_zr/aux_nk/aux_K of each listed chain as a new view and move the
  * column into it (state.py:1110-1116,1125-1154). */
-int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols, void* stream);
+int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols,
+                   int mode /* 1: aux_zr of the chain, 2: aux_zr_all of the (chain, column) */, void* stream);
 
 /* ---- grid Gibbs on hyperparameters (src/mixtures/dim.py:152-174) ------------ */
 
