@@ -81,10 +81,25 @@ __device__ __forceinline__ double normal_marginal(double N, double sx, double sx
 }
 // G(N): the N-only part of the predictive Z(N+1)-Z(N)-log(2pi)/2 (normal.py:165-173):
 //   predictive(x) = G(N) - log(sn)/2 - ((nun+1)/2) log1p(rn (x-mn)^2 / ((rn+1) sn))
+// lgamma(h + 1/2) - lgamma(h) is evaluated directly: shift h up to >= 16 with
+// Gamma(h+1) = h Gamma(h), then the asymptotic series
+//   1/2 log h - 1/(8h) + 1/(192 h^3) - 1/(640 h^5) + 17/(14336 h^7) - 31/(18432 h^9) + 691/(180224 h^11)
+// (coefficients (2^{1-k} - 2) B_k / (k (k-1)), k = 2,4,..,12; the next term is < 3e-18 at h = 16).
+// Relative error <= 1e-15 against 40-digit arithmetic for h in [1e-2, 3e6]; the reference's
+// difference of two libm lgamma values is itself only good to ~1e-9 at N ~ 1e6.  All logs of G
+// are folded into one.
 __device__ __forceinline__ double normal_G(double N, double r, double nu) {
     double h = 0.5 * (nu + N);
-    double rn = r + N;
-    return lgamma(h + 0.5) - lgamma(h) + 0.5 * log(rn / (rn + 1.0)) - 0.5 * CC_LOGPI;
+    const double rn = r + N;
+    double num = rn + 1.0, den = rn;            // argument of the single log: h' (den/num)^2 rn/(rn+1)
+    double pn = 1.0, pd = 1.0;
+    while (h < 16.0) { pn *= (h + 0.5); pd *= h; h += 1.0; }
+    num *= pn * pn;
+    den *= pd * pd * h;
+    const double ih = 1.0 / h, ih2 = ih * ih;
+    const double poly = ih * (-0.125 + ih2 * (1.0 / 192.0 + ih2 * (-1.0 / 640.0 + ih2 * (17.0 / 14336.0 +
+                        ih2 * (-31.0 / 18432.0 + ih2 * (691.0 / 180224.0))))));
+    return 0.5 * log(den / num) + poly - 0.5 * CC_LOGPI;
 }
 struct NormalCache { double mn, a, cst; };
 __device__ __forceinline__ NormalCache normal_cache(double N, double sx, double sxx, double gN, double m,

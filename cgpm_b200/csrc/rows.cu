@@ -8,19 +8,22 @@
 // One persistent CTA per (chain, view).  The scan over rows is strictly
 // sequential, exactly as in the reference; parallelism inside a step is over
 // (candidate cluster x column).  Warp roles:
-//   * NT consumer threads: groups of G lanes evaluate one candidate cluster
-//     each (lanes over the view's columns, shuffle-reduce), then every warp
-//     redundantly does the max / exp / inclusive-scan / inverse-CDF draw over
-//     the candidates (no second barrier), then threads over columns apply the
-//     move to the sufficient statistics.
+//   * NT consumer threads.  Step 1: groups of G lanes evaluate one candidate
+//     cluster each (lanes over the view's columns, shuffle-reduce).  Step 2:
+//     warp 0 does the max / w*exp / inclusive-scan / inverse-CDF draw over the
+//     candidates while the group that scored the row's own cluster replays the
+//     reference's re-incorporation.  Step 3 (only if the row moves): threads
+//     over columns update the two clusters' tables, one thread the CRP.
 //   * one producer warp: stages the rows of the next batch into shared memory
 //     (whole 16-byte-aligned rows by 1-D bulk copies -- the TMA engine -- or
-//     per-cell cp.async gathers when rows are too wide), together with the
-//     row ids and their current cluster, behind a full/empty mbarrier pair.
+//     per-cell cp.async gathers when rows are too wide), together with the row
+//     ids, their current cluster and their uniform, behind a full/empty
+//     mbarrier pair.
 // The per-(cluster, column) tables (sufficient statistics + the cached
 // predictive constants) live in shared memory when they fit and in global
-// memory (L2) otherwise; the kernel migrates them from shared to global if the
-// number of clusters outgrows shared memory mid-sweep.
+// memory (L2) otherwise; the sweep is compiled once per address space and
+// migrates from the shared to the global variant if the number of clusters
+// outgrows shared memory mid-sweep.
 //
 // Exactness: sufficient statistics are updated with the same IEEE operations,
 // in the same order, as the reference (x*x is rounded before it is added,
@@ -44,22 +47,14 @@ struct RowsParams {
     int B;          // rows per staged batch (<= 32)
     int bulk;       // 1: stage whole rows with cp.async.bulk
     int smem_bytes; // dynamic shared memory given to the CTA
-};
-
-struct Tab {            // table accessor (shared or global)
-    double* f[CC_NFIELD];
-    double* cnt;
-    int kstride;        // elements between clusters in a field
-    int cstride;        // elements between clusters in cnt
-    int global;         // 0: shared-memory tables
+    int prof;       // debug: per-CTA cycles / D / K / moves into st.seq[(chain, view)][0..3]
 };
 
 template <int NT>
-__device__ __forceinline__ void consumer_sync_t() {
+__device__ __forceinline__ void consumer_sync() {
     if (NT == 32) __syncwarp();                       // single consumer warp: no block barrier at all
     else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
-#define consumer_sync(nt) consumer_sync_t<NT>()
 
 // cached predictive constants for the rows kernel: same formulas as normal_cache, with the two
 // divisions replaced by reciprocals (the values feed log-densities only, never the statistics)
@@ -92,6 +87,310 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
     return x;
 }
 
+// Everything a sweep needs, resolved once per CTA.
+struct Ctx {
+    cc_state st;
+    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride;
+    size_t sv;
+    // shared memory
+    uint64_t *bar_full, *bar_empty;
+    int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice
+    int *live, *nk;
+    double* lp;
+    int *col, *cto, *ctype, *ncat;
+    double* hyp;            // [4][D]
+    int *rowidx, *zrow;
+    double *u, *x, *tab;
+    // global
+    int32_t *zr, *moved, *g_cid;
+    uint8_t* movedflag;
+    double alpha;
+    double* trace;
+    int trace_stride;
+    long long trace_off;
+};
+
+// table access, specialised on the address space (GT = tables in global memory)
+template <bool GT>
+struct Tab {
+    const Ctx& c;
+    double* gf[CC_NFIELD];
+    double* gcnt;
+    __device__ __forceinline__ Tab(const Ctx& cx) : c(cx) {
+        if (GT) {
+#pragma unroll
+            for (int f = 0; f < CC_NFIELD; ++f) gf[f] = stat_field(cx.st, cx.s, f);
+            gcnt = cx.st.cnt + (size_t)cx.s * cx.st.Kcap * cx.st.CT;
+        }
+    }
+    __device__ __forceinline__ double& at(int f, int k, int j) const {
+        if (GT) return gf[f][(size_t)k * c.st.C + c.col[j]];
+        return c.tab[(f * c.Kc + k) * c.D + j];
+    }
+    __device__ __forceinline__ double* counts(int k, int j) const {
+        if (GT) return gcnt + (size_t)k * c.st.CT + c.st.catoff[c.col[j]];
+        return c.tab + CC_NFIELD * c.Kc * c.D + k * c.CTv + c.cto[j];
+    }
+    __device__ __forceinline__ int prior() const { return GT ? (c.st.Kcap - 1) : (c.Kc - 1); }
+};
+
+// One pass over rows [i_begin, n).  Returns n when finished, or the index of the row whose
+// move needs a cluster slot that does not fit in shared memory (GT = false only): the caller
+// migrates the tables to global memory and continues there with the same row.
+template <int NT, bool GT>
+__device__ int sweep(const Ctx& c, int i_begin, bool resume) {
+    const Tab<GT> T(c);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int D = c.D, B = c.B, n = c.n, Kcap = c.st.Kcap;
+    int G = 1;
+    while (G < D && G < 32) G <<= 1;
+    const int gid = tid / G, gl = tid & (G - 1), ngroups = NT / G;
+    const int pslot = T.prior();
+    const double* hm = c.hyp, *hr = c.hyp + D, *hs = c.hyp + 2 * D, *hnu = c.hyp + 3 * D;
+
+    for (int i = i_begin; i < n; ++i) {
+        const int b = i / B, slot = i - b * B, buf = b & 1;
+        if (slot == 0 || i == i_begin) mbar_wait(&c.bar_full[buf], (b >> 1) & 1);
+        const int r = c.rowidx[buf * 32 + slot];
+        const int z = c.zrow[buf * 32 + slot];
+        const double* xrow = c.x + (buf * B + slot) * c.xstride;
+        const int K = c.scal[0];
+        const int nkz = c.nk[z];
+        const bool singleton = nkz == 1;
+        const int ncand = K + (singleton ? 0 : 1);
+
+        // a row handed over by the shared-memory sweep was already scored and drawn (steps 1-2)
+        const bool skip12 = resume && i == i_begin;
+        if (!skip12) {
+        // ---- step 1: per-candidate data log-likelihood --------------------------------
+        for (int base = 0; base < ncand; base += ngroups) {      // trip count uniform per warp (full-mask shuffles)
+            const int pc = base + gid;
+            const bool active = pc < ncand;
+            const int k = (active && pc < K) ? c.live[pc] : pslot;
+            const bool own = active && (pc < K) && (k == z);
+            double acc = 0.0;
+            for (int j = gl; active && j < D; j += G) {
+                const double x = xrow[c.bulk ? c.col[j] : j];
+                if (isnan(x)) continue;                                  // dim.py:130-132
+                if (c.ctype[j] == CC_NORMAL) {
+                    const double nu = hnu[j];
+                    if (!own) {
+                        acc += normal_predictive_cached(x, T.at(CC_F_MN, k, j), T.at(CC_F_A, k, j), T.at(CC_F_CST, k, j),
+                                                        T.at(CC_F_N, k, j), nu);
+                    } else {
+                        // view.py:416-419: unincorporate, then score (the re-incorporation is step 2).
+                        // With the row removed the cluster has (N1, sx1, sxx1) -> sn1; with it the
+                        // cached sn (cst = G(N) - log(sn)/2).  Z(N1+1) - Z(N1) of normal.py:165-173 is
+                        // G(N1) + (b1 - 1/2) log sn1 - b1 log sn,  b1 = (nu + N1 + 1)/2: one log.
+                        const double N1 = T.at(CC_F_N, k, j) - 1.0;
+                        const double sx1 = __dsub_rn(T.at(CC_F_SX, k, j), x);
+                        const double sxx1 = __dsub_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
+                        const double m = hm[j], rr = hr[j], ss = hs[j];
+                        const double rn1 = rr + N1;
+                        const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
+                        double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
+                                               __dmul_rn(__dmul_rn(rn1, mn1), mn1));
+                        if (sn1 == 0.0) sn1 = ss;
+                        const double b1 = 0.5 * (nu + N1 + 1.0);
+                        const double logsn = 2.0 * (T.at(CC_F_GN, k, j) - T.at(CC_F_CST, k, j));
+                        acc += T.at(CC_F_GM1, k, j) + (b1 - 0.5) * log(sn1) - b1 * logsn;
+                    }
+                } else {
+                    const double a = hm[j];
+                    const int xi = (int)x, kc = c.ncat[j];
+                    if (pc >= K) acc += log(a) - log(a * kc);            // empty cluster
+                    else {
+                        const double cntx = T.counts(k, j)[xi];
+                        if (!own) acc += log(a + cntx) - T.at(CC_F_CST, k, j);
+                        else acc += log(a + (cntx - 1.0)) - log((T.at(CC_F_N, k, j) - 1.0) + a * kc);
+                    }
+                }
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (gl == 0 && active) {
+                c.lp[pc] = acc;
+                if (own) c.scal[4] = pc;
+            }
+        }
+        consumer_sync<NT>();
+
+        // ---- step 2: warp 0 draws; the own cluster's group re-incorporates the row -----
+        if (tid < 32) {
+            const double uu = c.u[buf * 32 + slot];
+            double mx = -INFINITY;
+            for (int pc = lane; pc < ncand; pc += 32) mx = fmax(mx, c.lp[pc]);
+            int width = 1;
+            while (width < ncand && width < 32) width <<= 1;
+            for (int o = width >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            mx = __shfl_sync(0xffffffffu, mx, 0);
+            auto weight = [&](int pc) -> double {
+                if (pc >= K) return c.alpha;
+                const int k = c.live[pc];
+                if (k == z) return singleton ? c.alpha : (double)(nkz - 1);
+                return (double)c.nk[k];
+            };
+            int choice = -1;
+            if (ncand <= 32) {
+                const double e = (lane < ncand) ? weight(lane) * exp(c.lp[lane] - mx) : 0.0;
+                double inc = e;
+                for (int o = 1; o < width; o <<= 1) {
+                    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                const double tot = __shfl_sync(0xffffffffu, inc, ncand - 1);
+                const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && inc > uu * tot);
+                choice = hit ? (__ffs(hit) - 1) : -1;
+            } else {
+                double carry = 0.0;
+                for (int base = 0; base < ncand; base += 32) {
+                    const int pc = base + lane;
+                    const double e = (pc < ncand) ? weight(pc) * exp(c.lp[pc] - mx) : 0.0;
+                    carry += __shfl_sync(0xffffffffu, warp_incl_scan(e, lane), 31);
+                }
+                const double tot = carry;
+                carry = 0.0;
+                for (int base = 0; base < ncand && choice < 0; base += 32) {
+                    const int pc = base + lane;
+                    const double e = (pc < ncand) ? weight(pc) * exp(c.lp[pc] - mx) : 0.0;
+                    const double inc = warp_incl_scan(e, lane) + carry;
+                    const unsigned hit = __ballot_sync(0xffffffffu, pc < ncand && inc > uu * tot);
+                    if (hit) choice = base + __ffs(hit) - 1;
+                    carry = __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+            if (choice < 0) {                       // NaN / all -inf: keep the row, flag the chain
+                choice = c.scal[4];
+                if (lane == 0) c.scal[7] = CC_ERR_ARG;
+            }
+            if (c.trace && lane == 0) {
+                double* tr = c.trace + c.trace_off + (size_t)i * c.trace_stride;
+                tr[0] = (double)r;
+                tr[1] = (double)ncand;
+                tr[2] = (double)((choice < K) ? c.g_cid[c.live[choice]] : (c.g_cid[c.live[K - 1]] + 1));
+                for (int pc = 0; pc < ncand && pc + 3 < c.trace_stride; ++pc) tr[3 + pc] = c.lp[pc] + log(weight(pc));
+            }
+            if (lane == 0) c.scal[8] = choice;
+        }
+        if (gid == c.scal[4] % ngroups) {
+            // view.py:419: incorporate the row back; the sums may differ from before in the last bit
+            for (int j = gl; j < D; j += G) {
+                if (c.ctype[j] != CC_NORMAL) continue;
+                const double x = xrow[c.bulk ? c.col[j] : j];
+                if (isnan(x)) continue;
+                const double sx0 = T.at(CC_F_SX, z, j), sxx0 = T.at(CC_F_SXX, z, j);
+                const double xx = __dmul_rn(x, x);
+                const double sx2 = __dadd_rn(__dsub_rn(sx0, x), x), sxx2 = __dadd_rn(__dsub_rn(sxx0, xx), xx);
+                if (sx2 != sx0 || sxx2 != sxx0) {
+                    T.at(CC_F_SX, z, j) = sx2;
+                    T.at(CC_F_SXX, z, j) = sxx2;
+                    const NormalCache c2 = normal_cache_fast(T.at(CC_F_N, z, j), sx2, sxx2, T.at(CC_F_GN, z, j), hm[j], hr[j], hs[j], hnu[j]);
+                    T.at(CC_F_MN, z, j) = c2.mn; T.at(CC_F_A, z, j) = c2.a; T.at(CC_F_CST, z, j) = c2.cst;
+                }
+            }
+        }
+        consumer_sync<NT>();
+        }   // !skip12
+
+        // ---- step 3: apply the move (view.py:424-429) -----------------------------------
+        const int ownpos = c.scal[4];
+        const int choice = c.scal[8];
+        bool newc = choice >= K;
+        int zb = newc ? c.scal[2] : c.live[choice];
+        if (newc && zb >= Kcap - 1) {            // no free cluster slot: keep the row, flag the chain
+            if (tid == 0) c.scal[7] = CC_ERR_CAPACITY;
+            newc = false;
+            zb = z;
+        }
+        if (zb != z) {
+            if (!GT && newc && zb >= c.Kc - 1) return i;     // needs the global-memory tables
+            for (int t = tid; t < 2 * D; t += NT) {
+                const int j = (t < D) ? t : t - D;
+                const bool is_old = t < D;
+                if (is_old && singleton) continue;            // the emptied cluster is dropped
+                const double x = xrow[c.bulk ? c.col[j] : j];
+                const int k = is_old ? z : zb;
+                const bool isnan_x = isnan(x);
+                if (c.ctype[j] == CC_NORMAL) {
+                    const double m = hm[j], rr = hr[j], ss = hs[j], nu = hnu[j];
+                    double N, sx, sxx, gN, gM1;
+                    if (is_old) {
+                        if (isnan_x) continue;
+                        N = T.at(CC_F_N, k, j) - 1.0;
+                        sx = __dsub_rn(T.at(CC_F_SX, k, j), x);
+                        sxx = __dsub_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
+                        gN = T.at(CC_F_GM1, k, j);
+                        gM1 = (N >= 1.0) ? normal_G(N - 1.0, rr, nu) : 0.0;
+                    } else if (newc) {
+                        // fresh cluster object: 0 + x, 0 + x*x (normal.py:51-53,64-70)
+                        if (isnan_x) { N = 0.0; sx = 0.0; sxx = 0.0; gN = T.at(CC_F_GN, pslot, j); gM1 = 0.0; }
+                        else {
+                            N = 1.0; sx = __dadd_rn(0.0, x); sxx = __dadd_rn(0.0, __dmul_rn(x, x));
+                            gM1 = T.at(CC_F_GN, pslot, j);
+                            gN = normal_G(1.0, rr, nu);
+                        }
+                    } else {
+                        if (isnan_x) continue;
+                        N = T.at(CC_F_N, k, j) + 1.0;
+                        sx = __dadd_rn(T.at(CC_F_SX, k, j), x);
+                        sxx = __dadd_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
+                        gM1 = T.at(CC_F_GN, k, j);
+                        gN = normal_G(N, rr, nu);
+                    }
+                    const NormalCache cc = normal_cache_fast(N, sx, sxx, gN, m, rr, ss, nu);
+                    T.at(CC_F_N, k, j) = N; T.at(CC_F_SX, k, j) = sx; T.at(CC_F_SXX, k, j) = sxx;
+                    T.at(CC_F_MN, k, j) = cc.mn; T.at(CC_F_A, k, j) = cc.a; T.at(CC_F_CST, k, j) = cc.cst;
+                    T.at(CC_F_GN, k, j) = gN; T.at(CC_F_GM1, k, j) = gM1;
+                } else {
+                    const double a = hm[j];
+                    const int kc = c.ncat[j];
+                    double* cn = T.counts(k, j);
+                    const bool fresh = !is_old && newc;
+                    double N = fresh ? 0.0 : T.at(CC_F_N, k, j);
+                    if (fresh) for (int q = 0; q < kc; ++q) cn[q] = 0.0;
+                    if (isnan_x && !fresh) continue;
+                    if (!isnan_x) {
+                        const int xi = (int)x;
+                        if (is_old) { cn[xi] -= 1.0; N -= 1.0; }
+                        else { cn[xi] += 1.0; N += 1.0; }
+                    }
+                    T.at(CC_F_N, k, j) = N;
+                    T.at(CC_F_CST, k, j) = log(N + a * kc);
+                }
+            }
+            // bookkeeping of the row CRP (crp.py:45-59) by one thread
+            if (tid == 0) {
+                c.zr[r] = zb;
+                const int nm = c.scal[3];
+                c.moved[nm] = r;
+                c.movedflag[r] = 1;
+                c.scal[3] = nm + 1;
+                c.nk[z] = nkz - 1;
+                if (newc) {
+                    c.g_cid[zb] = c.g_cid[c.live[K - 1]] + 1;              // crp.py:142 max(counts)+1
+                    c.live[K] = zb;
+                    c.nk[zb] = 1;
+                    c.scal[0] = K + 1;
+                    int fh = zb + 1;
+                    while (fh < Kcap - 1 && c.nk[fh] != 0) ++fh;
+                    c.scal[2] = fh;
+                } else {
+                    c.nk[zb] += 1;
+                }
+                if (singleton) {
+                    // the emptied cluster leaves the ascending-id list; its slot is free again
+                    for (int q = ownpos; q < K - 1; ++q) c.live[q] = c.live[q + 1];
+                    c.live[K - 1] = -1;
+                    c.scal[0] = K - 1;
+                    if (z < c.scal[2]) c.scal[2] = z;
+                }
+            }
+            consumer_sync<NT>();
+        }
+        if ((slot == B - 1 || i == n - 1) && tid == 0) mbar_arrive(&c.bar_empty[buf]);
+    }
+    return n;
+}
+
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p) {
     const cc_state& st = p.st;
@@ -104,131 +403,122 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     const size_t sv = sv_index(st, s, v);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // ---- fixed shared region --------------------------------------------------
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem_raw);      // [2]
-    uint64_t* bar_empty = bar_full + 2;                               // [2]
-    int* s_scal = reinterpret_cast<int*>(bar_empty + 2);              // [16] scalars
-    // s_scal: 0 K, 1 D, 2 free head, 3 nmoved, 4 own position, 5 global mode, 6 CTv, 7 error
-    int* s_live = s_scal + 16;                                        // [Kcap]
-    int* s_nk = s_live + Kcap;                                        // [Kcap]
-    double* s_lp = reinterpret_cast<double*>(s_nk + Kcap + ((2 * Kcap) & 1)); // [Kcap+1] (8-byte aligned)
-    // ---- view columns -----------------------------------------------------------
-    // count the view's columns (all threads, redundantly cheap) ---------------
+    const long long t_start = clock64();
+    Ctx c;
+    c.st = st; c.s = s; c.v = v; c.n = n; c.B = B; c.bulk = p.bulk; c.sv = sv;
+    // ---- fixed shared region ----------------------------------------------------
+    c.bar_full = reinterpret_cast<uint64_t*>(smem_raw);               // [2]
+    c.bar_empty = c.bar_full + 2;                                     // [2]
+    c.scal = reinterpret_cast<int*>(c.bar_empty + 2);                 // [16]
+    c.live = c.scal + 16;                                             // [Kcap]
+    c.nk = c.live + Kcap;                                             // [Kcap]
+    c.lp = reinterpret_cast<double*>(c.nk + Kcap);                    // [Kcap+1]
     const int32_t* zv = st.zv + (size_t)s * C;
     __shared__ int s_D_tmp;
     if (tid == 0) {
         int D = 0;
-        for (int c = 0; c < C; ++c) D += (zv[c] == v);
+        for (int q = 0; q < C; ++q) D += (zv[q] == v);
         s_D_tmp = D;
-        mbar_init(&bar_full[0], 33); mbar_init(&bar_full[1], 33);
-        mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
+        mbar_init(&c.bar_full[0], 33); mbar_init(&c.bar_full[1], 33);
+        mbar_init(&c.bar_empty[0], 1); mbar_init(&c.bar_empty[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int D = s_D_tmp;
-    double* after_lp = s_lp + (Kcap + 1);
-    int* s_col = reinterpret_cast<int*>(after_lp);                    // [D]
-    int* s_cto = s_col + D;                                           // [D] local count offsets
-    int* s_rowidx = s_cto + D;                                        // [2][32]
-    int* s_zrow = s_rowidx + 64;                                      // [2][32]
-    size_t off = (size_t)((unsigned char*)(s_zrow + 64) - smem_raw);
+    c.D = D;
+    c.hyp = c.lp + (Kcap + 1);                                        // [4][D]
+    c.u = c.hyp + 4 * D;                                              // [2][32]
+    c.col = reinterpret_cast<int*>(c.u + 64);                         // [D]
+    c.cto = c.col + D;                                                // [D]
+    c.ctype = c.cto + D;                                              // [D]
+    c.ncat = c.ctype + D;                                             // [D]
+    c.rowidx = c.ncat + D;                                            // [2][32]
+    c.zrow = c.rowidx + 64;                                           // [2][32]
+    size_t off = (size_t)((unsigned char*)(c.zrow + 64) - smem_raw);
     off = (off + 15) & ~(size_t)15;
-    double* s_u = reinterpret_cast<double*>(smem_raw + off);          // [2][32] the row's uniform
-    off += 64 * sizeof(double);
-    const int xstride = p.bulk ? Cp : ((D + 1) & ~1);
-    double* s_x = reinterpret_cast<double*>(smem_raw + off);          // [2][B][xstride]
-    off += (size_t)2 * B * xstride * sizeof(double);
-    double* s_tab = reinterpret_cast<double*>(smem_raw + off);
+    c.xstride = p.bulk ? Cp : ((D + 1) & ~1);
+    c.x = reinterpret_cast<double*>(smem_raw + off);                  // [2][B][xstride]
+    off += (size_t)2 * B * c.xstride * sizeof(double);
+    c.tab = reinterpret_cast<double*>(smem_raw + off);
     const size_t tab_avail = (p.smem_bytes > (int)off) ? (size_t)p.smem_bytes - off : 0;
 
     if (tid == 0) {
         int j = 0, ct = 0;
-        for (int c = 0; c < C; ++c)
-            if (zv[c] == v) {
-                s_col[j] = c;
-                s_cto[j] = ct;
-                ct += st.ncat[c];
+        for (int q = 0; q < C; ++q)
+            if (zv[q] == v) {
+                c.col[j] = q;
+                c.cto[j] = ct;
+                c.ctype[j] = st.ctype[q];
+                c.ncat[j] = st.ncat[q];
+                ct += st.ncat[q];
                 ++j;
             }
-        s_scal[6] = ct;
-        s_scal[3] = 0;
-        s_scal[7] = 0;
+        c.scal[6] = ct;
+        c.scal[3] = 0;
+        c.scal[7] = 0;
     }
-    // live list / counts ----------------------------------------------------------
     const int K0 = st.nclu[sv];
     int32_t* g_live = st.live + sv * Kcap;
     int32_t* g_nk = st.nk + sv * Kcap;
-    int32_t* g_cid = st.cid + sv * Kcap;
+    c.g_cid = st.cid + sv * Kcap;
     for (int i = tid; i < Kcap; i += blockDim.x) {
-        s_nk[i] = 0;
-        s_live[i] = (i < K0) ? g_live[i] : -1;
+        c.nk[i] = 0;
+        c.live[i] = (i < K0) ? g_live[i] : -1;
     }
     __syncthreads();
-    for (int i = tid; i < K0; i += blockDim.x) s_nk[s_live[i]] = g_nk[s_live[i]];
+    for (int i = tid; i < K0; i += blockDim.x) c.nk[c.live[i]] = g_nk[c.live[i]];
+    for (int e = tid; e < 4 * D; e += blockDim.x) {
+        const int f = e / D, j = e - f * D;
+        c.hyp[e] = st.hyp[((size_t)s * C + c.col[j]) * 4 + f];
+    }
     __syncthreads();
-    const int CTv = s_scal[6];
-    // shared-table capacity: Kc cluster slots (the prior record sits at slot Kc-1)
+    const int CTv = c.scal[6];
+    c.CTv = CTv;
+    c.K0 = K0;
+    // shared-table capacity: Kc cluster slots (the empty-cluster record sits at slot Kc-1)
     const size_t per_cluster = (size_t)(CC_NFIELD * D + CTv) * sizeof(double);
     int Kc = (int)(tab_avail / (per_cluster ? per_cluster : 1));
     if (Kc > Kcap) Kc = Kcap;
-    int maxslot = -1;
+    c.Kc = Kc;
     if (tid == 0) {
-        for (int i = 0; i < K0; ++i) maxslot = max(maxslot, s_live[i]);
+        int maxslot = -1;
+        for (int i = 0; i < K0; ++i) maxslot = max(maxslot, c.live[i]);
         int fh = 0;
-        while (fh < Kcap - 1 && s_nk[fh] != 0) ++fh;
-        s_scal[0] = K0;
-        s_scal[1] = D;
-        s_scal[2] = fh;
-        s_scal[5] = (Kc < 3 || maxslot + 2 > Kc - 1) ? 1 : 0;
+        while (fh < Kcap - 1 && c.nk[fh] != 0) ++fh;
+        c.scal[0] = K0;
+        c.scal[2] = fh;
+        c.scal[5] = (Kc < 3 || maxslot + 2 > Kc - 1) ? 1 : 0;
     }
     __syncthreads();
+    const bool start_global = c.scal[5] != 0;
 
-    Tab T;
-    auto set_tab = [&](int global) {
-        T.global = global;
-        if (global) {
-            for (int f = 0; f < CC_NFIELD; ++f) T.f[f] = stat_field(st, s, f);
-            T.cnt = st.cnt + (size_t)s * Kcap * CT;
-            T.kstride = C;
-            T.cstride = CT;
-        } else {
-            for (int f = 0; f < CC_NFIELD; ++f) T.f[f] = s_tab + (size_t)f * Kc * D;
-            T.cnt = s_tab + (size_t)CC_NFIELD * Kc * D;
-            T.kstride = D;
-            T.cstride = CTv;
-        }
-    };
-    set_tab(s_scal[5]);
-    // slot index of the prior (empty-cluster) record in the active table
-    auto prior_slot = [&]() { return T.global ? (Kcap - 1) : (Kc - 1); };
-    auto jidx = [&](int j) { return T.global ? s_col[j] : j; };
-    auto cidx = [&](int j) { return T.global ? st.catoff[s_col[j]] : s_cto[j]; };
-
-    // load shared tables ---------------------------------------------------------
-    if (!T.global) {
+    // load the shared tables -----------------------------------------------------------
+    if (!start_global) {
         for (int e = tid; e < (K0 + 1) * D; e += blockDim.x) {
             const int pp = e / D, j = e - pp * D;
-            const int gk = (pp < K0) ? s_live[pp] : (Kcap - 1);
+            const int gk = (pp < K0) ? c.live[pp] : (Kcap - 1);
             const int sk = (pp < K0) ? gk : (Kc - 1);
-            const int c = s_col[j];
+            const int q = c.col[j];
 #pragma unroll
             for (int f = 0; f < CC_NFIELD; ++f)
-                T.f[f][(size_t)sk * D + j] = stat_field(st, s, f)[(size_t)gk * C + c];
-            if (st.ctype[c] == CC_CATEGORICAL && pp < K0) {
-                const double* src = st.cnt + ((size_t)s * Kcap + gk) * CT + st.catoff[c];
-                double* dst = T.cnt + (size_t)sk * CTv + s_cto[j];
-                for (int q = 0; q < st.ncat[c]; ++q) dst[q] = src[q];
+                c.tab[(f * Kc + sk) * D + j] = stat_field(st, s, f)[(size_t)gk * C + q];
+            if (c.ctype[j] == CC_CATEGORICAL && pp < K0) {
+                const double* src = st.cnt + ((size_t)s * Kcap + gk) * CT + st.catoff[q];
+                double* dst = c.tab + CC_NFIELD * Kc * D + sk * CTv + c.cto[j];
+                for (int qq = 0; qq < c.ncat[j]; ++qq) dst[qq] = src[qq];
             }
         }
     }
     __syncthreads();
 
-    const double alpha = st.view_alpha[sv];
-    const double* hyp = st.hyp + (size_t)s * C * 4;
-    int32_t* zr = st.zr + sv * R;
+    c.alpha = st.view_alpha[sv];
+    c.zr = st.zr + sv * R;
+    c.moved = st.moved + sv * R;
+    c.movedflag = st.movedflag + sv * R;
+    c.trace = (p.trace && wk.trace_off >= 0) ? p.trace : nullptr;
+    c.trace_off = wk.trace_off;
+    c.trace_stride = p.trace_stride;
     const int32_t* order = st.order + sv * R;
-    int32_t* moved = st.moved + sv * R;
-    uint8_t* movedflag = st.movedflag + sv * R;
     const Philox rng(p.seed);
     const int nbatch = (n + B - 1) / B;
 
@@ -238,9 +528,10 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         uint32_t bits = 1;
         while ((1u << bits) < (uint32_t)n && bits < 31) ++bits;
         const uint4 pkey = rng(p.counter, stream_id(2, s, v));
+        const uint64_t ustream = stream_id(1, s, v);
         for (int b = 0; b < nbatch; ++b) {
             const int buf = b & 1;
-            if (b >= 2) mbar_wait(&bar_empty[buf], ((b >> 1) - 1) & 1);
+            if (b >= 2) mbar_wait(&c.bar_empty[buf], ((b >> 1) - 1) & 1);
             const int i = b * B + lane;
             const bool act = lane < B && i < n;
             int r = 0;
@@ -249,327 +540,114 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
                 if (wk.perm_off >= 0) idx = p.perm[wk.perm_off + i];
                 else idx = (int)keyed_perm((uint32_t)i, (uint32_t)n, bits, pkey);
                 r = wk.perm_is_index ? order[idx] : idx;
-                s_rowidx[buf * 32 + lane] = r;
+                c.rowidx[buf * 32 + lane] = r;
                 double uu;
                 if (wk.u_off >= 0) uu = p.u[wk.u_off + i];
-                else { const uint4 w4 = rng(p.counter * 0x100000000ull + (uint64_t)i, stream_id(1, s, v)); uu = u01_from_words(w4.x, w4.y); }
-                s_u[buf * 32 + lane] = uu;
+                else { const uint4 w4 = rng(p.counter * 0x100000000ull + (uint64_t)i, ustream); uu = u01_from_words(w4.x, w4.y); }
+                c.u[buf * 32 + lane] = uu;
             }
             const int nrows = min(B, n - b * B);
             __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(&bar_full[buf], p.bulk ? (uint32_t)(nrows * Cp * 8) : 0u);
+            if (lane == 0) mbar_arrive_expect_tx(&c.bar_full[buf], p.bulk ? (uint32_t)(nrows * Cp * 8) : 0u);
             __syncwarp();
             if (act) {
-                cp_async_4(&s_zrow[buf * 32 + lane], &zr[r]);
-                double* dst = s_x + (size_t)(buf * B + lane) * xstride;
+                cp_async_4(&c.zrow[buf * 32 + lane], &c.zr[r]);
+                double* dst = c.x + (size_t)(buf * B + lane) * c.xstride;
                 const double* src = st.Xrm + (size_t)r * Cp;
-                if (p.bulk) bulk_g2s(dst, src, (uint32_t)(Cp * 8), &bar_full[buf]);
-                else for (int j = 0; j < D; ++j) cp_async_8(&dst[j], &src[s_col[j]]);
+                if (p.bulk) bulk_g2s(dst, src, (uint32_t)(Cp * 8), &c.bar_full[buf]);
+                else for (int j = 0; j < D; ++j) cp_async_8(&dst[j], &src[c.col[j]]);
             }
-            cp_async_mbar_arrive_noinc(&bar_full[buf]);
+            cp_async_mbar_arrive_noinc(&c.bar_full[buf]);
         }
         return;
     }
 
     // ============================== consumers ===============================
-    const int lane = tid & 31;
-    int G = 1;
-    while (G < D && G < 32) G <<= 1;
-    const int gid = tid / G, gl = tid & (G - 1), ngroups = NT / G;
-
-    for (int i = 0; i < n; ++i) {
-        const int b = i / B, slot = i - b * B, buf = b & 1;
-        if (slot == 0) mbar_wait(&bar_full[buf], (b >> 1) & 1);
-        const int r = s_rowidx[buf * 32 + slot];
-        const int z = s_zrow[buf * 32 + slot];
-        const double* xrow = s_x + (size_t)(buf * B + slot) * xstride;
-        const int K = s_scal[0];
-        const int nkz = s_nk[z];
-        const bool singleton = nkz == 1;
-        const int ncand = K + (singleton ? 0 : 1);
-        const int pslot = prior_slot();
-
-        // ---- per-candidate data log-likelihood ----------------------------------
-        for (int base = 0; base < ncand; base += ngroups) {      // trip count uniform per warp (full-mask shuffles)
-            const int pc = base + gid;
-            const bool active = pc < ncand;
-            const int k = (active && pc < K) ? s_live[pc] : pslot;
-            const bool own = active && (pc < K) && (k == z);
-            double acc = 0.0;
-            for (int j = gl; active && j < D; j += G) {
-                const int c = s_col[j];
-                const double x = xrow[p.bulk ? c : j];
-                if (isnan(x)) continue;                                  // dim.py:130-132
-                const size_t e = (size_t)k * T.kstride + jidx(j);
-                if (st.ctype[c] == CC_NORMAL) {
-                    const double nu = __ldg(&hyp[c * 4 + 3]);
-                    if (!own) {
-                        acc += normal_predictive_cached(x, T.f[CC_F_MN][e], T.f[CC_F_A][e], T.f[CC_F_CST][e],
-                                                        T.f[CC_F_N][e], nu);
-                    } else {
-                        // view.py:416-419: unincorporate, score, incorporate
-                        const double m = __ldg(&hyp[c * 4 + 0]), rr = __ldg(&hyp[c * 4 + 1]), ss = __ldg(&hyp[c * 4 + 2]);
-                        const double N0 = T.f[CC_F_N][e], sx0 = T.f[CC_F_SX][e], sxx0 = T.f[CC_F_SXX][e];
-                        const double xx = __dmul_rn(x, x);
-                        const double N1 = N0 - 1.0, sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
-                        const NormalCache c1 = normal_cache_fast(N1, sx1, sxx1, T.f[CC_F_GM1][e], m, rr, ss, nu);
-                        acc += normal_predictive_cached(x, c1.mn, c1.a, c1.cst, N1, nu);
-                        const double sx2 = __dadd_rn(sx1, x), sxx2 = __dadd_rn(sxx1, xx);
-                        if (sx2 != sx0 || sxx2 != sxx0) {
-                            T.f[CC_F_SX][e] = sx2;
-                            T.f[CC_F_SXX][e] = sxx2;
-                            const NormalCache c2 = normal_cache_fast(N0, sx2, sxx2, T.f[CC_F_GN][e], m, rr, ss, nu);
-                            T.f[CC_F_MN][e] = c2.mn; T.f[CC_F_A][e] = c2.a; T.f[CC_F_CST][e] = c2.cst;
-                        }
-                    }
-                } else {
-                    const double a = __ldg(&hyp[c * 4 + 0]);
-                    const int xi = (int)x;
-                    const int kc = st.ncat[c];
-                    if (pc >= K) {
-                        acc += log(a) - log(a * kc);                     // empty cluster
-                    } else {
-                        const double cntx = T.cnt[(size_t)k * T.cstride + cidx(j) + xi];
-                        if (!own) acc += log(a + cntx) - T.f[CC_F_CST][e];
-                        else acc += log(a + (cntx - 1.0)) - log((T.f[CC_F_N][e] - 1.0) + a * kc);
-                    }
-                }
-            }
-            for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (gl == 0 && active) {
-                s_lp[pc] = acc;
-                if (own) s_scal[4] = pc;
-            }
-        }
-        consumer_sync(NT);
-
-        // ---- draw (every warp redundantly; identical arithmetic) ------------------
-        const double uu = s_u[buf * 32 + slot];
-        double mx = -INFINITY;
-        for (int pc = lane; pc < ncand; pc += 32) mx = fmax(mx, s_lp[pc]);
-        mx = warp_max(mx);
-        auto weight = [&](int pc) -> double {
-            if (pc >= K) return alpha;
-            const int k = s_live[pc];
-            if (k == z) return singleton ? alpha : (double)(nkz - 1);
-            return (double)s_nk[k];
-        };
-        int choice = -1;
-        if (ncand <= 32) {
-            const double e = (lane < ncand) ? weight(lane) * exp(s_lp[lane] - mx) : 0.0;
-            const double inc = warp_incl_scan(e, lane);
-            const double tot = __shfl_sync(0xffffffffu, inc, 31);
-            const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && inc > uu * tot);
-            choice = hit ? (__ffs(hit) - 1) : -1;
-        } else {
-            double carry = 0.0;
-            for (int base = 0; base < ncand; base += 32) {
-                const int pc = base + lane;
-                const double e = (pc < ncand) ? weight(pc) * exp(s_lp[pc] - mx) : 0.0;
-                carry += __shfl_sync(0xffffffffu, warp_incl_scan(e, lane), 31);
-            }
-            const double tot = carry;
-            carry = 0.0;
-            for (int base = 0; base < ncand && choice < 0; base += 32) {
-                const int pc = base + lane;
-                const double e = (pc < ncand) ? weight(pc) * exp(s_lp[pc] - mx) : 0.0;
-                const double inc = warp_incl_scan(e, lane) + carry;
-                const unsigned hit = __ballot_sync(0xffffffffu, pc < ncand && inc > uu * tot);
-                if (hit) choice = base + __ffs(hit) - 1;
-                carry = __shfl_sync(0xffffffffu, inc, 31);
-            }
-        }
-        if (choice < 0) {                       // NaN / all -inf: keep the row, flag the chain
-            choice = s_scal[4];
-            if (tid == 0) s_scal[7] = CC_ERR_ARG;
-        }
-        if (p.trace && wk.trace_off >= 0 && tid == 0) {
-            double* tr = p.trace + wk.trace_off + (size_t)i * p.trace_stride;
-            tr[0] = (double)r;
-            tr[1] = (double)ncand;
-            tr[2] = (double)((choice < K) ? g_cid[s_live[choice]] : (g_cid[s_live[K - 1]] + 1));
-            for (int pc = 0; pc < ncand && pc + 3 < p.trace_stride; ++pc) tr[3 + pc] = s_lp[pc] + log(weight(pc));
-        }
-
-        // ---- apply the move (view.py:424-429) -------------------------------------
-        bool newc = choice >= K;
-        int zb = newc ? s_scal[2] : s_live[choice];
-        const int ownpos = s_scal[4];
-        if (newc && zb >= Kcap - 1) {            // no free cluster slot: keep the row, flag the chain
-            if (tid == 0) s_scal[7] = CC_ERR_CAPACITY;
-            newc = false;
-            zb = z;
-        }
-        const bool move = zb != z;
-        if (move && newc && !T.global && zb >= Kc - 1) {
-            // the new slot does not fit in shared memory: migrate the tables to
-            // global memory (L2) and continue there
+    int done = 0;
+    if (!start_global) {
+        done = sweep<NT, false>(c, 0, false);
+        if (done < n) {
+            // migrate the shared tables to global memory (L2) and continue there with the same row
+            const int K = c.scal[0];
             for (int e = tid; e < K * D; e += NT) {
                 const int pp = e / D, j = e - pp * D;
-                const int k = s_live[pp], c = s_col[j];
+                const int k = c.live[pp], q = c.col[j];
 #pragma unroll
                 for (int f = 0; f < CC_NFIELD; ++f)
-                    stat_field(st, s, f)[(size_t)k * C + c] = T.f[f][(size_t)k * D + j];
-                if (st.ctype[c] == CC_CATEGORICAL) {
-                    double* dst = st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[c];
-                    const double* src = T.cnt + (size_t)k * CTv + s_cto[j];
-                    for (int q = 0; q < st.ncat[c]; ++q) dst[q] = src[q];
+                    stat_field(st, s, f)[(size_t)k * C + q] = c.tab[(f * Kc + k) * D + j];
+                if (c.ctype[j] == CC_CATEGORICAL) {
+                    double* dst = st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[q];
+                    const double* src = c.tab + CC_NFIELD * Kc * D + k * CTv + c.cto[j];
+                    for (int qq = 0; qq < c.ncat[j]; ++qq) dst[qq] = src[qq];
                 }
             }
-            consumer_sync(NT);
-            set_tab(1);
+            __threadfence_block();
+            consumer_sync<NT>();
         }
-        if (move) {
-            const bool del_old = singleton;
-            for (int t = tid; t < 2 * D; t += NT) {
-                const int j = (t < D) ? t : t - D;
-                const bool is_old = t < D;
-                if (is_old && del_old) continue;
-                const int c = s_col[j];
-                const double x = xrow[p.bulk ? c : j];
-                const int k = is_old ? z : zb;
-                const size_t e = (size_t)k * T.kstride + jidx(j);
-                const bool isnan_x = isnan(x);
-                if (st.ctype[c] == CC_NORMAL) {
-                    const double m = __ldg(&hyp[c * 4 + 0]), rr = __ldg(&hyp[c * 4 + 1]), ss = __ldg(&hyp[c * 4 + 2]),
-                                 nu = __ldg(&hyp[c * 4 + 3]);
-                    double N, sx, sxx, gN, gM1;
-                    if (is_old) {
-                        if (isnan_x) continue;
-                        const double xx = __dmul_rn(x, x);
-                        N = T.f[CC_F_N][e] - 1.0;
-                        sx = __dsub_rn(T.f[CC_F_SX][e], x);
-                        sxx = __dsub_rn(T.f[CC_F_SXX][e], xx);
-                        gN = T.f[CC_F_GM1][e];
-                        gM1 = (N >= 1.0) ? normal_G(N - 1.0, rr, nu) : 0.0;
-                    } else if (newc) {
-                        // fresh cluster object: 0 + x, 0 + x*x (normal.py:51-53,64-70)
-                        const size_t ep = (size_t)pslot * T.kstride + jidx(j);
-                        if (isnan_x) { N = 0.0; sx = 0.0; sxx = 0.0; gN = T.f[CC_F_GN][ep]; gM1 = 0.0; }
-                        else {
-                            N = 1.0; sx = __dadd_rn(0.0, x); sxx = __dadd_rn(0.0, __dmul_rn(x, x));
-                            gM1 = T.f[CC_F_GN][ep];
-                            gN = normal_G(1.0, rr, nu);
-                        }
-                    } else {
-                        if (isnan_x) continue;
-                        N = T.f[CC_F_N][e] + 1.0;
-                        sx = __dadd_rn(T.f[CC_F_SX][e], x);
-                        sxx = __dadd_rn(T.f[CC_F_SXX][e], __dmul_rn(x, x));
-                        gM1 = T.f[CC_F_GN][e];
-                        gN = normal_G(N, rr, nu);
-                    }
-                    const NormalCache cc = normal_cache_fast(N, sx, sxx, gN, m, rr, ss, nu);
-                    T.f[CC_F_N][e] = N; T.f[CC_F_SX][e] = sx; T.f[CC_F_SXX][e] = sxx;
-                    T.f[CC_F_MN][e] = cc.mn; T.f[CC_F_A][e] = cc.a; T.f[CC_F_CST][e] = cc.cst;
-                    T.f[CC_F_GN][e] = gN; T.f[CC_F_GM1][e] = gM1;
-                } else {
-                    const double a = __ldg(&hyp[c * 4 + 0]);
-                    const int kc = st.ncat[c];
-                    double* cn = T.cnt + (size_t)k * T.cstride + cidx(j);
-                    const bool fresh = !is_old && newc;
-                    double N = fresh ? 0.0 : T.f[CC_F_N][e];
-                    if (fresh) for (int q = 0; q < kc; ++q) cn[q] = 0.0;
-                    if (isnan_x && !fresh) continue;
-                    if (!isnan_x) {
-                        const int xi = (int)x;
-                        if (is_old) { cn[xi] -= 1.0; N -= 1.0; }
-                        else { cn[xi] += 1.0; N += 1.0; }
-                    }
-                    T.f[CC_F_N][e] = N;
-                    T.f[CC_F_CST][e] = log(N + a * kc);
-                }
-            }
-        }
-        consumer_sync(NT);           // every warp has finished its draw; tables are updated
-        if (move) {
-            // bookkeeping of the row CRP (crp.py:45-59) by one thread
-            if (tid == 0) {
-                zr[r] = zb;
-                const int nm = s_scal[3];
-                moved[nm] = r;
-                movedflag[r] = 1;
-                s_scal[3] = nm + 1;
-                s_nk[z] = nkz - 1;
-                if (newc) {
-                    g_cid[zb] = g_cid[s_live[K - 1]] + 1;                  // crp.py:142 max(counts)+1
-                    s_live[K] = zb;
-                    s_nk[zb] = 1;
-                    s_scal[0] = K + 1;
-                    int fh = zb + 1;
-                    while (fh < Kcap - 1 && s_nk[fh] != 0) ++fh;
-                    s_scal[2] = fh;
-                } else {
-                    s_nk[zb] += 1;
-                }
-                if (singleton) {
-                    // the emptied cluster leaves the ascending-id list; its slot is free again
-                    for (int q = ownpos; q < K - 1; ++q) s_live[q] = s_live[q + 1];
-                    s_live[K - 1] = -1;
-                    s_scal[0] = K - 1;
-                    if (z < s_scal[2]) s_scal[2] = z;
-                }
-            }
-            consumer_sync(NT);
-        }
-        if ((slot == B - 1 || i == n - 1) && tid == 0) mbar_arrive(&bar_empty[buf]);
     }
+    const bool in_global = start_global || done < n;
+    if (in_global) sweep<NT, true>(c, done, !start_global);
 
     // ---- write back ---------------------------------------------------------------
-    consumer_sync(NT);
-    const int K = s_scal[0];
-    if (!T.global) {
+    consumer_sync<NT>();
+    const int K = c.scal[0];
+    if (!in_global) {
         for (int e = tid; e < K * D; e += NT) {
             const int pp = e / D, j = e - pp * D;
-            const int k = s_live[pp], c = s_col[j];
+            const int k = c.live[pp], q = c.col[j];
 #pragma unroll
             for (int f = 0; f < CC_NFIELD; ++f)
-                stat_field(st, s, f)[(size_t)k * C + c] = T.f[f][(size_t)k * D + j];
-            if (st.ctype[c] == CC_CATEGORICAL) {
-                double* dst = st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[c];
-                const double* src = T.cnt + (size_t)k * CTv + s_cto[j];
-                for (int q = 0; q < st.ncat[c]; ++q) dst[q] = src[q];
+                stat_field(st, s, f)[(size_t)k * C + q] = c.tab[(f * Kc + k) * D + j];
+            if (c.ctype[j] == CC_CATEGORICAL) {
+                double* dst = st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[q];
+                const double* src = c.tab + CC_NFIELD * Kc * D + k * CTv + c.cto[j];
+                for (int qq = 0; qq < c.ncat[j]; ++qq) dst[qq] = src[qq];
             }
         }
     }
     for (int i = tid; i < Kcap; i += NT) {
-        g_live[i] = (i < K) ? s_live[i] : -1;
-        g_nk[i] = s_nk[i];
+        g_live[i] = (i < K) ? c.live[i] : -1;
+        g_nk[i] = c.nk[i];
     }
     if (tid == 0) {
         st.nclu[sv] = K;
-        if (s_scal[7]) st.err[s] = s_scal[7];
+        if (c.scal[7]) st.err[s] = c.scal[7];
+        if (p.prof) {
+            int32_t* q = st.seq + sv * R;
+            q[0] = (int)((clock64() - t_start) >> 10); q[1] = D; q[2] = K; q[3] = c.scal[3];
+        }
     }
     // ---- member order of the view's CRP: re-seated rows move to the end, in the
     //      order they were re-seated (OrderedDict pop + re-insert, crp.py:52,55) -----
-    const int nmoved = s_scal[3];
+    const int nmoved = c.scal[3];
     if (nmoved > 0) {
+        const int lane = tid & 31;
         int32_t* ord = st.order + sv * R;
         __shared__ int s_wsum[32];
         __shared__ int s_base;
         if (tid == 0) s_base = 0;
-        consumer_sync(NT);
+        consumer_sync<NT>();
         for (int i0 = 0; i0 < R; i0 += NT) {
             const int i = i0 + tid;
             int rr = -1, keep = 0;
-            if (i < R) { rr = ord[i]; keep = !movedflag[rr]; }
+            if (i < R) { rr = ord[i]; keep = !c.movedflag[rr]; }
             const unsigned bal = __ballot_sync(0xffffffffu, keep);
             const int wpre = __popc(bal & ((1u << lane) - 1u));
             if (lane == 0) s_wsum[tid >> 5] = __popc(bal);
-            consumer_sync(NT);
+            consumer_sync<NT>();
             int wbase = 0;
             for (int w = 0; w < (tid >> 5); ++w) wbase += s_wsum[w];
             const int base = s_base;
-            consumer_sync(NT);
+            consumer_sync<NT>();
             if (keep) ord[base + wbase + wpre] = rr;
             if (tid == NT - 1) s_base = base + wbase + wpre + keep;
-            consumer_sync(NT);
+            consumer_sync<NT>();
         }
         const int base = s_base;
         for (int i = tid; i < nmoved; i += NT) {
-            const int rr = moved[i];
+            const int rr = c.moved[i];
             ord[base + i] = rr;
-            movedflag[rr] = 0;
+            c.movedflag[rr] = 0;
         }
     }
 }
@@ -605,13 +683,13 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     RowsParams p;
     p.st = *st; p.work = dwork; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
     p.seed = seed; p.counter = counter;
+    p.prof = getenv("CGPM_B200_ROWS_PROF") ? 1 : 0;
     // rows are staged whole (bulk copy) when two batches of them stay small
     const int rowbytes = st->Cp * 8;
     p.bulk = (rowbytes <= 4096) ? 1 : 0;
     p.B = 32;
     if (p.bulk) while (p.B > 4 && 2 * p.B * rowbytes > 32 * 1024) p.B >>= 1;
-    // consumer threads: one warp (no block barriers) for narrow views, four warps otherwise;
-    // override with CGPM_B200_ROWS_NT=32|128
+    // consumer threads: four warps by default; CGPM_B200_ROWS_NT=32 selects the single-warp variant
     int nt = 128;
     if (const char* e = getenv("CGPM_B200_ROWS_NT")) nt = atoi(e) == 32 ? 32 : 128;
     // CTAs per SM wanted: enough to co-schedule all work items
@@ -621,7 +699,7 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     if (per_sm > maxb) per_sm = maxb;
     int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
     const int xbytes = 2 * p.B * (p.bulk ? st->Cp : ((st->C + 1) & ~1)) * 8;
-    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + st->C * 8 + 512 + 64 + 512 + xbytes;
+    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + st->C * (32 + 16) + 512 + 64 + 512 + xbytes;
     if (budget < fixed + 4096) budget = fixed + 4096;
     if (budget > max_smem) budget = max_smem;
     if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }

@@ -41,5 +41,15 @@ for it in range(sweeps):
     ms = e0.elapsed_time(e1)
     K = dev.t['nclu'].cpu().numpy()
     print('sweep %d: %.1f ms  %.3g cell-updates/s  K mean %.1f max %d' % (it, ms, R * C * S / ms * 1e3, K[nv > 0].mean(), K.max()))
+import os
+if os.environ.get('CGPM_B200_ROWS_PROF'):
+    seq = dev.t['seq'].cpu().numpy()
+    rec = sorted([(int(seq[w['chain'], w['view'], 0]), int(seq[w['chain'], w['view'], 1]), int(seq[w['chain'], w['view'], 2]), int(seq[w['chain'], w['view'], 3])) for w in work])
+    print('per-CTA (kcycles, D, K, moves): slowest', rec[-8:])
+    print('median', rec[len(rec)//2], 'fastest', rec[:3])
+    import collections
+    byD = collections.defaultdict(list)
+    for kc, D, K, mv in rec: byD[D // 8 * 8].append(kc)
+    print({d: (len(v), int(np.mean(v))) for d, v in sorted(byD.items())})
 dev.check_errors()
 print('score', dev.logpdf_score().cpu().numpy()[:3])
