@@ -44,7 +44,7 @@ struct RowsParams {
     double* trace;
     int trace_stride;
     uint64_t seed, counter;
-    int B;          // rows per staged batch (<= 32)
+    int B;          // rows per staged batch (power of two, <= 32)
     int bulk;       // 1: stage whole rows with cp.async.bulk
     int smem_bytes; // dynamic shared memory given to the CTA
     int prof;       // debug: per-CTA cycles / D / K / moves into st.seq[(chain, view)][0..3]
@@ -125,7 +125,7 @@ struct Tab {
     }
     __device__ __forceinline__ double& at(int f, int k, int j) const {
         if (GT) return gf[f][(size_t)k * c.st.C + c.col[j]];
-        return c.tab[(f * c.Kc + k) * c.D + j];
+        return c.tab[f * (c.Kc * c.D) + k * c.D + j];
     }
     __device__ __forceinline__ double* counts(int k, int j) const {
         if (GT) return gcnt + (size_t)k * c.st.CT + c.st.catoff[c.col[j]];
@@ -148,8 +148,10 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
     const int pslot = T.prior();
     const double* hm = c.hyp, *hr = c.hyp + D, *hs = c.hyp + 2 * D, *hnu = c.hyp + 3 * D;
 
+    const int lgB = 31 - __clz(B);                 // B is a power of two
+    const int gmask = ngroups - 1;                 // so is ngroups
     for (int i = i_begin; i < n; ++i) {
-        const int b = i / B, slot = i - b * B, buf = b & 1;
+        const int b = i >> lgB, slot = i & (B - 1), buf = b & 1;
         if (slot == 0 || i == i_begin) mbar_wait(&c.bar_full[buf], (b >> 1) & 1);
         const int r = c.rowidx[buf * 32 + slot];
         const int z = c.zrow[buf * 32 + slot];
@@ -271,7 +273,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
             }
             if (lane == 0) c.scal[8] = choice;
         }
-        if (gid == c.scal[4] % ngroups) {
+        if (gid == (c.scal[4] & gmask)) {
             // view.py:419: incorporate the row back; the sums may differ from before in the last bit
             for (int j = gl; j < D; j += G) {
                 if (c.ctype[j] != CC_NORMAL) continue;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         const uint64_t ustream = stream_id(1, s, v);
         for (int b = 0; b < nbatch; ++b) {
             const int buf = b & 1;
-            if (b >= 2) mbar_wait(&c.bar_empty[buf], ((b >> 1) - 1) & 1);
+            if (b >= 2) mbar_wait_sleep(&c.bar_empty[buf], ((b >> 1) - 1) & 1);
             const int i = b * B + lane;
             const bool act = lane < B && i < n;
             int r = 0;
