@@ -13,7 +13,9 @@
 //                   (state.py:1125-1154).  One warp per chain.  A move into the
 //                   auxiliary view pauses the chain; the host installs the view
 //                   (install_kernel) and resumes.
+#include <cstdlib>
 #include "cc_common.cuh"
+#include <math_constants.h>
 
 #define CC_MAXCAT 256
 
@@ -40,6 +42,8 @@ struct AuxParams {
     const int32_t* aidx;     // injected grid index per work item, or NULL
     const double* u;         // injected uniforms [n][R-1], or NULL
     int write_zr;
+    int prof;
+    int smem_l1;
     uint64_t seed, counter;
     int32_t* arena;
     size_t worker_stride;    // int32 units
@@ -63,6 +67,17 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
     int32_t* cursor = start + (R + 1);      // [R]
     int32_t* grouped = cursor + R;          // [R]
     const int ntree = R + n1 + n2 + 32;
+    // the upper levels of the count tree are kept in shared memory when they fit (p.smem_l1:
+    // levels 1-3, else levels 2-3); the leaf level stays in the arena (L2)
+    extern __shared__ int32_t s_tree[];
+    {
+        const int per_warp = (p.smem_l1 ? n1 : 0) + n2 + 32;
+        int32_t* sw = s_tree + (size_t)(threadIdx.x >> 5) * per_warp;
+        if (p.smem_l1) { Lv[1] = sw; sw += n1; }
+        Lv[2] = sw;
+        Lv[3] = sw + n2;
+    }
+    const int nup = (p.smem_l1 ? n1 : 0) + n2 + 32;
     const Philox rng(p.seed);
 
     for (int w = worker; w < p.n; w += nworkers) {
@@ -72,8 +87,14 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         if (p.aidx) ai = p.aidx[w];
         else { const uint4 r4 = rng(p.counter, stream_id(4, s, c)); ai = (int)(((uint64_t)r4.x * CC_NGRID) >> 32); }
         const double alpha = st.row_alpha_grid[ai];
+        const long long t0 = clock64();
         // ---- pass 1: sequential CRP-prior seating (crp.py:71-81) -------------------
-        for (int i = lane; i < ntree; i += 32) Lv[0][i] = 0;
+        for (int i = lane; i < (p.smem_l1 ? R : R + n1); i += 32) Lv[0][i] = 0;   // leaf (+ level 1 when it is in the arena)
+        {
+            int32_t* up = p.smem_l1 ? Lv[1] : Lv[2];
+            for (int i = lane; i < nup; i += 32) up[i] = 0;
+        }
+        (void)ntree;
         __syncwarp();
         int K = 1;              // tables so far
         int P = 1;              // this lane's inclusive prefix of the counts of tables 0..31 (table 0 holds row 0)
@@ -101,20 +122,24 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                 const int pk = __shfl_sync(0xffffffffu, packed, l);
                 const int tl = pk & 0x7fffffff;
                 int j;
+                // Tables >= 32 live in a 32-ary tree whose nodes store the INCLUSIVE PREFIX of their
+                // children's counts (entries past the last table hold the node total), so a search is
+                // one load + one ballot per level and an update is `entry[lane] += (lane >= child)`.
                 if (pk < 0) {
                     j = K;                                        // new table (index K)
                     if (K < 32) { if (lane >= K) P += 1; reg_total += 1; }
                     else {
                         const int jp = K - 32;
-                        if (lane == 0) {
-                            if (jp == 32) Lv[1][0] = mem_total;
-                            if (jp == 1024) Lv[2][0] = mem_total;
-                            if (jp == 32768) Lv[3][0] = mem_total;
-                            Lv[0][jp] = 1;
-                            if (jp >= 32) Lv[1][jp >> 5] += 1;
-                            if (jp >= 1024) Lv[2][jp >> 10] += 1;
-                            if (jp >= 32768) Lv[3][jp >> 15] += 1;
-                        }
+                        // a level comes into use when its first node fills up: everything seated so far
+                        // belongs to its child 0
+                        if (jp == 32) Lv[1][lane] = mem_total;
+                        if (jp == 1024) Lv[2][lane] = mem_total;
+                        if (jp == 32768) Lv[3][lane] = mem_total;
+                        __syncwarp();
+                        if (lane >= (jp & 31)) Lv[0][(jp & ~31) + lane] += 1;
+                        if (jp >= 32 && lane >= ((jp >> 5) & 31)) Lv[1][((jp >> 5) & ~31) + lane] += 1;
+                        if (jp >= 1024 && lane >= ((jp >> 10) & 31)) Lv[2][((jp >> 10) & ~31) + lane] += 1;
+                        if (jp >= 32768 && lane >= (jp >> 15)) Lv[3][lane] += 1;
                         mem_total += 1;
                         __syncwarp();
                     }
@@ -130,19 +155,14 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                     const int top = (Kp <= 32) ? 0 : (Kp <= 1024) ? 1 : (Kp <= 32768) ? 2 : 3;
                     int idx = 0;
                     for (int lev = top; lev >= 0; --lev) {
-                        const int size = (lev == 0) ? Kp : (lev == 1) ? ((Kp + 31) >> 5) : (lev == 2) ? ((Kp + 1023) >> 10) : ((Kp + 32767) >> 15);
-                        const int e = idx * 32 + lane;
-                        const int val = (e < size) ? Lv[lev][e] : 0;
-                        const int inc = warp_incl_scan_i(val, lane);
+                        int32_t* node = Lv[lev] + idx * 32;
+                        const int inc = node[lane];
                         unsigned hit = __ballot_sync(0xffffffffu, inc > tr);
-                        if (!hit) {             // unreachable in exact arithmetic; fall on the last occupied entry
-                            const unsigned nz = __ballot_sync(0xffffffffu, val > 0);
-                            hit = nz ? (1u << (31 - __clz(nz))) : 1u;
-                        }
+                        if (!hit) hit = 0x80000000u;      // unreachable in exact arithmetic
                         const int h = __ffs(hit) - 1;
-                        const int excl = __shfl_sync(0xffffffffu, inc - val, h);
-                        tr -= excl;
-                        if (lane == h) Lv[lev][e] = val + 1;
+                        const int excl = __shfl_sync(0xffffffffu, inc, (h + 31) & 31);
+                        if (h > 0) tr -= excl;
+                        if (lane >= h) node[lane] = inc + 1;
                         idx = idx * 32 + h;
                     }
                     __syncwarp();
@@ -154,6 +174,7 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             if (ii < R) z[ii] = zreg;                             // coalesced store of the batch
         }
         __syncwarp();
+        const long long t1 = clock64();
         // ---- pass 2: ordered per-table statistics of column c, marginal ------------
         // counts -> start offsets
         {
@@ -163,7 +184,7 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             for (int b0 = 0; b0 < K; b0 += 32) {
                 const int j = b0 + lane;
                 int cn = 0;
-                if (j < K) cn = (b0 == 0) ? myc : Lv[0][j - 32];
+                if (j < K) cn = (b0 == 0) ? myc : (Lv[0][j - 32] - (((j - 32) & 31) ? Lv[0][j - 33] : 0));
                 const int inc = warp_incl_scan_i(cn, lane);
                 if (j < K) { start[j] = carry + inc - cn; cursor[j] = carry + inc - cn; }
                 carry += __shfl_sync(0xffffffffu, inc, 31);
@@ -193,10 +214,48 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         const int ctype = st.ctype[c], kc = st.ncat[c];
         const double* xc = st.Xcm + (size_t)c * R;
         double lsum = 0.0;
+        const int BIG = 96;       // tables at least this large are summed by the whole warp
         for (int b0 = 0; b0 < K; b0 += 32) {
             const int j = b0 + lane;
-            if (j >= K) continue;
-            const int beg = start[j], end = start[j + 1];
+            const int beg = (j < K) ? start[j] : 0, end = (j < K) ? start[j + 1] : 0;
+            // large tables: the warp gathers 32 members at a time (coalesced for runs of consecutive
+            // rows) and every lane replays the same sequential adds, so the order is unchanged
+            unsigned big = __ballot_sync(0xffffffffu, end - beg >= BIG);
+            while (big) {
+                const int l0 = __ffs(big) - 1;
+                big &= big - 1;
+                const int bb = __shfl_sync(0xffffffffu, beg, l0), ee = __shfl_sync(0xffffffffu, end, l0);
+                double N = 0.0, sx = 0.0, sxx = 0.0;
+                if (ctype == CC_NORMAL) {
+                    for (int i0 = bb; i0 < ee; i0 += 32) {
+                        const int i = i0 + lane;
+                        const double xv = (i < ee) ? xc[grouped[i]] : CUDART_NAN;
+                        const int cntm = min(32, ee - i0);
+                        for (int l = 0; l < cntm; ++l) {
+                            const double v = __shfl_sync(0xffffffffu, xv, l);
+                            if (!isnan(v)) { N += 1.0; sx = __dadd_rn(sx, v); sxx = __dadd_rn(sxx, __dmul_rn(v, v)); }
+                        }
+                    }
+                    if (lane == 0) lsum += normal_marginal(N, sx, sxx, h0, h1, h2, h3);
+                } else {
+                    uint32_t lc[CC_MAXCAT];
+                    for (int q = 0; q < kc; ++q) lc[q] = 0;
+                    for (int i = bb + lane; i < ee; i += 32) {
+                        const double x0 = xc[grouped[i]];
+                        if (!isnan(x0)) lc[(int)x0]++;
+                    }
+                    const double A = kc * h0;
+                    double lg = 0.0;
+                    int Ni = 0;
+                    for (int q = 0; q < kc; ++q) {
+                        const int tq = __reduce_add_sync(0xffffffffu, (int)lc[q]);
+                        Ni += tq;
+                        lg += lgamma((double)tq + h0);
+                    }
+                    if (lane == 0) lsum += lgamma(A) - lgamma(A + (double)Ni) + lg - kc * lgamma(h0);
+                }
+            }
+            if (j >= K || end - beg >= BIG) continue;
             double N = 0.0, sx = 0.0, sxx = 0.0;
             if (ctype == CC_NORMAL) {
                 int i = beg;
@@ -229,6 +288,10 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         if (lane == 0) {
             st.colL[((size_t)s * st.C + c) * (st.Vcap + 1) + st.Vcap] = lsum;
             st.aux_alpha[(size_t)s * st.C + c] = alpha;
+            if (p.prof) {
+                int32_t* q = st.seq + ((size_t)s * st.C + c) * 4;
+                q[0] = (int)((t1 - t0) >> 10); q[1] = (int)((clock64() - t1) >> 10); q[2] = K; q[3] = ai;
+            }
         }
         __syncwarp();
     }
@@ -446,10 +509,15 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     AuxParams p;
     p.st = *st; p.n = n; p.aidx = nullptr; p.u = u_dev; p.write_zr = write_zr; p.seed = seed; p.counter = counter;
     p.arena = (int32_t*)st->arena; p.worker_stride = per;
+    p.prof = getenv("CGPM_B200_AUX_PROF") ? 1 : 0;
     int32_t *dch = nullptr, *dco = nullptr, *dai = nullptr;
     if (to_device(&dch, chains, n, stream) || to_device(&dco, cols, n, stream) || to_device(&dai, aidx, aidx ? n : 0, stream)) return CC_ERR_CUDA;
     p.chains = dch; p.cols = dco; p.aidx = dai;
-    aux_kernel<<<blocks, tpb, 0, stream>>>(p);
+    const int nw = tpb / 32;
+    p.smem_l1 = ((size_t)nw * (n1 + n2 + 32) * 4 <= 56 * 1024) ? 1 : 0;
+    const size_t smem = (size_t)nw * ((p.smem_l1 ? n1 : 0) + n2 + 32) * 4;
+    CC_CUDA(cudaFuncSetAttribute(aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aux_kernel<<<blocks, tpb, smem, stream>>>(p);
     CC_CUDA(cudaGetLastError());
     cudaFreeAsync(dch, stream); cudaFreeAsync(dco, stream);
     if (dai) cudaFreeAsync(dai, stream);
