@@ -472,12 +472,15 @@ class Chains(object):
                 cnt = np.full(len(w_ch), ncols, np.int32)
                 L.check(lib.cc_col_marginals(st, len(w_ch), _p(w_ch), _p(w_vw), _dp(cols_d), _p(off), _p(cnt), ncols, sp()), 'cc_col_marginals')
             self._mirror = None
+            rounds = 0
             while True:
+                rounds += 1
                 L.check(lib.cc_col_scan(st, nch, _dp(ch_d), _dp(cols_d), ncols, _dp(pos_d), _dp(pend_d), None,
                                         seed, C.c_uint64(counter), _dp(ci_off), _dp(ci_adj), _dp(tr_d), ts, sp()), 'cc_col_scan')
                 pend = pend_d.cpu().numpy()
                 idx = np.nonzero(pend >= 0)[0]
                 if len(idx) == 0:
+                    self.last_col_rounds = rounds
                     break
                 b_ch = np.ascontiguousarray(ch_h[idx], dtype=np.int32)
                 b_co = np.ascontiguousarray(perm[idx, pend[idx]], dtype=np.int32)

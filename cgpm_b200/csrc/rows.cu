@@ -617,6 +617,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         if (p.prof) {
             int32_t* q = st.seq + sv * R;
             q[0] = (int)((clock64() - t_start) >> 10); q[1] = D; q[2] = K; q[3] = c.scal[3];
+            q[4] = start_global ? 1 : (in_global ? 2 : 0);      // table mode: shared / global / migrated mid-sweep
         }
     }
     // ---- member order of the view's CRP: re-seated rows move to the end, in the
@@ -702,7 +703,9 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
     const int xbytes = 2 * p.B * (p.bulk ? st->Cp : ((st->C + 1) & ~1)) * 8;
     const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + st->C * (32 + 16) + 512 + 64 + 512 + xbytes;
-    if (budget < fixed + 4096) budget = fixed + 4096;
+    bool forced = false;
+    if (const char* e = getenv("CGPM_B200_ROWS_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) { budget = fixed + kb * 1024; forced = true; } }   // tests: force small tables
+    if (!forced && budget < fixed + 4096) budget = fixed + 4096;
     if (budget > max_smem) budget = max_smem;
     if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }
     p.smem_bytes = budget;

@@ -138,21 +138,23 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
         uint32_t lc[CC_MAXCAT];
         if (act && ctype == CC_CATEGORICAL) for (int q = 0; q < kc; ++q) lc[q] = 0;
         int i = beg;
-        // ordered accumulation; loads are batched 4 deep, adds stay sequential
-        for (; i + 4 <= end; i += 4) {
-            const int r0 = grouped[i], r1 = grouped[i + 1], r2 = grouped[i + 2], r3 = grouped[i + 3];
+        // ordered accumulation: loads are batched 8 deep (independent), the adds stay sequential
+        for (; i + 8 <= end; i += 8) {
+            int rr[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) rr[q] = grouped[i + q];
             if (act) {
-                const double x0 = X[(size_t)r0 * Cp], x1 = X[(size_t)r1 * Cp], x2 = X[(size_t)r2 * Cp], x3 = X[(size_t)r3 * Cp];
+                double xv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) xv[q] = X[(size_t)rr[q] * Cp];
                 if (ctype == CC_NORMAL) {
-                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
-                    if (!isnan(x1)) { N += 1.0; sx = __dadd_rn(sx, x1); sxx = __dadd_rn(sxx, __dmul_rn(x1, x1)); }
-                    if (!isnan(x2)) { N += 1.0; sx = __dadd_rn(sx, x2); sxx = __dadd_rn(sxx, __dmul_rn(x2, x2)); }
-                    if (!isnan(x3)) { N += 1.0; sx = __dadd_rn(sx, x3); sxx = __dadd_rn(sxx, __dmul_rn(x3, x3)); }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (!isnan(xv[q])) { N += 1.0; sx = __dadd_rn(sx, xv[q]); sxx = __dadd_rn(sxx, __dmul_rn(xv[q], xv[q])); }
                 } else {
-                    if (!isnan(x0)) { N += 1.0; lc[(int)x0]++; }
-                    if (!isnan(x1)) { N += 1.0; lc[(int)x1]++; }
-                    if (!isnan(x2)) { N += 1.0; lc[(int)x2]++; }
-                    if (!isnan(x3)) { N += 1.0; lc[(int)x3]++; }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (!isnan(xv[q])) { N += 1.0; lc[(int)xv[q]]++; }
                 }
             }
         }

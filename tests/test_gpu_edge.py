@@ -1,0 +1,122 @@
+"""GPU edge cases against the oracle: global-memory table mode and the mid-sweep
+migration out of shared memory, row / column subsets, Ci constraints, NaN-heavy
+and categorical-only tables, tiny tables."""
+import numpy as np
+import pytest
+
+import crosscat_oracle as co
+from helpers import oracle_suffstats, device_suffstats, assert_suffstats_equal
+from test_gpu_transition import compare
+
+pytestmark = pytest.mark.gpu
+
+
+def pair(X, cct, da, seed, S=2, **kw):
+    from cgpm_b200.engine import Engine, gen_rng
+    okw = {k: v for k, v in kw.items() if k in ('Zv', 'Zrv', 'alpha', 'view_alphas', 'Ci')}
+    eng = Engine(X, num_states=S, rng=gen_rng(seed), cctypes=cct, distargs=da, stream='numpy', **kw)
+    seeds = gen_rng(seed).randint(low=1, high=2 ** 32 - 1, size=S)
+    oracles = [co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(sd), **okw) for sd in seeds]
+    return eng, oracles
+
+
+def test_global_table_mode_and_mid_sweep_migration(monkeypatch):
+    """The per-(cluster, column) tables live in shared memory when they fit.  With the
+    shared tables capped (env override used only here), (1) a 60-column view with 30
+    clusters starts in global-table mode, (2) a 4-column view that grows from 2 to many
+    clusters migrates from shared to global memory mid-sweep.  Both must follow the oracle
+    exactly (partitions, bit-identical statistics)."""
+    from cgpm_b200 import synth
+    monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
+    modes = set()
+    cases = (('global', 60, 64, np.arange(90) % 30, 5.0), ('migrate', 4, 1, np.arange(90) % 2, 150.0))
+    for name, C, kb, Zr, alpha in cases:
+        monkeypatch.setenv('CGPM_B200_ROWS_SMEM_KB', str(kb))
+        cct = ['normal'] * C
+        X, _, _ = synth.gen_table(90, cct, [None] * C, n_views=1, clusters_per_view=3, seed=2)
+        Zv = {c: 0 for c in range(C)}
+        eng, oracles = pair(X, cct, None, 3, S=2, Zv=Zv, Zrv={0: [int(z) for z in Zr]}, view_alphas={0: alpha}, alpha=1.0)
+        compare(eng, oracles, (name, 'init'))
+        for it in range(3):
+            eng.transition(N=1, kernels=['rows'], progress=False)
+            for o in oracles:
+                o.transition(N=1, kernels=['rows'])
+            compare(eng, oracles, (name, it))
+            seq = eng._ch.dev.t['seq'].cpu().numpy()
+            modes |= set(int(seq[s, 0, 4]) for s in range(2))
+    assert {1, 2} <= modes, modes          # both the global start and the mid-sweep migration ran
+
+
+def test_row_and_column_subsets_and_views_argument():
+    from helpers import small_table
+    X, cct, da = small_table(70, 9)
+    eng, oracles = pair(X, cct, da, 9, S=2)
+    rows = [3, 5, 8, 13, 21, 34, 55]
+    eng.transition(N=1, kernels=['rows'], rowids=rows, progress=False)
+    for o in oracles:
+        if o.n_rows != 1:
+            for v in o.views:
+                o.views[v].transition_rows(rows=rows)
+            o._count('rows')
+    compare(eng, oracles, 'rows subset')
+    cols = [4, 1, 2]
+    eng.transition(N=1, kernels=['columns', 'column_hypers'], cols=cols, progress=False)
+    for o in oracles:
+        o.transition_dims(cols=cols)
+        o.transition_dim_hypers(cols=cols)
+    compare(eng, oracles, 'cols subset')
+
+
+def test_independence_constraints_are_respected():
+    from helpers import small_table
+    X, cct, da = small_table(50, 4)
+    Ci = [(0, 2), (4, 5)]
+    Zv = {0: 0, 1: 0, 2: 1, 3: 1, 4: 2, 5: 3}
+    eng, oracles = pair(X, cct, da, 4, S=3, Zv=Zv, Ci=Ci)
+    for it in range(4):
+        eng.transition(N=1, kernels=['columns', 'rows'], progress=False)
+        for o in oracles:
+            o.transition(N=1, kernels=['columns', 'rows'])
+        compare(eng, oracles, ('ci', it))
+        for s in range(3):
+            zv = dict(eng._ch.Zv_items(s))
+            assert zv[0] != zv[2] and zv[4] != zv[5]
+
+
+def test_nan_heavy_categorical_only_and_tiny_tables():
+    from cgpm_b200 import synth
+    cct = ['categorical'] * 4
+    da = [{'k': 2}, {'k': 3}, {'k': 5}, {'k': 2}]
+    X, _, _ = synth.gen_table(40, cct, da, n_views=2, clusters_per_view=2, seed=6, nan_frac=0.3)
+    eng, oracles = pair(X, cct, da, 6, S=2)
+    for it in range(3):
+        eng.transition(N=1, progress=False)
+        for o in oracles:
+            o.transition(N=1)
+        compare(eng, oracles, ('cat', it))
+    # two rows, one column
+    X2 = np.array([[0.5], [1.5]])
+    eng, oracles = pair(X2, ['normal'], None, 7, S=1)
+    eng.transition(N=3, progress=False)
+    for o in oracles:
+        o.transition(N=3)
+    compare(eng, oracles, 'tiny')
+    # all-NaN column next to a regular one
+    X3 = np.column_stack([np.linspace(-1, 1, 12), np.full(12, np.nan)])
+    X3[0, 1] = 0.25
+    eng, oracles = pair(X3, ['normal', 'normal'], None, 8, S=1)
+    eng.transition(N=2, progress=False)
+    for o in oracles:
+        o.transition(N=2)
+    compare(eng, oracles, 'nan column')
+
+
+def test_capacity_error_is_loud():
+    from cgpm_b200 import synth
+    from cgpm_b200._lib import CgpmB200Error
+    from cgpm_b200.engine import Engine, gen_rng
+    X, _, _ = synth.gen_table(64, ['normal'] * 3, [None] * 3, n_views=1, clusters_per_view=2, seed=1)
+    eng = Engine(X, num_states=1, rng=gen_rng(1), cctypes=['normal'] * 3, stream='philox', Kcap=4,
+                 Zv={0: 0, 1: 0, 2: 0}, Zrv={0: [0] * 64}, view_alphas={0: 50.0}, alpha=1.0)
+    with pytest.raises(CgpmB200Error):
+        eng.transition(N=3, kernels=['rows'], progress=False)
