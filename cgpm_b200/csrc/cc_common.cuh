@@ -11,6 +11,7 @@
 
 void cc_set_error(const char* fmt, ...);
 int cc_check_cuda(cudaError_t e, const char* what);
+void cc_prepare_pool();
 #define CC_CUDA(x) do { if (cc_check_cuda((x), #x)) return CC_ERR_CUDA; } while (0)
 
 // ---------------------------------------------------------------------------

@@ -490,6 +490,7 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     if (write_zr == 2 && !st->aux_zr_all) { cc_set_error("cc_col_aux: write_zr=2 needs aux_zr_all"); return CC_ERR_ARG; }
     if (st->R > (1 << 20) + 32) { cc_set_error("cc_col_aux: R > 2^20 not supported by the count tree"); return CC_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     const int R = st->R;
     const size_t n1 = (R + 31) >> 5, n2 = (n1 + 31) >> 5;
     size_t per = (size_t)R + (R + n1 + n2 + 32) + (R + 1) + R + R;
@@ -530,6 +531,7 @@ extern "C" int cc_col_marginals(const cc_state* st, int n_work, const int32_t* c
     if (!st || n_work < 0) { cc_set_error("cc_col_marginals: bad arguments"); return CC_ERR_ARG; }
     if (n_work == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     int32_t *dch = nullptr, *dvw = nullptr, *dof = nullptr, *dcn = nullptr;
     if (to_device(&dch, chains, n_work, stream) || to_device(&dvw, views, n_work, stream)) return CC_ERR_CUDA;
     if (cols_dev) {
@@ -563,6 +565,7 @@ extern "C" int cc_col_install(const cc_state* st, int n, const int32_t* chains, 
     if (!st || n < 0) { cc_set_error("cc_col_install: bad arguments"); return CC_ERR_ARG; }
     if (n == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     int32_t *dch = nullptr, *dco = nullptr;
     if (to_device(&dch, chains, n, stream) || to_device(&dco, cols, n, stream)) return CC_ERR_CUDA;
     if (mode == 2 && !st->aux_zr_all) { cc_set_error("cc_col_install: no stored partitions"); return CC_ERR_ARG; }

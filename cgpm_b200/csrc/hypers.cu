@@ -197,6 +197,7 @@ extern "C" int cc_transition_col_hypers(const cc_state* st, int n, const int32_t
     if (!st || n < 0) { cc_set_error("cc_transition_col_hypers: bad arguments"); return CC_ERR_ARG; }
     if (n == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     HyperParams p;
     p.st = *st; p.n = n; p.seed = seed; p.counter = counter;
     int32_t *dch = nullptr, *dco = nullptr, *dho = nullptr;
@@ -217,6 +218,7 @@ extern "C" int cc_transition_alphas(const cc_state* st, int n, const int32_t* ch
     if (!st || n < 0 || ndraw < 1) { cc_set_error("cc_transition_alphas: bad arguments"); return CC_ERR_ARG; }
     if (n == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     AlphaParams p;
     p.st = *st; p.n = n; p.ndraw = ndraw; p.seed = seed; p.counter = counter;
     int32_t *dch = nullptr, *dvw = nullptr;

@@ -20,3 +20,17 @@ int cc_check_cuda(cudaError_t e, const char* what) {
 
 extern "C" const char* cc_last_error(void) { return g_err; }
 extern "C" int cc_abi_version(void) { return CC_ABI_VERSION; }
+
+// Keep the stream-ordered allocator's memory across synchronisation points: with the default
+// release threshold (0) every cudaMallocAsync after a sync goes back to the driver.
+void cc_prepare_pool() {
+    static int done[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[dev] = 1;
+}

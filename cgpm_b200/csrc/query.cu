@@ -310,6 +310,7 @@ extern "C" int cc_logpdf_bulk(const cc_state* st, int n_chains, const int32_t* c
     if (!st || n_chains < 0 || Q < 0) { cc_set_error("cc_logpdf_bulk: bad arguments"); return CC_ERR_ARG; }
     if (n_chains == 0 || Q == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     QueryParams p;
     p.st = *st; p.n_chains = n_chains; p.Q = Q; p.rowid = rowid_dev; p.qoff = qoff_dev; p.qcol = qcol_dev;
     p.qval = qval_dev; p.qrole = qrole_dev; p.out = out_dev; p.flag = flag_dev;
@@ -333,6 +334,7 @@ extern "C" int cc_simulate_bulk(const cc_state* st, int n_chains, const int32_t*
     if (!st || n_chains < 0 || Q < 0 || max_targets < 1) { cc_set_error("cc_simulate_bulk: bad arguments"); return CC_ERR_ARG; }
     if (n_chains == 0 || Q == 0 || total_samples == 0) return CC_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     SimParams p;
     p.st = *st; p.n_chains = n_chains; p.Q = Q; p.rowid = rowid_dev; p.qoff = qoff_dev; p.qcol = qcol_dev;
     p.qval = qval_dev; p.qrole = qrole_dev; p.soff = soff_dev; p.total_samples = total_samples;

@@ -664,6 +664,7 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     if (n_work == 0) return CC_OK;
     if (st->Kcap > 4096 || st->Kcap < 4) { cc_set_error("cc_transition_rows: Kcap must be in [4, 4096], got %d", st->Kcap); return CC_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     for (int i = 0; i < n_work; ++i) {
         const cc_row_work& w = work[i];
         if (w.chain < 0 || w.chain >= st->S || w.view < 0 || w.view >= st->Vcap || w.n < 0 || w.n > st->R) {

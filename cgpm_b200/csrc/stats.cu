@@ -322,6 +322,7 @@ extern "C" int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains,
                           const uint8_t* d_mask, void* stream_) {
     if (!st) { cc_set_error("cc_rebuild: null state"); return CC_ERR_ARG; }
     cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
     int32_t *dch = nullptr, *dvw = nullptr, *dcount = nullptr;
     int rc = CC_OK;
     if (views == nullptr) {
