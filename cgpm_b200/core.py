@@ -364,7 +364,8 @@ class Chains(object):
         off = 0
         for s in chains:
             for v in self._views_for(s, views, cols):
-                w = dict(chain=s, view=v, n=n, perm_is_index=1 if rows is None else 0)
+                w = dict(chain=s, view=v, n=n, perm_is_index=1 if rows is None else 0,
+                         n_cols=int(self.mirror()['nv'][s][v]))
                 if self.stream == 'numpy':
                     rng = self.rngs[s]
                     perms.append(np.asarray(rng.permutation(R if rows is None else rows), dtype=np.int32))

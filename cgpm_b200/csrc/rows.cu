@@ -47,6 +47,7 @@ struct RowsParams {
     int B;          // rows per staged batch (power of two, <= 32)
     int bulk;       // 1: stage whole rows with cp.async.bulk
     int smem_bytes; // dynamic shared memory given to the CTA
+    int wide;       // 1: very wide views -- per-column hypers / types stay in global memory, tables too
     int prof;       // debug: per-CTA cycles / D / K / moves into st.seq[(chain, view)][0..3]
 };
 
@@ -90,7 +91,7 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
 // Everything a sweep needs, resolved once per CTA.
 struct Ctx {
     cc_state st;
-    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride;
+    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride, wide;
     size_t sv;
     // shared memory
     uint64_t *bar_full, *bar_empty;
@@ -146,7 +147,11 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
     while (G < D && G < 32) G <<= 1;
     const int gid = tid / G, gl = tid & (G - 1), ngroups = NT / G;
     const int pslot = T.prior();
-    const double* hm = c.hyp, *hr = c.hyp + D, *hs = c.hyp + 2 * D, *hnu = c.hyp + 3 * D;
+    // per-column hyperparameters / types: shared memory, or global memory for very wide views
+    const double* ghyp = c.st.hyp + (size_t)c.s * c.st.C * 4;
+    auto H = [&](int f, int j) -> double { return c.wide ? __ldg(&ghyp[c.col[j] * 4 + f]) : c.hyp[f * D + j]; };
+    auto CTYPE = [&](int j) -> int { return c.wide ? c.st.ctype[c.col[j]] : c.ctype[j]; };
+    auto NCAT = [&](int j) -> int { return c.wide ? c.st.ncat[c.col[j]] : c.ncat[j]; };
 
     const int lgB = 31 - __clz(B);                 // B is a power of two
     const int gmask = ngroups - 1;                 // so is ngroups
@@ -174,8 +179,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
             for (int j = gl; active && j < D; j += G) {
                 const double x = xrow[c.bulk ? c.col[j] : j];
                 if (isnan(x)) continue;                                  // dim.py:130-132
-                if (c.ctype[j] == CC_NORMAL) {
-                    const double nu = hnu[j];
+                if (CTYPE(j) == CC_NORMAL) {
+                    const double nu = H(3, j);
                     if (!own) {
                         acc += normal_predictive_cached(x, T.at(CC_F_MN, k, j), T.at(CC_F_A, k, j), T.at(CC_F_CST, k, j),
                                                         T.at(CC_F_N, k, j), nu);
@@ -187,7 +192,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                         const double N1 = T.at(CC_F_N, k, j) - 1.0;
                         const double sx1 = __dsub_rn(T.at(CC_F_SX, k, j), x);
                         const double sxx1 = __dsub_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
-                        const double m = hm[j], rr = hr[j], ss = hs[j];
+                        const double m = H(0, j), rr = H(1, j), ss = H(2, j);
                         const double rn1 = rr + N1;
                         const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
                         double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
@@ -198,8 +203,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                         acc += T.at(CC_F_GM1, k, j) + (b1 - 0.5) * log(sn1) - b1 * logsn;
                     }
                 } else {
-                    const double a = hm[j];
-                    const int xi = (int)x, kc = c.ncat[j];
+                    const double a = H(0, j);
+                    const int xi = (int)x, kc = NCAT(j);
                     if (pc >= K) acc += log(a) - log(a * kc);            // empty cluster
                     else {
                         const double cntx = T.counts(k, j)[xi];
@@ -276,7 +281,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
         if (gid == (c.scal[4] & gmask)) {
             // view.py:419: incorporate the row back; the sums may differ from before in the last bit
             for (int j = gl; j < D; j += G) {
-                if (c.ctype[j] != CC_NORMAL) continue;
+                if (CTYPE(j) != CC_NORMAL) continue;
                 const double x = xrow[c.bulk ? c.col[j] : j];
                 if (isnan(x)) continue;
                 const double sx0 = T.at(CC_F_SX, z, j), sxx0 = T.at(CC_F_SXX, z, j);
@@ -285,7 +290,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                 if (sx2 != sx0 || sxx2 != sxx0) {
                     T.at(CC_F_SX, z, j) = sx2;
                     T.at(CC_F_SXX, z, j) = sxx2;
-                    const NormalCache c2 = normal_cache_fast(T.at(CC_F_N, z, j), sx2, sxx2, T.at(CC_F_GN, z, j), hm[j], hr[j], hs[j], hnu[j]);
+                    const NormalCache c2 = normal_cache_fast(T.at(CC_F_N, z, j), sx2, sxx2, T.at(CC_F_GN, z, j), H(0, j), H(1, j), H(2, j), H(3, j));
                     T.at(CC_F_MN, z, j) = c2.mn; T.at(CC_F_A, z, j) = c2.a; T.at(CC_F_CST, z, j) = c2.cst;
                 }
             }
@@ -312,8 +317,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                 const double x = xrow[c.bulk ? c.col[j] : j];
                 const int k = is_old ? z : zb;
                 const bool isnan_x = isnan(x);
-                if (c.ctype[j] == CC_NORMAL) {
-                    const double m = hm[j], rr = hr[j], ss = hs[j], nu = hnu[j];
+                if (CTYPE(j) == CC_NORMAL) {
+                    const double m = H(0, j), rr = H(1, j), ss = H(2, j), nu = H(3, j);
                     double N, sx, sxx, gN, gM1;
                     if (is_old) {
                         if (isnan_x) continue;
@@ -343,8 +348,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                     T.at(CC_F_MN, k, j) = cc.mn; T.at(CC_F_A, k, j) = cc.a; T.at(CC_F_CST, k, j) = cc.cst;
                     T.at(CC_F_GN, k, j) = gN; T.at(CC_F_GM1, k, j) = gM1;
                 } else {
-                    const double a = hm[j];
-                    const int kc = c.ncat[j];
+                    const double a = H(0, j);
+                    const int kc = NCAT(j);
                     double* cn = T.counts(k, j);
                     const bool fresh = !is_old && newc;
                     double N = fresh ? 0.0 : T.at(CC_F_N, k, j);
@@ -428,13 +433,14 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     __syncthreads();
     const int D = s_D_tmp;
     c.D = D;
-    c.hyp = c.lp + (Kcap + 1);                                        // [4][D]
-    c.u = c.hyp + 4 * D;                                              // [2][32]
+    c.wide = p.wide;
+    c.hyp = c.lp + (Kcap + 1);                                        // [4][D] (not in wide mode)
+    c.u = c.hyp + (p.wide ? 0 : 4 * D);                               // [2][32]
     c.col = reinterpret_cast<int*>(c.u + 64);                         // [D]
-    c.cto = c.col + D;                                                // [D]
-    c.ctype = c.cto + D;                                              // [D]
-    c.ncat = c.ctype + D;                                             // [D]
-    c.rowidx = c.ncat + D;                                            // [2][32]
+    c.cto = c.col + D;                                                // [D]   (these three not in wide mode)
+    c.ctype = c.cto + (p.wide ? 0 : D);                               // [D]
+    c.ncat = c.ctype + (p.wide ? 0 : D);                              // [D]
+    c.rowidx = c.ncat + (p.wide ? 0 : D);                             // [2][32]
     c.zrow = c.rowidx + 64;                                           // [2][32]
     size_t off = (size_t)((unsigned char*)(c.zrow + 64) - smem_raw);
     off = (off + 15) & ~(size_t)15;
@@ -449,9 +455,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         for (int q = 0; q < C; ++q)
             if (zv[q] == v) {
                 c.col[j] = q;
-                c.cto[j] = ct;
-                c.ctype[j] = st.ctype[q];
-                c.ncat[j] = st.ncat[q];
+                if (!p.wide) {
+                    c.cto[j] = ct;
+                    c.ctype[j] = st.ctype[q];
+                    c.ncat[j] = st.ncat[q];
+                }
                 ct += st.ncat[q];
                 ++j;
             }
@@ -469,7 +477,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     }
     __syncthreads();
     for (int i = tid; i < K0; i += blockDim.x) c.nk[c.live[i]] = g_nk[c.live[i]];
-    for (int e = tid; e < 4 * D; e += blockDim.x) {
+    for (int e = tid; !p.wide && e < 4 * D; e += blockDim.x) {
         const int f = e / D, j = e - f * D;
         c.hyp[e] = st.hyp[((size_t)s * C + c.col[j]) * 4 + f];
     }
@@ -489,7 +497,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         while (fh < Kcap - 1 && c.nk[fh] != 0) ++fh;
         c.scal[0] = K0;
         c.scal[2] = fh;
-        c.scal[5] = (Kc < 3 || maxslot + 2 > Kc - 1) ? 1 : 0;
+        c.scal[5] = (p.wide || Kc < 3 || maxslot + 2 > Kc - 1) ? 1 : 0;
     }
     __syncthreads();
     const bool start_global = c.scal[5] != 0;
@@ -688,11 +696,21 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     p.st = *st; p.work = dwork; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
     p.seed = seed; p.counter = counter;
     p.prof = getenv("CGPM_B200_ROWS_PROF") ? 1 : 0;
-    // rows are staged whole (bulk copy) when two batches of them stay small
+    // widest view among the work items (callers that do not know pass 0 -> assume all columns)
+    int dmax = 0;
+    for (int i = 0; i < n_work; ++i) {
+        const int d = work[i].n_cols;
+        if (d <= 0 || d > st->C) { dmax = st->C; break; }
+        if (d > dmax) dmax = d;
+    }
+    // rows are staged whole (bulk copy) when they are short; otherwise only the view's cells
+    // are gathered.  Two batches of B rows (a power of two) must stay within 32 KB.
     const int rowbytes = st->Cp * 8;
     p.bulk = (rowbytes <= 4096) ? 1 : 0;
+    const int stagebytes = p.bulk ? rowbytes : ((dmax + 1) & ~1) * 8;
+    p.wide = (dmax > 1024) ? 1 : 0;
     p.B = 32;
-    if (p.bulk) while (p.B > 4 && 2 * p.B * rowbytes > 32 * 1024) p.B >>= 1;
+    while (p.B > 1 && 2 * p.B * stagebytes > 32 * 1024) p.B >>= 1;
     // consumer threads: four warps by default; CGPM_B200_ROWS_NT=32 selects the single-warp variant
     int nt = 128;
     if (const char* e = getenv("CGPM_B200_ROWS_NT")) nt = atoi(e) == 32 ? 32 : 128;
@@ -702,8 +720,8 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     if (per_sm < 1) per_sm = 1;
     if (per_sm > maxb) per_sm = maxb;
     int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
-    const int xbytes = 2 * p.B * (p.bulk ? st->Cp : ((st->C + 1) & ~1)) * 8;
-    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + st->C * (32 + 16) + 512 + 64 + 512 + xbytes;
+    const int xbytes = 2 * p.B * stagebytes;
+    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + dmax * (p.wide ? 4 : 48) + 512 + 64 + 512 + xbytes;
     bool forced = false;
     if (const char* e = getenv("CGPM_B200_ROWS_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) { budget = fixed + kb * 1024; forced = true; } }   // tests: force small tables
     if (!forced && budget < fixed + 4096) budget = fixed + 4096;

@@ -103,6 +103,8 @@ typedef struct cc_row_work {
     int64_t perm_off;     /* into `perm`, or -1: device pseudo-random permutation of `order` */
     int64_t u_off;        /* into `u`,    or -1: Philox uniforms                  */
     int64_t trace_off;    /* into `trace`, or -1                                  */
+    int32_t n_cols;       /* number of columns of the view if the caller knows it (sizes shared memory), else 0 */
+    int32_t _pad;
 } cc_row_work;
 
 const char* cc_last_error(void);

@@ -120,3 +120,24 @@ def test_capacity_error_is_loud():
                  Zv={0: 0, 1: 0, 2: 0}, Zrv={0: [0] * 64}, view_alphas={0: 50.0}, alpha=1.0)
     with pytest.raises(CgpmB200Error):
         eng.transition(N=3, kernels=['rows'], progress=False)
+
+
+def test_very_wide_views_use_the_wide_mode():
+    """More than 1024 columns in a view: per-column hypers / types and the tables stay in
+    global memory (rows kernel 'wide' mode); results still follow the oracle exactly."""
+    from cgpm_b200 import synth
+    C, R = 1100, 14
+    cct = ['normal'] * C
+    X, _, _ = synth.gen_table(R, cct, [None] * C, n_views=2, clusters_per_view=2, seed=4)
+    Zv = {c: (0 if c < 1060 else 1) for c in range(C)}
+    eng, oracles = pair(X, cct, None, 5, S=1, Zv=Zv, Vcap=8)
+    compare(eng, oracles, 'wide init')
+    for it in range(2):
+        eng.transition(N=1, kernels=['rows'], progress=False)
+        for o in oracles:
+            o.transition(N=1, kernels=['rows'])
+        compare(eng, oracles, ('wide rows', it))
+    eng.transition(N=1, kernels=['columns'], cols=list(range(0, C, 37)), progress=False)
+    for o in oracles:
+        o.transition_dims(cols=list(range(0, C, 37)))
+    compare(eng, oracles, 'wide columns')
