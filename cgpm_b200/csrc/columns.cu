@@ -47,6 +47,7 @@ struct AuxParams {
     uint64_t seed, counter;
     int32_t* arena;
     size_t worker_stride;    // int32 units
+    int* queue;              // device work counter (dynamic assignment of pairs to warps)
 };
 
 __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
@@ -80,7 +81,13 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
     const int nup = (p.smem_l1 ? n1 : 0) + n2 + 32;
     const Philox rng(p.seed);
 
-    for (int w = worker; w < p.n; w += nworkers) {
+    // pairs are handed out dynamically: their cost varies ~5x with the drawn alpha
+    (void)nworkers;
+    for (;;) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(p.queue, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= p.n) break;
         const int s = p.chains[w], c = p.cols[w];
         // ---- alpha of the fresh view: rng.choice(grid) (view.py:99, dim.py:181-183)
         int ai;
@@ -514,13 +521,17 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     int32_t *dch = nullptr, *dco = nullptr, *dai = nullptr;
     if (to_device(&dch, chains, n, stream) || to_device(&dco, cols, n, stream) || to_device(&dai, aidx, aidx ? n : 0, stream)) return CC_ERR_CUDA;
     p.chains = dch; p.cols = dco; p.aidx = dai;
+    int* dq = nullptr;
+    CC_CUDA(cudaMallocAsync(&dq, sizeof(int), stream));
+    CC_CUDA(cudaMemsetAsync(dq, 0, sizeof(int), stream));
+    p.queue = dq;
     const int nw = tpb / 32;
     p.smem_l1 = ((size_t)nw * (n1 + n2 + 32) * 4 <= 56 * 1024) ? 1 : 0;
     const size_t smem = (size_t)nw * ((p.smem_l1 ? n1 : 0) + n2 + 32) * 4;
     CC_CUDA(cudaFuncSetAttribute(aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     aux_kernel<<<blocks, tpb, smem, stream>>>(p);
     CC_CUDA(cudaGetLastError());
-    cudaFreeAsync(dch, stream); cudaFreeAsync(dco, stream);
+    cudaFreeAsync(dch, stream); cudaFreeAsync(dco, stream); cudaFreeAsync(dq, stream);
     if (dai) cudaFreeAsync(dai, stream);
     return CC_OK;
 }
