@@ -31,7 +31,9 @@
 // `+= x`, view.py:416-419), so they are bit-identical for the same sequence of
 // moves.  The predictive is evaluated in the algebraically equal Student-t form
 // (see cc_common.cuh) in fp64.
+#include <algorithm>
 #include <cstdlib>
+#include <vector>
 #include "cc_common.cuh"
 
 namespace {
@@ -98,6 +100,7 @@ struct Ctx {
     int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice
     int *live, *nk;
     double* lp;
+    double* w;              // [Kcap+1] CRP weight of each candidate (written with lp)
     int *col, *cto, *ctype, *ncat;
     double* hyp;            // [4][D]
     int *rowidx, *zrow;
@@ -171,7 +174,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
         if (!skip12) {
         // ---- step 1: per-candidate data log-likelihood --------------------------------
         for (int base = 0; base < ncand; base += ngroups) {      // trip count uniform per warp (full-mask shuffles)
-            const int pc = base + gid;
+            const int pc = base + (gmask - gid);      // low positions -> high groups: keeps warp 0 free for the draw
             const bool active = pc < ncand;
             const int k = (active && pc < K) ? c.live[pc] : pslot;
             const bool own = active && (pc < K) && (k == z);
@@ -216,6 +219,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
             for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (gl == 0 && active) {
                 c.lp[pc] = acc;
+                // crp.py:111-124: n_k, n_k - 1 for the row's own table, alpha for a fresh / re-used singleton table
+                c.w[pc] = (pc >= K) ? c.alpha : own ? (singleton ? c.alpha : (double)(nkz - 1)) : (double)c.nk[k];
                 if (own) c.scal[4] = pc;
             }
         }
@@ -224,30 +229,32 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
         // ---- step 2: warp 0 draws; the own cluster's group re-incorporates the row -----
         if (tid < 32) {
             const double uu = c.u[buf * 32 + slot];
-            double mx = -INFINITY;
-            for (int pc = lane; pc < ncand; pc += 32) mx = fmax(mx, c.lp[pc]);
-            int width = 1;
-            while (width < ncand && width < 32) width <<= 1;
-            for (int o = width >> 1; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            mx = __shfl_sync(0xffffffffu, mx, 0);
-            auto weight = [&](int pc) -> double {
-                if (pc >= K) return c.alpha;
-                const int k = c.live[pc];
-                if (k == z) return singleton ? c.alpha : (double)(nkz - 1);
-                return (double)c.nk[k];
-            };
+            auto weight = [&](int pc) -> double { return c.w[pc]; };
             int choice = -1;
             if (ncand <= 32) {
-                const double e = (lane < ncand) ? weight(lane) * exp(c.lp[lane] - mx) : 0.0;
-                double inc = e;
-                for (int o = 1; o < width; o <<= 1) {
-                    const double t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += t;
+                const double lpv = (lane < ncand) ? c.lp[lane] : -INFINITY;
+                const double wv = (lane < ncand) ? c.w[lane] : 0.0;
+                double mx = lpv;
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                if (ncand > 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+                if (ncand > 8) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 8)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); }
+                double inc = wv * exp(lpv - mx);
+                double t;
+                t = __shfl_up_sync(0xffffffffu, inc, 1); if (lane >= 1) inc += t;
+                t = __shfl_up_sync(0xffffffffu, inc, 2); if (lane >= 2) inc += t;
+                if (ncand > 4) { t = __shfl_up_sync(0xffffffffu, inc, 4); if (lane >= 4) inc += t; }
+                if (ncand > 8) {
+                    t = __shfl_up_sync(0xffffffffu, inc, 8); if (lane >= 8) inc += t;
+                    t = __shfl_up_sync(0xffffffffu, inc, 16); if (lane >= 16) inc += t;
                 }
                 const double tot = __shfl_sync(0xffffffffu, inc, ncand - 1);
                 const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && inc > uu * tot);
                 choice = hit ? (__ffs(hit) - 1) : -1;
             } else {
+                double mx = -INFINITY;
+                for (int pc = lane; pc < ncand; pc += 32) mx = fmax(mx, c.lp[pc]);
+                mx = warp_max(mx);
                 double carry = 0.0;
                 for (int base = 0; base < ncand; base += 32) {
                     const int pc = base + lane;
@@ -278,7 +285,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
             }
             if (lane == 0) c.scal[8] = choice;
         }
-        if (gid == (c.scal[4] & gmask)) {
+        if (gid == gmask - (c.scal[4] & gmask)) {
             // view.py:419: incorporate the row back; the sums may differ from before in the last bit
             for (int j = gl; j < D; j += G) {
                 if (CTYPE(j) != CC_NORMAL) continue;
@@ -434,7 +441,8 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     const int D = s_D_tmp;
     c.D = D;
     c.wide = p.wide;
-    c.hyp = c.lp + (Kcap + 1);                                        // [4][D] (not in wide mode)
+    c.w = c.lp + (Kcap + 1);                                          // [Kcap+1]
+    c.hyp = c.w + (Kcap + 1);                                         // [4][D] (not in wide mode)
     c.u = c.hyp + (p.wide ? 0 : 4 * D);                               // [2][32]
     c.col = reinterpret_cast<int*>(c.u + 64);                         // [D]
     c.cto = c.col + D;                                                // [D]   (these three not in wide mode)
@@ -684,58 +692,97 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
             return CC_ERR_ARG;
         }
     }
+    // Work items are split by view width: views wider than 32 columns get 8 consumer warps
+    // (each candidate cluster needs a full warp or more), the others 4.  The two launches run
+    // concurrently (the second on an internal stream ordered after / before `stream` by events).
+    std::vector<cc_row_work> sorted(work, work + n_work);
+    int n_wide = 0;
+    if (!getenv("CGPM_B200_ROWS_NT")) {
+        std::stable_partition(sorted.begin(), sorted.end(), [](const cc_row_work& w) { return w.n_cols > 32; });
+        for (int i = 0; i < n_work; ++i) n_wide += sorted[i].n_cols > 32;
+    }
     cc_row_work* dwork = nullptr;
     CC_CUDA(cudaMallocAsync(&dwork, sizeof(cc_row_work) * n_work, stream));
-    CC_CUDA(cudaMemcpyAsync(dwork, work, sizeof(cc_row_work) * n_work, cudaMemcpyHostToDevice, stream));
+    CC_CUDA(cudaMemcpyAsync(dwork, sorted.data(), sizeof(cc_row_work) * n_work, cudaMemcpyHostToDevice, stream));
+    CC_CUDA(cudaStreamSynchronize(stream));            // `sorted` is a local; n_work is small
 
     int dev = 0, nsm = 148, max_smem = 0;
     CC_CUDA(cudaGetDevice(&dev));
     CC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     CC_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    RowsParams p;
-    p.st = *st; p.work = dwork; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
-    p.seed = seed; p.counter = counter;
-    p.prof = getenv("CGPM_B200_ROWS_PROF") ? 1 : 0;
-    // widest view among the work items (callers that do not know pass 0 -> assume all columns)
-    int dmax = 0;
-    for (int i = 0; i < n_work; ++i) {
-        const int d = work[i].n_cols;
-        if (d <= 0 || d > st->C) { dmax = st->C; break; }
-        if (d > dmax) dmax = d;
+    static cudaStream_t side[64] = {nullptr};
+    static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
+    if (n_wide > 0 && n_wide < n_work && dev >= 0 && dev < 64 && !side[dev]) {
+        CC_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+        CC_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
+        CC_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
     }
-    // rows are staged whole (bulk copy) when they are short; otherwise only the view's cells
-    // are gathered.  Two batches of B rows (a power of two) must stay within 32 KB.
-    const int rowbytes = st->Cp * 8;
-    p.bulk = (rowbytes <= 4096) ? 1 : 0;
-    const int stagebytes = p.bulk ? rowbytes : ((dmax + 1) & ~1) * 8;
-    p.wide = (dmax > 1024) ? 1 : 0;
-    p.B = 32;
-    while (p.B > 1 && 2 * p.B * stagebytes > 32 * 1024) p.B >>= 1;
-    // consumer threads: four warps by default; CGPM_B200_ROWS_NT=32 selects the single-warp variant
-    int nt = 128;
-    if (const char* e = getenv("CGPM_B200_ROWS_NT")) nt = atoi(e) == 32 ? 32 : 128;
-    // CTAs per SM wanted: enough to co-schedule all work items
-    const int maxb = (nt == 32) ? 8 : 3;
-    int per_sm = (n_work + nsm - 1) / nsm;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > maxb) per_sm = maxb;
-    int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
-    const int xbytes = 2 * p.B * stagebytes;
-    const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 8 + dmax * (p.wide ? 4 : 48) + 512 + 64 + 512 + xbytes;
-    bool forced = false;
-    if (const char* e = getenv("CGPM_B200_ROWS_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) { budget = fixed + kb * 1024; forced = true; } }   // tests: force small tables
-    if (!forced && budget < fixed + 4096) budget = fixed + 4096;
-    if (budget > max_smem) budget = max_smem;
-    if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }
-    p.smem_bytes = budget;
-    if (nt == 32) {
-        CC_CUDA(cudaFuncSetAttribute(rows_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        rows_kernel<32, 8><<<n_work, 64, budget, stream>>>(p);
-    } else {
-        CC_CUDA(cudaFuncSetAttribute(rows_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-        rows_kernel<128, 3><<<n_work, 160, budget, stream>>>(p);
+    int env_nt = 0;
+    if (const char* e = getenv("CGPM_B200_ROWS_NT")) { const int v = atoi(e); env_nt = (v == 32 || v == 64 || v == 256) ? v : 128; }
+
+    auto launch = [&](const cc_row_work* hw, const cc_row_work* dw, int cnt, int nt, int total_ctas, cudaStream_t strm) -> int {
+        RowsParams p;
+        p.st = *st; p.work = dw; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
+        p.seed = seed; p.counter = counter;
+        p.prof = getenv("CGPM_B200_ROWS_PROF") ? 1 : 0;
+        // widest view among the work items (callers that do not know pass 0 -> assume all columns)
+        int dmax = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const int d = hw[i].n_cols;
+            if (d <= 0 || d > st->C) { dmax = st->C; break; }
+            if (d > dmax) dmax = d;
+        }
+        // rows are staged whole (bulk copy) when they are short; otherwise only the view's cells
+        // are gathered.  Two batches of B rows (a power of two) must stay within 32 KB.
+        const int rowbytes = st->Cp * 8;
+        p.bulk = (rowbytes <= 4096) ? 1 : 0;
+        const int stagebytes = p.bulk ? rowbytes : ((dmax + 1) & ~1) * 8;
+        p.wide = (dmax > 1024) ? 1 : 0;
+        p.B = 32;
+        while (p.B > 1 && 2 * p.B * stagebytes > 32 * 1024) p.B >>= 1;
+        // CTAs per SM wanted: enough to co-schedule all work items of both launches
+        const int maxb = (nt == 32) ? 8 : (nt == 64) ? 5 : (nt == 256) ? 2 : 3;
+        int per_sm = (total_ctas + nsm - 1) / nsm;
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > maxb) per_sm = maxb;
+        int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
+        const int xbytes = 2 * p.B * stagebytes;
+        const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 16 + dmax * (p.wide ? 4 : 48) + 512 + 64 + 512 + xbytes;
+        bool forced = false;
+        if (const char* e = getenv("CGPM_B200_ROWS_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) { budget = fixed + kb * 1024; forced = true; } }   // tests: force small tables
+        if (!forced && budget < fixed + 4096) budget = fixed + 4096;
+        if (budget > max_smem) budget = max_smem;
+        if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }
+        p.smem_bytes = budget;
+        if (nt == 32) {
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<32, 8><<<cnt, 64, budget, strm>>>(p);
+        } else if (nt == 64) {
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<64, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<64, 5><<<cnt, 96, budget, strm>>>(p);
+        } else if (nt == 256) {
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<256, 2><<<cnt, 288, budget, strm>>>(p);
+        } else {
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<128, 3><<<cnt, 160, budget, strm>>>(p);
+        }
+        CC_CUDA(cudaGetLastError());
+        return CC_OK;
+    };
+    int rc = CC_OK;
+    if (env_nt) rc = launch(sorted.data(), dwork, n_work, env_nt, n_work, stream);
+    else if (n_wide == 0) rc = launch(sorted.data(), dwork, n_work, 128, n_work, stream);
+    else if (n_wide == n_work) rc = launch(sorted.data(), dwork, n_work, 256, n_work, stream);
+    else {
+        CC_CUDA(cudaEventRecord(ev_fork[dev], stream));
+        CC_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
+        rc = launch(sorted.data(), dwork, n_wide, 256, n_work, side[dev]);
+        if (rc == CC_OK) rc = launch(sorted.data() + n_wide, dwork + n_wide, n_work - n_wide, 128, n_work, stream);
+        CC_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
+        CC_CUDA(cudaStreamWaitEvent(stream, ev_join[dev], 0));
     }
-    CC_CUDA(cudaGetLastError());
+    if (rc != CC_OK) return rc;
     CC_CUDA(cudaFreeAsync(dwork, stream));
     return CC_OK;
 }
