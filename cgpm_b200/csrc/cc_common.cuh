@@ -190,7 +190,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(256);
+        __nanosleep(2000);
     }
 }
 // 1-D bulk copy global -> shared, completion on an mbarrier (TMA engine)
