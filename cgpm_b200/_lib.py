@@ -26,7 +26,7 @@ class cc_state(C.Structure):
         ('ncat', C.c_void_p), ('catoff', C.c_void_p), ('grids', C.c_void_p),
         ('row_alpha_grid', C.c_void_p), ('col_alpha_grid', C.c_void_p),
         ('hyp', C.c_void_p), ('zv', C.c_void_p), ('nv', C.c_void_p),
-        ('view_id', C.c_void_p), ('col_alpha', C.c_void_p), ('view_alpha', C.c_void_p),
+        ('view_id', C.c_void_p), ('col_alpha', C.c_void_p), ('view_alpha', C.c_void_p), ('view_grid', C.c_void_p),
         ('nclu', C.c_void_p), ('live', C.c_void_p), ('cid', C.c_void_p), ('nk', C.c_void_p),
         ('zr', C.c_void_p), ('order', C.c_void_p), ('stat', C.c_void_p), ('cnt', C.c_void_p),
         ('err', C.c_void_p),
@@ -60,6 +60,8 @@ def _declare(lib):
     lib.cc_abi_version.argtypes = []
     lib.cc_rebuild.restype = I
     lib.cc_rebuild.argtypes = [C.POINTER(cc_state), I, P, P, P, P]
+    lib.cc_refresh_tables.restype = I
+    lib.cc_refresh_tables.argtypes = [C.POINTER(cc_state), I, P, P, P]
     lib.cc_logpdf_score.restype = I
     lib.cc_logpdf_score.argtypes = [C.POINTER(cc_state), P, P]
     lib.cc_transition_rows.restype = I
@@ -92,7 +94,7 @@ def _declare(lib):
 OPTIONAL = {}
 
 # every symbol include/cgpm_b200.h declares (checked by tests/test_abi.py)
-SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_logpdf_score',
+SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_refresh_tables', 'cc_logpdf_score',
            'cc_transition_rows', 'cc_col_aux', 'cc_col_marginals', 'cc_col_scan', 'cc_col_install',
            'cc_transition_col_hypers', 'cc_transition_alphas', 'cc_logpdf_bulk', 'cc_simulate_bulk']
 

@@ -27,7 +27,7 @@ def pack_chain(spec, R, C):
         'col_alpha': float(spec['alpha']),
         'view_slots': list(range(len(vids))), 'view_id': [int(v) for v in vids],
         'nv': [int(np.sum(zv == j)) for j in range(len(vids))],
-        'view_alpha': [], 'cid': [], 'nk': [], 'zr': [], 'order': [],
+        'view_alpha': [], 'cid': [], 'nk': [], 'zr': [], 'order': [], 'view_grid': [],
     }
     for vid in vids:
         vw = spec['views'][vid]
@@ -35,6 +35,7 @@ def pack_chain(spec, R, C):
         assert ids.shape == (R,)
         uniq, inv, counts = np.unique(ids, return_inverse=True, return_counts=True)
         out['view_alpha'].append(float(vw['alpha']))
+        out['view_grid'].append(vw.get('grid'))
         out['cid'].append(uniq.astype(np.int32))
         out['nk'].append(counts.astype(np.int32))
         out['zr'].append(inv.astype(np.int32))
@@ -62,7 +63,7 @@ def unpack_chain(dl, views_order=None):
         ids = dl['cid_by_slot'][j][dl['zr'][j]]
         spec['views'][int(vid_of_slot[v])] = {
             'alpha': dl['view_alpha'][j], 'Zr': ids.astype(np.int64),
-            'order': dl['order'][j].copy(), 'slot': v,
+            'order': dl['order'][j].copy(), 'slot': v, 'grid': (dl['view_grid'][j] if 'view_grid' in dl else None),
             'cid': dl['cid'][j], 'nk': dl['nk'][j], 'live': dl['live'][j],
         }
     return spec

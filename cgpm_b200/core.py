@@ -47,7 +47,8 @@ def _dp(t):
 
 class Chains(object):
     def __init__(self, X, outputs=None, cctypes=None, distargs=None, Cd=None, Ci=None,
-                 S=1, stream='philox', device=None, Vcap=None, Kcap=None, seed=0):
+                 S=1, stream='philox', device=None, Vcap=None, Kcap=None, seed=0, grids=None,
+                 row_alpha_grid=None, col_alpha_grid=None):
         X = np.asarray(X, dtype=np.float64)
         if X.ndim != 2:
             raise ValueError('X must be a 2-D table.')
@@ -75,7 +76,8 @@ class Chains(object):
         self.col_index = {c: i for i, c in enumerate(self.outputs)}
         if Vcap is None:
             Vcap = min(Cn, 32) if R * min(Cn, 32) <= (1 << 24) else min(Cn, 16)
-        self.dev = DeviceChains(X, self.ctype, self.ncat, S, Vcap=Vcap, Kcap=Kcap, device=device)
+        self.dev = DeviceChains(X, self.ctype, self.ncat, S, Vcap=Vcap, Kcap=Kcap, device=device, grids=grids,
+                                row_alpha_grid=row_alpha_grid, col_alpha_grid=col_alpha_grid)
         self.R, self.C, self.S = R, Cn, S
         self.rngs = [None] * S
         self.views_order = [[] for _ in range(S)]

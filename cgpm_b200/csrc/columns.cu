@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(256) install_kernel(const cc_state st, int n, 
         const int own = st.zv[(size_t)s * C + c];
         st.nclu[sv] = K;
         st.view_alpha[sv] = st.aux_alpha[(size_t)s * C + c];
+        for (int g = 0; g < CC_NGRID; ++g) st.view_grid[sv * CC_NGRID + g] = st.row_alpha_grid[g];   // view.py:98-99
         view_id[slot] = s_newid;
         nv[slot] = 1;
         st.zv[(size_t)s * C + c] = slot;

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(32) alpha_kernel(const AlphaParams p) {
         const int32_t* nk = st.nk + sv * st.Kcap;
         for (int i = lane; i < Kv; i += 32) { sumlg += lgamma((double)nk[live[i]]); ++K; }
         N = st.R;
-        grid = st.row_alpha_grid;
+        grid = st.view_grid + sv * CC_NGRID;
     }
     sumlg = warp_sum(sumlg);
     K = __reduce_add_sync(0xffffffffu, K);

@@ -286,6 +286,41 @@ __global__ void __launch_bounds__(NT) score_kernel(const cc_state st, double* __
     if (tid == 0) out[s] = total;
 }
 
+// cached constants only (statistics untouched): one thread per (cluster position | empty record, column of the view)
+__global__ void refresh_kernel(const cc_state st, int n_work, const int32_t* __restrict__ chains,
+                               const int32_t* __restrict__ views) {
+    const int w = blockIdx.x;
+    if (w >= n_work) return;
+    const int s = chains[w], v = views[w];
+    const size_t sv = sv_index(st, s, v);
+    const int C = st.C, Kcap = st.Kcap, K = st.nclu[sv];
+    const int32_t* live = st.live + sv * Kcap;
+    for (int e = threadIdx.x; e < (K + 1) * C; e += blockDim.x) {
+        const int pos = e / C, c = e - pos * C;
+        if (st.zv[(size_t)s * C + c] != v) continue;
+        const int k = (pos < K) ? live[pos] : (Kcap - 1);
+        const size_t idx = (size_t)k * C + c;
+        const double* hyp = st.hyp + ((size_t)s * C + c) * 4;
+        if (pos >= K) {
+            stat_field(st, s, CC_F_N)[idx] = 0.0; stat_field(st, s, CC_F_SX)[idx] = 0.0; stat_field(st, s, CC_F_SXX)[idx] = 0.0;
+        }
+        const double N = stat_field(st, s, CC_F_N)[idx];
+        if (st.ctype[c] == CC_NORMAL) {
+            const double gN = normal_G(N, hyp[1], hyp[3]);
+            const double gM1 = (N >= 1.0) ? normal_G(N - 1.0, hyp[1], hyp[3]) : 0.0;
+            const NormalCache cc = normal_cache(N, stat_field(st, s, CC_F_SX)[idx], stat_field(st, s, CC_F_SXX)[idx], gN,
+                                                hyp[0], hyp[1], hyp[2], hyp[3]);
+            stat_field(st, s, CC_F_MN)[idx] = cc.mn;
+            stat_field(st, s, CC_F_A)[idx] = cc.a;
+            stat_field(st, s, CC_F_CST)[idx] = cc.cst;
+            stat_field(st, s, CC_F_GN)[idx] = gN;
+            stat_field(st, s, CC_F_GM1)[idx] = gM1;
+        } else {
+            stat_field(st, s, CC_F_CST)[idx] = log(N + hyp[0] * st.ncat[c]);
+        }
+    }
+}
+
 __global__ void list_views_kernel(const cc_state st, int32_t* chains, int32_t* views, int32_t* count) {
     // enumerate live (chain, view) pairs (single thread; S*Vcap is small)
     if (blockIdx.x || threadIdx.x) return;
@@ -347,6 +382,24 @@ extern "C" int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains,
     if (dvw) cudaFreeAsync(dvw, stream);
     if (dcount) cudaFreeAsync(dcount, stream);
     return rc;
+}
+
+extern "C" int cc_refresh_tables(const cc_state* st, int n_work, const int32_t* chains, const int32_t* views,
+                                 void* stream_) {
+    if (!st || n_work < 0 || (n_work > 0 && (!chains || !views))) { cc_set_error("cc_refresh_tables: bad arguments"); return CC_ERR_ARG; }
+    if (n_work == 0) return CC_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cc_prepare_pool();
+    int32_t *dch = nullptr, *dvw = nullptr;
+    CC_CUDA(cudaMallocAsync(&dch, sizeof(int32_t) * n_work, stream));
+    CC_CUDA(cudaMallocAsync(&dvw, sizeof(int32_t) * n_work, stream));
+    CC_CUDA(cudaMemcpyAsync(dch, chains, sizeof(int32_t) * n_work, cudaMemcpyHostToDevice, stream));
+    CC_CUDA(cudaMemcpyAsync(dvw, views, sizeof(int32_t) * n_work, cudaMemcpyHostToDevice, stream));
+    refresh_kernel<<<n_work, 256, 0, stream>>>(*st, n_work, dch, dvw);
+    CC_CUDA(cudaGetLastError());
+    cudaFreeAsync(dch, stream);
+    cudaFreeAsync(dvw, stream);
+    return CC_OK;
 }
 
 extern "C" int cc_logpdf_score(const cc_state* st, double* out, void* stream_) {

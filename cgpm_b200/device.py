@@ -47,7 +47,7 @@ def crp_grid(n, n_grid=L.NGRID):
 
 
 # CUDA kernels launched per C-ABI call (for the bench's gpu_launches count)
-KERNELS_PER_CALL = {'cc_rebuild': 2, 'cc_logpdf_score': 1, 'cc_transition_rows': 1, 'cc_col_aux': 1,
+KERNELS_PER_CALL = {'cc_rebuild': 2, 'cc_refresh_tables': 1, 'cc_logpdf_score': 1, 'cc_transition_rows': 1, 'cc_col_aux': 1,
                     'cc_col_marginals': 2, 'cc_col_scan': 1, 'cc_col_install': 1,
                     'cc_transition_col_hypers': 1, 'cc_transition_alphas': 1, 'cc_logpdf_bulk': 1,
                     'cc_simulate_bulk': 1}
@@ -75,7 +75,8 @@ class _CountingLib(object):
 class DeviceChains(object):
     """S CrossCat chains over one shared table, resident on one GPU."""
 
-    def __init__(self, X, ctype, ncat, S, Vcap=None, Kcap=None, device=None):
+    def __init__(self, X, ctype, ncat, S, Vcap=None, Kcap=None, device=None, grids=None,
+                 row_alpha_grid=None, col_alpha_grid=None):
         L.load()          # fail loudly when the CUDA extension is missing
         if not torch.cuda.is_available():
             raise L.CgpmB200Error('cgpm_b200 needs a CUDA device (no CPU fallback).')
@@ -106,9 +107,12 @@ class DeviceChains(object):
         self.catoff_h = catoff
         self.CT = int(max(int(ncat.sum()), 1))
         self.X_h = X
-        self.grids_h = np.stack([hyper_grids(X[:, c], ctype[c]) for c in range(Cn)])
-        self.row_alpha_grid_h = crp_grid(R)
-        self.col_alpha_grid_h = crp_grid(Cn)
+        # grids are fixed when a column / CRP is created (dim.py:176-184); callers that edit the
+        # table afterwards (incorporate rows / dims) pass the original ones
+        self.grids_h = np.stack([grids[c] if grids is not None and grids[c] is not None else hyper_grids(X[:, c], ctype[c])
+                                 for c in range(Cn)])
+        self.row_alpha_grid_h = crp_grid(R) if row_alpha_grid is None else np.asarray(row_alpha_grid, dtype=np.float64)
+        self.col_alpha_grid_h = crp_grid(Cn) if col_alpha_grid is None else np.asarray(col_alpha_grid, dtype=np.float64)
         dev = self.device
         f64, i32 = torch.float64, torch.int32
         Xp = np.full((R, self.Cp), np.nan)
@@ -130,6 +134,7 @@ class DeviceChains(object):
         t['view_id'] = torch.full((S_, V), -1, dtype=i32, device=dev)
         t['col_alpha'] = torch.ones((S_,), dtype=f64, device=dev)
         t['view_alpha'] = torch.ones((S_, V), dtype=f64, device=dev)
+        t['view_grid'] = torch.from_numpy(np.tile(self.row_alpha_grid_h, (S_, V, 1))).to(dev)
         t['nclu'] = z((S_, V), i32)
         t['live'] = torch.full((S_, V, K), -1, dtype=i32, device=dev)
         t['cid'] = z((S_, V, K), i32)
@@ -154,7 +159,7 @@ class DeviceChains(object):
         st.R, st.C, st.Cp, st.S = R, Cn, self.Cp, S_
         st.Vcap, st.Kcap, st.CT = V, K, self.CT
         for name in ('Xrm', 'Xcm', 'ctype', 'ncat', 'catoff', 'grids', 'row_alpha_grid',
-                     'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha',
+                     'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha', 'view_grid',
                      'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'seq',
                      'moved', 'movedflag', 'colL', 'aux_zr', 'aux_nk', 'aux_K', 'aux_alpha', 'aux_K_all'):
             setattr(st, name, t[name].data_ptr())
@@ -207,6 +212,10 @@ class DeviceChains(object):
             nv[v] = ch['nv'][j]; view_id[v] = ch['view_id'][j]; valpha[v] = ch['view_alpha'][j]
             nclu[v] = Kv
             live[v, :Kv] = np.arange(Kv); cid[v, :Kv] = ch['cid'][j]; nk[v, :Kv] = ch['nk'][j]
+            if ch.get('view_grid') is not None and ch['view_grid'][j] is not None:
+                t['view_grid'][s, v].copy_(torch.from_numpy(np.asarray(ch['view_grid'][j], dtype=np.float64)))
+            else:
+                t['view_grid'][s, v].copy_(torch.from_numpy(self.row_alpha_grid_h))
             t['zr'][s, v].copy_(torch.from_numpy(ch['zr'][j]))
             t['order'][s, v].copy_(torch.from_numpy(ch['order'][j]))
         t['nv'][s].copy_(torch.from_numpy(nv)); t['view_id'][s].copy_(torch.from_numpy(view_id))
@@ -227,6 +236,8 @@ class DeviceChains(object):
         valpha = t['view_alpha'][s].cpu().numpy()
         out['view_alpha'] = [float(valpha[v]) for v in slots]
         out['col_alpha'] = float(t['col_alpha'][s].item())
+        vg = t['view_grid'][s].cpu().numpy()
+        out['view_grid'] = [vg[v].copy() for v in slots]
         out['zv'] = t['zv'][s].cpu().numpy()
         out['hyp'] = t['hyp'][s].cpu().numpy()
         nclu = t['nclu'][s].cpu().numpy()

@@ -154,6 +154,41 @@ class _Api(object):
         return (z[:, None] == z[None, :]).astype(float)
 
 
+    # ---- incremental edits (state.py:187-320, engine.py:119-174) ---------------------------
+    def _after_edit(self, new):
+        self._ch = new
+
+    def incorporate(self, rowid, observation, inputs=None, multiprocess=1):
+        if inputs:
+            raise ValueError('Cannot incorporate with inputs: %s' % inputs)
+        from . import structure
+        self._after_edit(structure.incorporate(self._ch, rowid, observation))
+
+    def incorporate_bulk(self, rowids, observations, inputs=None, multiprocess=1):
+        for rowid, observation in zip(rowids, observations):
+            self.incorporate(rowid, observation, inputs)
+
+    def unincorporate(self, rowid, multiprocess=1):
+        from . import structure
+        self._after_edit(structure.unincorporate(self._ch, rowid))
+
+    def force_cell(self, rowid, observation, multiprocess=1):
+        from . import structure
+        self._after_edit(structure.force_cell(self._ch, rowid, observation))
+
+    def force_cell_bulk(self, rowids, queries, multiprocess=1):
+        for rowid, query in zip(rowids, queries):
+            self.force_cell(rowid, query)
+
+    def incorporate_dim(self, T, outputs, inputs=None, cctype=None, distargs=None, v=None, multiprocess=1):
+        from . import structure
+        self._after_edit(structure.incorporate_dim(self._ch, T, outputs, inputs, cctype, distargs, v))
+
+    def unincorporate_dim(self, col, multiprocess=1):
+        from . import structure
+        self._after_edit(structure.unincorporate_dim(self._ch, col))
+
+
 class State(_Api):
     """cgpm.crosscat.state.State for one chain (src/crosscat/state.py:44-1284)."""
 
@@ -175,6 +210,10 @@ class State(_Api):
         self.outputs = list(self._ch.outputs)
         self.inputs = []
         self.Cd, self.Ci = self._ch.Cd, self._ch.Ci
+
+    def _after_edit(self, new):
+        self._ch = new
+        self.outputs = list(new.outputs)
 
     # ---- structure ---------------------------------------------------------------
     @property
@@ -320,6 +359,12 @@ class Engine(_Api):
             self._init_from_kwargs(s, gen_rng(seed), kwargs)
         if num_states:
             self._ch.finish_init()
+
+    def _after_edit(self, new):
+        self._ch = new
+        self.X = new.dev.X_h.copy()
+        self._state_kwargs = dict(self._state_kwargs, outputs=list(new.outputs), cctypes=list(new.cctypes),
+                                  distargs=[dict(d) for d in new.distargs])
 
     def _make_chains(self, S, seed):
         kw = self._state_kwargs

@@ -69,6 +69,8 @@ typedef struct cc_state {
     int32_t* view_id;    /* [S][Vcap]   reference view id, -1 = free slot         */
     double*  col_alpha;  /* [S]         column-CRP alpha                          */
     double*  view_alpha; /* [S][Vcap]   row-CRP alpha per view                    */
+    double*  view_grid;  /* [S][Vcap][CC_NGRID] alpha grid of each view's row CRP: fixed when the view is
+                            created from the row count at that time (view.py:98-99) */
     int32_t* nclu;       /* [S][Vcap]   live clusters K                           */
     int32_t* live;       /* [S][Vcap][Kcap] cluster slots in ascending cluster-id order */
     int32_t* cid;        /* [S][Vcap][Kcap] reference cluster id of a slot        */
@@ -119,6 +121,13 @@ int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains /*host*/,
                const int32_t* views /*host*/, const uint8_t* mask /*device [S][C] or NULL:
                rebuild only these columns, state.py:1117-1121 re-incorporates only the
                visited column*/, void* stream);
+
+/* Recompute only the cached predictive constants (and the empty-cluster record) of the
+ * listed views' columns from their sufficient statistics and hypers, leaving the sums
+ * untouched: used after incremental edits (State.incorporate / unincorporate / force_cell,
+ * src/crosscat/state.py:255-315) that update the statistics with the reference's own `+=`. */
+int cc_refresh_tables(const cc_state* st, int n_work, const int32_t* chains /*host*/,
+                      const int32_t* views /*host*/, void* stream);
 
 /* State.logpdf_score (src/crosscat/state.py:384-387): column-CRP marginal +
  * per view [row-CRP marginal + sum of cluster marginals].  out: device [S]. */

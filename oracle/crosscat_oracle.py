@@ -466,6 +466,33 @@ class OView(object):
         for dim in self.dims.values():
             dim.incorporate(self.X[dim.col][rowid], k_new)
 
+    # incremental observation (view.py:149-191) ---------------------------------------
+    def incorporate(self, rowid, values, cluster=None):
+        """view.py:149-172: seat the row (table 0 unless given), add its cells, then one
+        Gibbs step for it when the table was not given."""
+        k = 0 if cluster is None else cluster
+        self.crp.incorporate(rowid, k)
+        for dim in self.dims.values():
+            dim.incorporate(values[dim.col], k)
+        if cluster is None:
+            self.transition_rows(rows=[rowid])
+
+    def unincorporate(self, rowid):
+        """view.py:174-183."""
+        k = self.Zr[rowid]
+        for dim in self.dims.values():
+            dim.unincorporate(self.X[dim.col][rowid] if rowid < len(self.X[dim.col]) else self._popped[dim.col], k)
+        self.crp.unincorporate(rowid)
+        if k not in self.Nk:
+            for dim in self.dims.values():
+                del dim.clusters[k]
+
+    def force_cell(self, rowid, observation):
+        """view.py:186-191 (the cell was NaN: nothing to remove)."""
+        k = self.Zr[rowid]
+        for d, x in observation.items():
+            self.dims[d].incorporate(x, k)
+
     def transition_rows(self, rows=None, trace=None):
         """view.py:247-252."""
         if rows is None:
@@ -612,6 +639,88 @@ class OState(object):
                 del self.views[own]
         else:
             self.views[own].incorporate_dim(dim)
+
+    # incremental structure changes (state.py:187-320) ---------------------------------
+    CRP_ID_VIEW = 10 ** 7
+
+    def incorporate(self, rowid, observation):
+        """state.py:255-283."""
+        if rowid != self.n_rows:
+            raise ValueError('Only contiguous rowids supported: %d' % (rowid,))
+        tokens = {self.CRP_ID_VIEW + v: v for v in self.views}
+        if not all(q in self.outputs or q in tokens for q in observation):
+            raise ValueError('Invalid observation: %s' % observation)
+        if any(math.isnan(v) for v in observation.values()):
+            raise ValueError('Cannot incorporate nan: %s.' % observation)
+        for c in self.outputs:
+            self.X[c].append(observation.get(c, float('nan')))
+        self.n_rows += 1
+        for v in self.views:
+            view = self.views[v]
+            values = {d: self.X[d][rowid] for d in view.dims}
+            view.incorporate(rowid, values, observation.get(self.CRP_ID_VIEW + v))
+
+    def unincorporate(self, rowid):
+        """state.py:285-299."""
+        if rowid != self.n_rows - 1:
+            raise ValueError('Only last rowid may be unincorporated.')
+        if self.n_rows == 1:
+            raise ValueError('Cannot unincorporate last rowid.')
+        popped = {c: self.X[c].pop() for c in self.outputs}
+        self.n_rows -= 1
+        for v in self.views:
+            self.views[v]._popped = popped
+            self.views[v].unincorporate(rowid)
+
+    def force_cell(self, rowid, observation):
+        """state.py:302-315."""
+        if not 0 <= rowid < self.n_rows:
+            raise ValueError('Force observation requires existing rowid.')
+        if not all(math.isnan(self.X[c][rowid]) for c in observation):
+            raise ValueError('Force observations requires NaN cells.')
+        for col, value in observation.items():
+            self.X[col][rowid] = value
+        for col, value in observation.items():
+            self.views[self.Zv[col]].force_cell(rowid, {col: value})
+
+    def incorporate_dim(self, T, outputs, cctype=None, distargs=None, v=None):
+        """state.py:187-236."""
+        if len(T) != self.n_rows:
+            raise ValueError('%d rows are required, received: %d.' % (self.n_rows, len(T)))
+        col = outputs[0]
+        if col in self.outputs:
+            raise ValueError('Specified outputs already exist: %s, %s.' % (outputs, self.outputs))
+        self.X[col] = [float(x) for x in T]
+        self.outputs = self.outputs + [col]
+        self.n_cols += 1
+        transition = [col] if v is None else []
+        v_add = 0 if v is None else v
+        if v_add in self.views:
+            view = self.views[v_add]
+        else:
+            view = OView(self.X, self.n_rows, None, None, self.rng)
+            self.views[v_add] = view
+        dim = ODim(col, cctype, distargs, None, self.X[col], self.rng)
+        view.incorporate_dim(dim)
+        self.crp.incorporate(col, v_add)
+        self.transition_dims(cols=transition)
+        self.transition_dim_hypers(cols=[col])
+
+    def unincorporate_dim(self, col):
+        """state.py:238-253."""
+        if self.n_cols == 1:
+            raise ValueError('State has only one dim, cannot unincorporate.')
+        if col not in self.outputs:
+            raise ValueError('col does not exist: %s' % (col,))
+        v_del = self.Zv[col]
+        delete = self.Nv[v_del] == 1
+        del self.views[v_del].dims[col]
+        self.crp.unincorporate(col)
+        if delete:
+            del self.views[v_del]
+        del self.X[col]
+        self.outputs = [i for i in self.outputs if i != col]
+        self.n_cols -= 1
 
     def transition(self, N=1, kernels=None, trace=None):
         """state.py:727-761,866-905 (N iterations, kernels in caller order)."""

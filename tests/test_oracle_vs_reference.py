@@ -53,3 +53,36 @@ def test_oracle_equals_reference_over_transitions(seed):
         assert o.logpdf_score() == ref.logpdf_score()
     assert o.logpdf(-1, {0: 1.0, 1: 2}, {2: 0.5}) == ref.logpdf(-1, {0: 1.0, 1: 2}, {2: 0.5})
     assert o.rng.random_sample() == ref.rng.random_sample()
+
+
+def test_incremental_edits():
+    """incorporate / unincorporate / force_cell / incorporate_dim / unincorporate_dim
+    (state.py:187-320): oracle == reference, bit for bit, including the stream."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from cgpm.crosscat.state import State
+    X, cct, da = small_table(40, 3)
+    ref = State(X, cctypes=cct, distargs=da, rng=np.random.RandomState(1))
+    o = co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(1))
+
+    def both(f):
+        f(ref)
+        f(o)
+        assert snapshot_oracle(o) == ref_snapshot(ref)
+        assert o.logpdf_score() == ref.logpdf_score()
+
+    def tr(kernels, N=1):
+        return lambda s: s.transition(N=N, kernels=kernels, **({'progress': False} if isinstance(s, State) else {}))
+    both(tr(['rows', 'columns']))
+    both(lambda s: s.incorporate(40, {0: 1.5, 1: 2, 3: 0}))
+    both(lambda s: s.incorporate(41, {2: -0.5, 5: 3.0, 4: 0.1}))
+    both(lambda s: s.force_cell(41, {0: 0.25}))
+    both(tr(['rows', 'column_hypers']))
+    both(lambda s: s.unincorporate(41))
+    T = list(np.random.RandomState(9).normal(size=41))
+    both(lambda s: s.incorporate_dim(T, [77], cctype='normal', distargs=None))
+    both(lambda s: s.incorporate_dim([float(i % 3) for i in range(41)], [78], cctype='categorical', distargs={'k': 3}, v=9))
+    both(tr(['rows', 'columns', 'alpha', 'view_alphas', 'column_hypers'], N=2))
+    both(lambda s: s.unincorporate_dim(2))
+    both(tr(['rows', 'columns']))
+    assert o.rng.random_sample() == ref.rng.random_sample()
