@@ -154,6 +154,83 @@ class _Api(object):
         return (z[:, None] == z[None, :]).astype(float)
 
 
+    # ---- ensemble queries built on the query kernels -----------------------
+    def _row_similarity(self, s, row0, row1, cols=None):
+        """state.py:580-584: fraction of the views of `cols` in which the rows share a cluster."""
+        views = self._views(s)
+        zv = self._Zv(s)
+        vids = set(zv[c] for c in (cols if cols is not None else self._ch.outputs))
+        return float(np.mean([views[v].Zr(row0) == views[v].Zr(row1) for v in vids]))
+
+    def _row_similarity_pairwise(self, s, cols=None):
+        """state.py:586-594, evaluated on the device partitions."""
+        import torch
+        ch = self._ch
+        m = ch.mirror()
+        cidx = [ch.col_index[c] for c in cols] if cols is not None else list(range(ch.C))
+        slots = sorted(set(int(m['zv'][s][i]) for i in cidx))
+        acc = torch.zeros((ch.R, ch.R), dtype=torch.float64, device=ch.dev.device)
+        for v in slots:
+            z = ch.dev.t['zr'][s, v]
+            acc += (z[:, None] == z[None, :]).to(torch.float64)
+        return (acc / len(slots)).cpu().numpy()
+
+    def _relevance_probability(self, s, rowid_target, rowid_query, col, hypotheticals=None):
+        """state.py:599-633 without hypothetical rows."""
+        if hypotheticals:
+            raise NotImplementedError('cgpm_b200: relevance_probability with hypothetical rows is out of scope.')
+        if col not in self._ch.col_index:
+            raise ValueError('Unknown column: %s' % (col,))
+        view = self._views(s)[self._Zv(s)[col]]
+        return int(all(view.Zr(rowid_target) == view.Zr(rq) for rq in rowid_query)) if rowid_query else 0
+
+    def _mutual_information(self, s, col0, col1, constraints=None, T=None, N=None):
+        """state.py:638-722 for non-composite states: the connected components are the views."""
+        from . import query
+        constraints = dict(constraints or {})
+        if any(c in constraints for c in col0 + col1):
+            raise ValueError('Target and constraints columns must be disjoint.')
+        if any(c in col1 for c in col0) and set(col0) != set(col1):
+            raise ValueError('Targets must match exactly or be disjoint.')
+        zv = self._Zv(s)
+        blocks = {}
+        for c in col0:
+            blocks.setdefault(zv[c], ([], [], {}))[0].append(c)
+        for c in col1:
+            blocks.setdefault(zv[c], ([], [], {}))[1].append(c)
+        for c, x in constraints.items():
+            blocks.setdefault(zv[c], ([], [], {}))[2][c] = x
+        N = N or 100
+        T = T or 100
+        ch = self._ch
+
+        def lp(targets_list, const):
+            n = len(targets_list)
+            return np.asarray(query.logpdf_bulk(ch, [s], [-1] * n, targets_list, [const] * n)[0])
+
+        def estimator(c0, c1, const):
+            if set(c0) != set(c1):
+                samples = query.simulate_bulk(ch, [s], [-1], [c0 + c1], [const], [N])[0][0]
+                pxy = lp(samples, const)
+                px = lp([{c: smp[c] for c in c0} for smp in samples], const)
+                py = lp([{c: smp[c] for c in c1} for smp in samples], const)
+                return float((pxy.sum() - px.sum() - py.sum()) / N)
+            samples = query.simulate_bulk(ch, [s], [-1], [c0], [const], [N])[0][0]
+            return float(-lp([{c: smp[c] for c in c0} for smp in samples], const).sum() / N)
+
+        total = 0.0
+        for c0, c1, const in blocks.values():
+            if not (c0 and c1):
+                continue
+            e_const = {e: x for e, x in const.items() if x is not None}
+            m_const = [e for e, x in const.items() if x is None]
+            if not m_const:
+                total += estimator(c0, c1, const)
+                continue
+            m_samples = query.simulate_bulk(ch, [s], [-1], [m_const], [{}], [T])[0][0]
+            total += sum(estimator(c0, c1, dict(e_const, **smp)) for smp in m_samples) / float(T)
+        return total
+
     # ---- incremental edits (state.py:187-320, engine.py:119-174) ---------------------------
     def _after_edit(self, new):
         self._ch = new
@@ -298,6 +375,18 @@ class State(_Api):
     def dependence_probability_pairwise(self, colnos=None):
         return self._dependence_probability_pairwise(0, colnos)
 
+    def row_similarity(self, row0, row1, cols=None):
+        return self._row_similarity(0, row0, row1, cols)
+
+    def row_similarity_pairwise(self, cols=None):
+        return self._row_similarity_pairwise(0, cols)
+
+    def relevance_probability(self, rowid_target, rowid_query, col, hypotheticals=None):
+        return self._relevance_probability(0, rowid_target, rowid_query, col, hypotheticals)
+
+    def mutual_information(self, col0, col1, constraints=None, T=None, N=None, progress=None):
+        return self._mutual_information(0, col0, col1, constraints, T, N)
+
     def logpdf(self, rowid, targets, constraints=None, inputs=None, accuracy=None):
         return self._ch.logpdf_bulk([0], [rowid], [targets], [constraints or {}])[0][0]
 
@@ -420,6 +509,26 @@ class Engine(_Api):
     def dependence_probability_pairwise(self, colnos=None, statenos=None, multiprocess=1):
         statenos = statenos or range(self.num_states())
         return [self._dependence_probability_pairwise(s, colnos) for s in statenos]
+
+    def row_similarity(self, row0, row1, cols=None, statenos=None, multiprocess=1):
+        statenos = statenos or range(self.num_states())
+        return [self._row_similarity(s, row0, row1, cols) for s in statenos]
+
+    def row_similarity_pairwise(self, cols=None, statenos=None, multiprocess=1):
+        statenos = statenos or range(self.num_states())
+        return [self._row_similarity_pairwise(s, cols) for s in statenos]
+
+    def relevance_probability(self, rowid_target, rowid_query, col, hypotheticals=None, statenos=None,
+                              multiprocess=1):
+        statenos = statenos or range(self.num_states())
+        return [self._relevance_probability(s, rowid_target, rowid_query, col, hypotheticals) for s in statenos]
+
+    def mutual_information(self, col0, col1, constraints=None, T=None, N=None, progress=None, statenos=None,
+                           multiprocess=1):
+        """engine.py:253-263: one estimate per state."""
+        self._seed_states()
+        statenos = statenos or range(self.num_states())
+        return [self._mutual_information(s, col0, col1, constraints, T, N) for s in statenos]
 
     def _likelihood_weighted_integrate(self, logpdfs, rowid, constraints=None, inputs=None, statenos=None,
                                        multiprocess=1):

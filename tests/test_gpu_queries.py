@@ -140,3 +140,38 @@ def test_metadata_round_trip_and_reference_schema():
     eng.drop_state(0)
     assert eng.num_states() == 3
     eng.transition(N=1, progress=False)
+
+
+def test_row_similarity_relevance_and_mutual_information():
+    """SURVEY 8(f) rank 4, built on the query kernels."""
+    X, cct, da, eng, oracles = make(n_rows=100, seed=51, S=2, iters=6)
+    for s, o in enumerate(oracles):
+        views = set(o.Zv[c] for c in o.outputs)
+        ref = np.mean([o.views[v].Zr[3] == o.views[v].Zr[7] for v in views])
+        assert eng.row_similarity(3, 7)[s] == ref
+        P = eng.row_similarity_pairwise()[s]
+        assert P.shape == (100, 100) and np.allclose(np.diag(P), 1.0) and P[3, 7] == ref and np.allclose(P, P.T)
+        v = o.Zv[0]
+        same = [r for r in range(100) if o.views[v].Zr[r] == o.views[v].Zr[5]][:3]
+        assert eng.relevance_probability(5, same, 0)[s] == 1
+    # mutual information: zero across views, positive entropy, and close to a brute-force
+    # integral of the oracle's densities for a dependent pair of normal columns
+    st = eng.get_state(0)
+    o = oracles[0]
+    zv = o.Zv
+    normal_cols = [c for c in range(len(cct)) if cct[c] == 'normal']
+    dep = [(a, b) for a in normal_cols for b in normal_cols if a < b and zv[a] == zv[b]]
+    ind = [(a, b) for a in normal_cols for b in normal_cols if a < b and zv[a] != zv[b]]
+    if ind:
+        assert st.mutual_information([ind[0][0]], [ind[0][1]], N=50) == 0
+    assert st.mutual_information([normal_cols[0]], [normal_cols[0]], N=200) > 0          # entropy
+    if dep:
+        a, b = dep[0]
+        est = np.mean([st.mutual_information([a], [b], N=2000) for _ in range(3)])
+        xa = X[:, a][~np.isnan(X[:, a])]; xb = X[:, b][~np.isnan(X[:, b])]
+        ga = np.linspace(xa.min() - 4, xa.max() + 4, 70); gb = np.linspace(xb.min() - 4, xb.max() + 4, 70)
+        pa = np.array([o.logpdf(-1, {a: x}) for x in ga]); pb = np.array([o.logpdf(-1, {b: y}) for y in gb])
+        pab = np.array([[o.logpdf(-1, {a: x, b: y}) for y in gb] for x in ga])
+        w = (ga[1] - ga[0]) * (gb[1] - gb[0])
+        ref = float(np.sum(np.exp(pab) * (pab - pa[:, None] - pb[None, :])) * w)
+        assert abs(est - ref) < 0.12 + 0.15 * abs(ref), (est, ref)
