@@ -62,6 +62,8 @@ def _declare(lib):
     lib.cc_rebuild.argtypes = [C.POINTER(cc_state), I, P, P, P, P]
     lib.cc_refresh_tables.restype = I
     lib.cc_refresh_tables.argtypes = [C.POINTER(cc_state), I, P, P, P]
+    lib.cc_check_state.restype = I
+    lib.cc_check_state.argtypes = [C.POINTER(cc_state), P, P]
     lib.cc_logpdf_score.restype = I
     lib.cc_logpdf_score.argtypes = [C.POINTER(cc_state), P, P]
     lib.cc_transition_rows.restype = I
@@ -94,7 +96,7 @@ def _declare(lib):
 OPTIONAL = {}
 
 # every symbol include/cgpm_b200.h declares (checked by tests/test_abi.py)
-SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_refresh_tables', 'cc_logpdf_score',
+SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_refresh_tables', 'cc_check_state', 'cc_logpdf_score',
            'cc_transition_rows', 'cc_col_aux', 'cc_col_marginals', 'cc_col_scan', 'cc_col_install',
            'cc_transition_col_hypers', 'cc_transition_alphas', 'cc_logpdf_bulk', 'cc_simulate_bulk']
 

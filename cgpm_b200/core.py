@@ -253,8 +253,34 @@ class Chains(object):
             print('\rCompleted: %d iterations in %f seconds.' % (iters, time.time() - start))
         return iters
 
+    CHECK_CODES = {1: 'nv is not the histogram of zv', 2: 'live view without id', 3: 'column in no view',
+                   4: 'non-positive CRP alpha', 5: 'cluster count out of range', 6: 'invalid or repeated live slot',
+                   7: 'live cluster without members', 8: 'cluster ids not ascending', 9: 'cluster sizes do not sum to R',
+                   10: 'row in a dead cluster', 11: 'cluster size is not the histogram of zr',
+                   12: 'member order is not a permutation', 13: 'scratch flags not clear',
+                   14: 'N of a (cluster, column) differs from its non-NaN members'}
+
+    def check_partitions(self):
+        """Device form of _check_partitions (view.py:528-560, state.py:1162-1184)."""
+        out = torch.zeros((self.S,), dtype=torch.int32, device=self.dev.device)
+        L.check(self.dev.lib.cc_check_state(C.byref(self.dev.st), _dp(out), self.dev.stream_ptr()), 'cc_check_state')
+        codes = out.cpu().numpy()
+        bad = np.nonzero(codes)[0]
+        if len(bad):
+            raise AssertionError('partition invariants violated: ' + ', '.join(
+                'chain %d: %s' % (s, self.CHECK_CODES.get(int(codes[s]), codes[s])) for s in bad[:8]))
+
+    @staticmethod
+    def check_env_debug():
+        """src/utils/config.py:112-114."""
+        import os
+        return 'GPMCCDEBUG' in os.environ
+
     def _timed(self, name, f):
         def run():
+            if self.check_env_debug():
+                f()
+                return self.check_partitions()
             if self.events is None:
                 return f()
             e0 = torch.cuda.Event(enable_timing=True)

@@ -321,6 +321,101 @@ __global__ void refresh_kernel(const cc_state st, int n_work, const int32_t* __r
     }
 }
 
+// Device form of the reference's debug invariants (View._check_partitions / State._check_partitions,
+// src/mixtures/view.py:528-560, src/crosscat/state.py:1162-1184; enabled there by GPMCCDEBUG).
+// One CTA per chain; out[s] = 0 or the code of the first violated invariant.
+__global__ void __launch_bounds__(256) check_kernel(const cc_state st, int32_t* __restrict__ out) {
+    const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int R = st.R, C = st.C, Vcap = st.Vcap, Kcap = st.Kcap;
+    extern __shared__ int s_hist[];                 // [Kcap] + [Kcap]
+    int* s_mark = s_hist + Kcap;
+    __shared__ int s_bad, s_sum;
+    if (tid == 0) { s_bad = 0; s_sum = 0; }
+    __syncthreads();
+    auto fail = [&](int code) { atomicCAS(&s_bad, 0, code); };
+    const int32_t* zv = st.zv + (size_t)s * C;
+    const int32_t* nv = st.nv + (size_t)s * Vcap;
+    // 1. column partition: every column in a live view, nv is the histogram of zv, sum = C
+    for (int v = tid; v < Vcap; v += nt) {
+        int cnt = 0;
+        for (int c = 0; c < C; ++c) cnt += (zv[c] == v);
+        if (cnt != nv[v]) fail(1);
+        if (nv[v] > 0 && st.view_id[(size_t)s * Vcap + v] < 0) fail(2);
+        if (nv[v] < 0) fail(1);
+    }
+    for (int c = tid; c < C; c += nt) if (zv[c] < 0 || zv[c] >= Vcap) fail(3);
+    if (!(st.col_alpha[s] > 0.0)) fail(4);
+    __syncthreads();
+    for (int v = 0; v < Vcap && !s_bad; ++v) {
+        if (nv[v] <= 0) continue;
+        const size_t sv = sv_index(st, s, v);
+        const int K = st.nclu[sv];
+        const int32_t* live = st.live + sv * Kcap;
+        const int32_t* nk = st.nk + sv * Kcap;
+        const int32_t* cid = st.cid + sv * Kcap;
+        const int32_t* zr = st.zr + sv * R;
+        const int32_t* ord = st.order + sv * R;
+        uint8_t* flag = st.movedflag + sv * R;
+        if (K < 1 || K > Kcap - 1) { if (tid == 0) fail(5); __syncthreads(); break; }
+        if (!(st.view_alpha[sv] > 0.0) && tid == 0) fail(4);
+        for (int k = tid; k < Kcap; k += nt) { s_hist[k] = 0; s_mark[k] = 0; }
+        if (tid == 0) s_sum = 0;
+        __syncthreads();
+        // 2. live list: valid distinct slots, ascending cluster ids, positive sizes summing to R
+        for (int i = tid; i < K; i += nt) {
+            const int k = live[i];
+            if (k < 0 || k >= Kcap - 1) { fail(6); continue; }
+            if (atomicAdd(&s_mark[k], 1) != 0) fail(6);
+            if (nk[k] < 1) fail(7);
+            if (i > 0 && live[i - 1] >= 0 && live[i - 1] < Kcap && cid[live[i - 1]] >= cid[k]) fail(8);
+            atomicAdd(&s_sum, nk[k]);
+        }
+        __syncthreads();
+        if (s_sum != R && tid == 0) fail(9);
+        // 3. every row sits in a live cluster and the sizes are the histogram of zr
+        for (int r = tid; r < R; r += nt) {
+            const int k = zr[r];
+            if (k < 0 || k >= Kcap - 1 || s_mark[k] != 1) { fail(10); continue; }
+            atomicAdd(&s_hist[k], 1);
+        }
+        __syncthreads();
+        for (int i = tid; i < K; i += nt) { const int k = live[i]; if (k >= 0 && k < Kcap && s_hist[k] != nk[k]) fail(11); }
+        // 4. the member order is a permutation of the rows (scratch flags must be clear between kernels)
+        for (int i = tid; i < R; i += nt) {
+            const int r = ord[i];
+            if (r < 0 || r >= R) { fail(12); continue; }
+            if (flag[r] != 0) fail(13);
+        }
+        __syncthreads();
+        for (int i = tid; i < R; i += nt) { const int r = ord[i]; if (r >= 0 && r < R) flag[r] = 1; }
+        __syncthreads();
+        for (int r = tid; r < R; r += nt) if (flag[r] != 1) fail(12);
+        __syncthreads();
+        for (int r = tid; r < R; r += nt) flag[r] = 0;
+        __syncthreads();
+        // 5. law of conservation of rowids (view.py:552-560): N of a (cluster, column) = its non-NaN members
+        for (int c = 0; c < C && !s_bad; ++c) {
+            if (zv[c] != v) continue;
+            for (int k = tid; k < Kcap; k += nt) s_hist[k] = 0;
+            __syncthreads();
+            for (int r = tid; r < R; r += nt) {
+                const double x = st.Xrm[(size_t)r * st.Cp + c];
+                const int k = zr[r];
+                if (!isnan(x) && k >= 0 && k < Kcap) atomicAdd(&s_hist[k], 1);
+            }
+            __syncthreads();
+            for (int i = tid; i < K; i += nt) {
+                const int k = live[i];
+                if (k >= 0 && k < Kcap && (double)s_hist[k] != stat_field(st, s, CC_F_N)[(size_t)k * C + c]) fail(14);
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (tid == 0) out[s] = s_bad;
+}
+
 __global__ void list_views_kernel(const cc_state st, int32_t* chains, int32_t* views, int32_t* count) {
     // enumerate live (chain, view) pairs (single thread; S*Vcap is small)
     if (blockIdx.x || threadIdx.x) return;
@@ -399,6 +494,14 @@ extern "C" int cc_refresh_tables(const cc_state* st, int n_work, const int32_t* 
     CC_CUDA(cudaGetLastError());
     cudaFreeAsync(dch, stream);
     cudaFreeAsync(dvw, stream);
+    return CC_OK;
+}
+
+extern "C" int cc_check_state(const cc_state* st, int32_t* out_dev, void* stream_) {
+    if (!st || !out_dev) { cc_set_error("cc_check_state: null argument"); return CC_ERR_ARG; }
+    if (st->S == 0) return CC_OK;
+    check_kernel<<<st->S, 256, sizeof(int) * 2 * st->Kcap, (cudaStream_t)stream_>>>(*st, out_dev);
+    CC_CUDA(cudaGetLastError());
     return CC_OK;
 }
 

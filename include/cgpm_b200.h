@@ -129,6 +129,12 @@ int cc_rebuild(const cc_state* st, int n_work, const int32_t* chains /*host*/,
 int cc_refresh_tables(const cc_state* st, int n_work, const int32_t* chains /*host*/,
                       const int32_t* views /*host*/, void* stream);
 
+/* Debug invariants of the partitions (View._check_partitions / State._check_partitions,
+ * src/mixtures/view.py:528-560, src/crosscat/state.py:1162-1184, enabled in the reference by
+ * the GPMCCDEBUG environment variable): out_dev[S] = 0, or the code of the first violated
+ * invariant of that chain. */
+int cc_check_state(const cc_state* st, int32_t* out_dev, void* stream);
+
 /* State.logpdf_score (src/crosscat/state.py:384-387): column-CRP marginal +
  * per view [row-CRP marginal + sum of cluster marginals].  out: device [S]. */
 int cc_logpdf_score(const cc_state* st, double* out, void* stream);

@@ -141,3 +141,28 @@ def test_very_wide_views_use_the_wide_mode():
     for o in oracles:
         o.transition_dims(cols=list(range(0, C, 37)))
     compare(eng, oracles, 'wide columns')
+
+
+def test_debug_invariants_like_gpmccdebug(monkeypatch):
+    """GPMCCDEBUG (src/utils/config.py:112-114) turns on the partition invariants after every
+    kernel; a corrupted partition is reported."""
+    import torch
+    from helpers import small_table
+    from cgpm_b200.engine import Engine, gen_rng
+    monkeypatch.setenv('GPMCCDEBUG', '1')
+    X, cct, da = small_table(60, 12)
+    eng = Engine(X, num_states=3, rng=gen_rng(12), cctypes=cct, distargs=da, stream='philox')
+    eng.transition(N=3, progress=False)                      # checks run after each kernel, no violation
+    eng._ch.check_partitions()
+    ch = eng._ch
+    nv = ch.dev.t['nv'].cpu().numpy()
+    v = int(np.nonzero(nv[1] > 0)[0][0])
+    saved = int(ch.dev.t['zr'][1, v, 5].item())
+    ch.dev.t['zr'][1, v, 5] = ch.dev.Kcap - 2                # a dead slot
+    with pytest.raises(AssertionError, match='chain 1'):
+        ch.check_partitions()
+    ch.dev.t['zr'][1, v, 5] = saved
+    ch.check_partitions()
+    ch.dev.t['stat'][2, 0, 0, :] += 1.0                      # corrupt N of cluster slot 0 in every column
+    with pytest.raises(AssertionError, match='chain 2'):
+        ch.check_partitions()
