@@ -97,7 +97,7 @@ struct Ctx {
     size_t sv;
     // shared memory
     uint64_t *bar_full, *bar_empty;
-    int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice
+    int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice, 9 destination slot, 10 new-cluster flag
     int *live, *nk;
     double* lp;
     double* w;              // [Kcap+1] CRP weight of each candidate (written with lp)
@@ -183,15 +183,20 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                 const double x = xrow[c.bulk ? c.col[j] : j];
                 if (isnan(x)) continue;                                  // dim.py:130-132
                 if (CTYPE(j) == CC_NORMAL) {
+                    // Both cases end in ONE log of a different argument, so the own cluster's group does
+                    // not serialise a second transcendental against the other groups of its warp:
+                    //   other cluster: cst - b log(1 + a (x-mn)^2)            (Student-t form, cached a, mn, cst)
+                    //   own cluster  : G(N1) - b1 log sn + (b1 - 1/2) log sn1 (view.py:416-419: the row is removed
+                    //                  first; sn1 from the reference's posterior update of the decremented sums,
+                    //                  log sn = 2 (G(N) - cst) is cached; the re-incorporation is step 2)
                     const double nu = H(3, j);
+                    double arg, coef, base;
                     if (!own) {
-                        acc += normal_predictive_cached(x, T.at(CC_F_MN, k, j), T.at(CC_F_A, k, j), T.at(CC_F_CST, k, j),
-                                                        T.at(CC_F_N, k, j), nu);
+                        const double zz = x - T.at(CC_F_MN, k, j);
+                        arg = fma(T.at(CC_F_A, k, j) * zz, zz, 1.0);
+                        coef = -0.5 * (nu + T.at(CC_F_N, k, j) + 1.0);
+                        base = T.at(CC_F_CST, k, j);
                     } else {
-                        // view.py:416-419: unincorporate, then score (the re-incorporation is step 2).
-                        // With the row removed the cluster has (N1, sx1, sxx1) -> sn1; with it the
-                        // cached sn (cst = G(N) - log(sn)/2).  Z(N1+1) - Z(N1) of normal.py:165-173 is
-                        // G(N1) + (b1 - 1/2) log sn1 - b1 log sn,  b1 = (nu + N1 + 1)/2: one log.
                         const double N1 = T.at(CC_F_N, k, j) - 1.0;
                         const double sx1 = __dsub_rn(T.at(CC_F_SX, k, j), x);
                         const double sxx1 = __dsub_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
@@ -202,9 +207,11 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                                                __dmul_rn(__dmul_rn(rn1, mn1), mn1));
                         if (sn1 == 0.0) sn1 = ss;
                         const double b1 = 0.5 * (nu + N1 + 1.0);
-                        const double logsn = 2.0 * (T.at(CC_F_GN, k, j) - T.at(CC_F_CST, k, j));
-                        acc += T.at(CC_F_GM1, k, j) + (b1 - 0.5) * log(sn1) - b1 * logsn;
+                        arg = sn1;
+                        coef = b1 - 0.5;
+                        base = T.at(CC_F_GM1, k, j) - b1 * (2.0 * (T.at(CC_F_GN, k, j) - T.at(CC_F_CST, k, j)));
                     }
+                    acc += base + coef * log(arg);
                 } else {
                     const double a = H(0, j);
                     const int xi = (int)x, kc = NCAT(j);
@@ -283,7 +290,14 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                 tr[2] = (double)((choice < K) ? c.g_cid[c.live[choice]] : (c.g_cid[c.live[K - 1]] + 1));
                 for (int pc = 0; pc < ncand && pc + 3 < c.trace_stride; ++pc) tr[3 + pc] = c.lp[pc] + log(weight(pc));
             }
-            if (lane == 0) c.scal[8] = choice;
+            if (lane == 0) {
+                // destination slot and "new cluster" flag, resolved here so that step 3 never reads
+                // the live list / free head while the bookkeeping thread is already rewriting them
+                int nc = choice >= K;
+                int dst = nc ? c.scal[2] : c.live[choice];
+                if (nc && dst >= Kcap - 1) { c.scal[7] = CC_ERR_CAPACITY; nc = 0; dst = z; }   // no free slot: keep the row
+                c.scal[8] = choice; c.scal[9] = dst; c.scal[10] = nc;
+            }
         }
         if (gid == gmask - (c.scal[4] & gmask)) {
             // view.py:419: incorporate the row back; the sums may differ from before in the last bit
@@ -307,19 +321,17 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
 
         // ---- step 3: apply the move (view.py:424-429) -----------------------------------
         const int ownpos = c.scal[4];
-        const int choice = c.scal[8];
-        bool newc = choice >= K;
-        int zb = newc ? c.scal[2] : c.live[choice];
-        if (newc && zb >= Kcap - 1) {            // no free cluster slot: keep the row, flag the chain
-            if (tid == 0) c.scal[7] = CC_ERR_CAPACITY;
-            newc = false;
-            zb = z;
-        }
+        const int zb = c.scal[9];
+        const bool newc = c.scal[10] != 0;
         if (zb != z) {
             if (!GT && newc && zb >= c.Kc - 1) return i;     // needs the global-memory tables
-            for (int t = tid; t < 2 * D; t += NT) {
-                const int j = (t < D) ? t : t - D;
-                const bool is_old = t < D;
+            // the lower half of the CTA updates the old cluster, the upper half the new one (different
+            // warps whenever NT > 32, so the two divergent update paths run side by side)
+            const int half = (NT > 32) ? NT / 2 : NT;
+            const bool is_old_half = (NT > 32) ? (tid < half) : true;
+            for (int t = (NT > 32) ? (tid % half) : tid; t < ((NT > 32) ? D : 2 * D); t += half) {
+                const int j = (NT > 32) ? t : ((t < D) ? t : t - D);
+                const bool is_old = (NT > 32) ? is_old_half : (t < D);
                 if (is_old && singleton) continue;            // the emptied cluster is dropped
                 const double x = xrow[c.bulk ? c.col[j] : j];
                 const int k = is_old ? z : zb;
@@ -371,8 +383,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                     T.at(CC_F_CST, k, j) = log(N + a * kc);
                 }
             }
-            // bookkeeping of the row CRP (crp.py:45-59) by one thread
-            if (tid == 0) {
+            // bookkeeping of the row CRP (crp.py:45-59) by one thread, concurrently with the table updates
+            if (tid == NT - 1) {
                 c.zr[r] = zb;
                 const int nm = c.scal[3];
                 c.moved[nm] = r;
