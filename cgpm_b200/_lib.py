@@ -31,7 +31,7 @@ class cc_state(C.Structure):
         ('zr', C.c_void_p), ('order', C.c_void_p), ('stat', C.c_void_p), ('cnt', C.c_void_p),
         ('err', C.c_void_p),
         ('seq', C.c_void_p), ('moved', C.c_void_p), ('movedflag', C.c_void_p),
-        ('colL', C.c_void_p), ('aux_zr', C.c_void_p), ('aux_nk', C.c_void_p), ('aux_K', C.c_void_p),
+        ('colL', C.c_void_p), ('aux_zr', C.c_void_p), ('aux_K', C.c_void_p),
         ('aux_alpha', C.c_void_p), ('aux_zr_all', C.c_void_p), ('aux_K_all', C.c_void_p),
         ('arena', C.c_void_p), ('arena_bytes', C.c_int64),
     ]

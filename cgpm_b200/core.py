@@ -37,6 +37,33 @@ CCTYPES = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL}
 KERNELS = ['alpha', 'view_alphas', 'column_params', 'column_hypers', 'rows', 'columns']
 
 
+def philox4x32_10(ctr_lo, ctr_hi, seed):
+    """numpy mirror of the device generator (csrc/cc_common.cuh: Philox): returns the first
+    output word for arrays of 64-bit counters.  Used to order work by its expected cost."""
+    ctr_lo = np.asarray(ctr_lo, dtype=np.uint64); ctr_hi = np.asarray(ctr_hi, dtype=np.uint64)
+    m32 = np.uint64(0xFFFFFFFF)
+    c0, c1 = ctr_lo & m32, ctr_lo >> np.uint64(32)
+    c2, c3 = ctr_hi & m32, ctr_hi >> np.uint64(32)
+    a = np.uint64(int(seed) & 0xFFFFFFFF); b = np.uint64((int(seed) >> 32) & 0xFFFFFFFF)
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    for _ in range(10):
+        p0 = M0 * c0; p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & m32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & m32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ a) & m32, lo1, (hi0 ^ c3 ^ b) & m32, lo0
+        a = (a + np.uint64(0x9E3779B9)) & m32; b = (b + np.uint64(0xBB67AE85)) & m32
+    return c0
+
+
+def aux_alpha_index(seed, counter, chains, cols):
+    """Grid index the device will draw for the auxiliary view of each (chain, column)
+    (columns.cu: stream 4): ((x * 30) >> 32)."""
+    sid = (np.uint64(4) << np.uint64(56)) | ((np.asarray(chains, dtype=np.uint64) & np.uint64(0xFFFFFF)) << np.uint64(32)) \
+        | np.asarray(cols, dtype=np.uint64)
+    x = philox4x32_10(np.full(len(sid), counter, dtype=np.uint64), sid, seed)
+    return ((x * np.uint64(L.NGRID)) >> np.uint64(32)).astype(np.int64)
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
@@ -488,6 +515,9 @@ class Chains(object):
             # auxiliary views of every (chain, column) and marginals under every live view
             a_ch = np.repeat(ch_h, ncols).astype(np.int32)
             a_co = perm.reshape(-1).astype(np.int32)
+            # the cost of a pair grows with its alpha (number of tables): hand out the expensive ones first
+            cost = np.argsort(-aux_alpha_index(self.seed, counter, a_ch, a_co), kind='stable')
+            a_ch = np.ascontiguousarray(a_ch[cost]); a_co = np.ascontiguousarray(a_co[cost])
             L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), None, None, 2 if stored else 0, seed,
                                    C.c_uint64(counter), sp()), 'cc_col_aux')
             m = self.mirror()

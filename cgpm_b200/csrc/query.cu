@@ -28,13 +28,6 @@ __device__ double cell_logpdf(const cc_state& st, int s, int c, int k, double x)
     return log(a + cnt) - stat_field(st, s, CC_F_CST)[e];
 }
 
-__device__ double warp_logsumexp(double v, bool valid) {
-    double m = warp_max(valid ? v : -INFINITY);
-    if (m == -INFINITY) return -INFINITY;
-    double e = valid ? exp(v - m) : 0.0;
-    return m + log(warp_sum(e));
-}
-
 struct QueryParams {
     cc_state st;
     int n_chains, Q;

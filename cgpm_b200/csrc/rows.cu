@@ -704,14 +704,14 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
             return CC_ERR_ARG;
         }
     }
-    // Work items are split by view width: views wider than 32 columns get 8 consumer warps
+    // Work items are split by view width: views wider than 16 columns get 8 consumer warps
     // (each candidate cluster needs a full warp or more), the others 4.  The two launches run
     // concurrently (the second on an internal stream ordered after / before `stream` by events).
     std::vector<cc_row_work> sorted(work, work + n_work);
     int n_wide = 0;
     if (!getenv("CGPM_B200_ROWS_NT")) {
-        std::stable_partition(sorted.begin(), sorted.end(), [](const cc_row_work& w) { return w.n_cols > 32; });
-        for (int i = 0; i < n_work; ++i) n_wide += sorted[i].n_cols > 32;
+        std::stable_partition(sorted.begin(), sorted.end(), [](const cc_row_work& w) { return w.n_cols > 16; });
+        for (int i = 0; i < n_work; ++i) n_wide += sorted[i].n_cols > 16;
     }
     cc_row_work* dwork = nullptr;
     CC_CUDA(cudaMallocAsync(&dwork, sizeof(cc_row_work) * n_work, stream));

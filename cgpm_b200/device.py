@@ -149,7 +149,6 @@ class DeviceChains(object):
         t['movedflag'] = z((S_, V, R), torch.uint8)
         t['colL'] = z((S_, Cn, V + 1), f64)
         t['aux_zr'] = z((S_, R), i32)
-        t['aux_nk'] = z((S_, R), i32)
         t['aux_K'] = z((S_,), i32)
         t['aux_alpha'] = z((S_, Cn), f64)
         t['aux_K_all'] = z((S_, Cn), i32)
@@ -161,7 +160,7 @@ class DeviceChains(object):
         for name in ('Xrm', 'Xcm', 'ctype', 'ncat', 'catoff', 'grids', 'row_alpha_grid',
                      'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha', 'view_grid',
                      'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'seq',
-                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_nk', 'aux_K', 'aux_alpha', 'aux_K_all'):
+                     'moved', 'movedflag', 'colL', 'aux_zr', 'aux_K', 'aux_alpha', 'aux_K_all'):
             setattr(st, name, t[name].data_ptr())
         st.arena = None
         st.arena_bytes = 0

@@ -81,9 +81,6 @@ def crp_simulate_fast(n, alpha, rng):
         if np.array_equal(nxt, parent):
             break
         parent = nxt
-    _, first = np.unique(parent, return_index=True)
-    order = np.argsort(first)
-    relabel = np.empty(len(first), dtype=np.int64)
-    relabel[order] = np.arange(len(first))
+    # roots are first members, so sorted roots are already in order of appearance
     _, inv = np.unique(parent, return_inverse=True)
-    return relabel[inv]
+    return inv.astype(np.int64)

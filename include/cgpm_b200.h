@@ -81,12 +81,11 @@ typedef struct cc_state {
     double*  cnt;        /* [S][Kcap][CT]   categorical counts                    */
     int32_t* err;        /* [S]  sticky per-chain error code (CC_ERR_CAPACITY)    */
     /* ---- scratch (caller-allocated, contents undefined between calls) ----- */
-    int32_t* seq;        /* [S][Vcap][R]  row visiting sequence of the current sweep */
+    int32_t* seq;        /* [S][Vcap][R]  spare scratch (per-CTA / per-pair cycle counters of the debug probes) */
     int32_t* moved;      /* [S][Vcap][R]  rows re-seated in the current sweep, in order */
     uint8_t* movedflag;  /* [S][Vcap][R]                                          */
     double*  colL;       /* [S][C][Vcap+1] column marginal matrix (last = auxiliary view) */
     int32_t* aux_zr;     /* [S][R]   auxiliary-view partition (one column step)   */
-    int32_t* aux_nk;     /* [S][R]   (reserved)                                            */
     int32_t* aux_K;      /* [S]      number of tables                             */
     double*  aux_alpha;  /* [S][C]   alpha drawn for each column's auxiliary view */
     int32_t* aux_zr_all; /* [S][C][R] every column's auxiliary partition, or NULL when it does not fit */
@@ -182,7 +181,7 @@ int cc_col_scan(const cc_state* st, int n_chains, const int32_t* chains_dev, con
                 uint64_t seed, uint64_t counter, const int32_t* ci_off_dev, const int32_t* ci_adj_dev,
                 double* trace_dev, int trace_stride, void* stream);
 
-/* Install aux_zr/aux_nk/aux_K of each listed chain as a new view and move the
+/* Install aux_zr/aux_K of each listed chain (or the stored aux_zr_all/aux_K_all of the pair) as a new view and move the
  * column into it (state.py:1110-1116,1125-1154). */
 int cc_col_install(const cc_state* st, int n, const int32_t* chains, const int32_t* cols,
                    int mode /* 1: aux_zr of the chain, 2: aux_zr_all of the (chain, column) */, void* stream);

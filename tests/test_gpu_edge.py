@@ -166,3 +166,20 @@ def test_debug_invariants_like_gpmccdebug(monkeypatch):
     ch.dev.t['stat'][2, 0, 0, :] += 1.0                      # corrupt N of cluster slot 0 in every column
     with pytest.raises(AssertionError, match='chain 2'):
         ch.check_partitions()
+
+
+def test_host_philox_mirror_matches_the_device_generator():
+    """core.aux_alpha_index (numpy Philox4x32-10) predicts the alpha the device draws for every
+    auxiliary view: it is used to schedule expensive (chain, column) pairs first."""
+    from helpers import small_table
+    from cgpm_b200.core import aux_alpha_index
+    from cgpm_b200.engine import Engine, gen_rng
+    X, cct, da = small_table(40, 5)
+    eng = Engine(X, num_states=3, rng=gen_rng(5), cctypes=cct, distargs=da, stream='philox')
+    ch = eng._ch
+    counter = ch.counter + 1                          # the counter the next kernel call will use
+    eng.transition(N=1, kernels=['columns'], progress=False)
+    aux_alpha = ch.dev.t['aux_alpha'].cpu().numpy()
+    chains = np.repeat(np.arange(3), 6); cols = np.tile(np.arange(6), 3)
+    idx = aux_alpha_index(ch.seed, counter, chains, cols)
+    assert np.array_equal(aux_alpha[chains, cols], ch.dev.row_alpha_grid_h[idx])
