@@ -417,10 +417,12 @@ class Chains(object):
         n = R if rows is None else len(rows)
         work, perms, us = [], [], []
         off = 0
+        m = self.mirror()
+        is_normal = self.ctype == CCTYPES['normal']
         for s in chains:
             for v in self._views_for(s, views, cols):
                 w = dict(chain=s, view=v, n=n, perm_is_index=1 if rows is None else 0,
-                         n_cols=int(self.mirror()['nv'][s][v]))
+                         n_cols=int(m['nv'][s][v]), n_normal=int(np.sum(is_normal & (m['zv'][s] == v))))
                 if self.stream == 'numpy':
                     rng = self.rngs[s]
                     perms.append(np.asarray(rng.permutation(R if rows is None else rows), dtype=np.int32))

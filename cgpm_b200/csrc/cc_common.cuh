@@ -97,10 +97,10 @@ __device__ __forceinline__ double normal_G(double N, double r, double nu) {
     while (h < 16.0) { pn *= (h + 0.5); pd *= h; h += 1.0; }
     num *= pn * pn;
     den *= pd * pd * h;
-    const double ih = 1.0 / h, ih2 = ih * ih;
+    const double ih = __drcp_rn(h), ih2 = ih * ih;
     const double poly = ih * (-0.125 + ih2 * (1.0 / 192.0 + ih2 * (-1.0 / 640.0 + ih2 * (17.0 / 14336.0 +
                         ih2 * (-31.0 / 18432.0 + ih2 * (691.0 / 180224.0))))));
-    return 0.5 * log(den / num) + poly - 0.5 * CC_LOGPI;
+    return 0.5 * log(den * __drcp_rn(num)) + poly - 0.5 * CC_LOGPI;
 }
 struct NormalCache { double mn, a, cst; };
 __device__ __forceinline__ NormalCache normal_cache(double N, double sx, double sxx, double gN, double m,

@@ -241,20 +241,20 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
             if (ncand <= 32) {
                 const double lpv = (lane < ncand) ? c.lp[lane] : -INFINITY;
                 const double wv = (lane < ncand) ? c.w[lane] : 0.0;
-                double mx = lpv;
-                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-                if (ncand > 4) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-                if (ncand > 8) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 8)); mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 16)); }
-                double inc = wv * exp(lpv - mx);
+                // any common reference point near the maximum will do (it cancels in inc > u * tot):
+                // the float-rounded maximum costs one redux instead of five 64-bit shuffle rounds
+                float mf = (float)lpv;
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mf) : "f"(mf));
+                const double dl = lpv - (double)mf;
+                // below e^-80 of the maximum a candidate cannot change a 53-bit prefix sum; keeping the
+                // argument in range also keeps exp on its fast path
+                double inc = (dl > -80.0) ? wv * exp(fmax(dl, -80.0)) : ((dl == dl) ? 0.0 : dl);
                 double t;
                 t = __shfl_up_sync(0xffffffffu, inc, 1); if (lane >= 1) inc += t;
                 t = __shfl_up_sync(0xffffffffu, inc, 2); if (lane >= 2) inc += t;
                 if (ncand > 4) { t = __shfl_up_sync(0xffffffffu, inc, 4); if (lane >= 4) inc += t; }
-                if (ncand > 8) {
-                    t = __shfl_up_sync(0xffffffffu, inc, 8); if (lane >= 8) inc += t;
-                    t = __shfl_up_sync(0xffffffffu, inc, 16); if (lane >= 16) inc += t;
-                }
+                if (ncand > 8) { t = __shfl_up_sync(0xffffffffu, inc, 8); if (lane >= 8) inc += t; }
+                if (ncand > 16) { t = __shfl_up_sync(0xffffffffu, inc, 16); if (lane >= 16) inc += t; }
                 const double tot = __shfl_sync(0xffffffffu, inc, ncand - 1);
                 const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && inc > uu * tot);
                 choice = hit ? (__ffs(hit) - 1) : -1;
@@ -683,6 +683,389 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     }
 }
 
+// Normal cell of one row against one candidate cluster.
+//   other cluster: cst - b log(1 + a (x-mn)^2)   (Student-t form, cached a, mn, cst)
+//   own cluster  : the row is removed first (view.py:416-419).  With sn1 = sn - rn/(rn-1) (x-mn)^2 (the
+//     Normal-Gamma downdate; rn, mn, sn, a = rn/((rn+1) sn) of the cluster WITH the row) the predictive
+//     G(N-1) - b1 log sn + (b1-1/2) log sn1 becomes cst + G(N-1) - G(N) + (b1-1/2) log(1 - a (rn+1)/(rn-1)
+//     (x-mn)^2): the same loads and the same single log as for any other cluster.  Heavy cancellation
+//     (arg < 2^-20) takes the reference's posterior update of the decremented sums instead.  A singleton's
+//     own cluster without the row IS the empty cluster (the caller passes that cell as p).  The `-= x; += x`
+//     replay (view.py:416-419) is reported in `drift`: set if the sums come back changed.
+// p: the candidate's cell (field f at p[f * fs]); po: the cell of the row's own cluster (k), read only if `own`.
+// ms(m, s): loads the two hyperparameters only the rare exact branch needs.
+template <typename FS, typename MS>
+__device__ __forceinline__ double normal_core(const double* p, const double* po, FS fs, double x, double nu, double rr,
+                                              bool own, bool dn, int& drift, MS ms) {
+    const double Nf = p[CC_F_N * fs];
+    const double zz = x - p[CC_F_MN * fs];
+    double sc = p[CC_F_A * fs];
+    double bs = p[CC_F_CST * fs];
+    double coef = -0.5 * (nu + Nf + 1.0);
+    if (own) {
+        const double sx0 = po[CC_F_SX * fs], sxx0 = po[CC_F_SXX * fs];
+        const double xx = __dmul_rn(x, x);
+        const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
+        if (!isnan(x) && (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, xx) != sxx0)) drift = 1;
+        if (dn) {
+            const double rn = rr + Nf;
+            sc = -sc * ((rn + 1.0) * __drcp_rn(rn - 1.0));
+            coef = 0.5 * (nu + Nf - 1.0);
+            bs += p[CC_F_GM1 * fs] - p[CC_F_GN * fs];
+            if (!(fma(sc * zz, zz, 1.0) >= 0x1p-20)) {
+                double m, ss;
+                ms(m, ss);
+                const double N1 = Nf - 1.0;
+                const double rn1 = rr + N1;
+                const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
+                double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
+                                       __dmul_rn(__dmul_rn(rn1, mn1), mn1));
+                if (sn1 == 0.0) sn1 = ss;
+                const double b1 = 0.5 * (nu + N1 + 1.0);
+                bs = p[CC_F_GM1 * fs] - b1 * (2.0 * (p[CC_F_GN * fs] - p[CC_F_CST * fs]));
+                const double t = bs + coef * log(sn1);
+                return isnan(x) ? 0.0 : t;
+            }
+        }
+    }
+    const double t = bs + coef * log(fma(sc * zz, zz, 1.0));
+    return isnan(x) ? 0.0 : t;                                   // dim.py:130-132
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Narrow views (one or two normal columns): one warp per (chain, view), no CTA barriers at all.
+// Such views carry little evidence per row, so a large share of their rows move at every sweep
+// and the cost of a step is pure latency.  Here a lane owns one candidate cluster (its score and
+// CRP weight never leave its registers), the draw is a handful of warp collectives, the row batch
+// is prefetched into registers one batch ahead, and the whole step is one short loop that stays
+// in the instruction cache.  The arithmetic, the order of the operations on the sufficient
+// statistics and the stream use are those of the general kernel above (same trajectories).
+// Shared memory: live[Kcap], nk[Kcap], cid[Kcap] (int); tab[8][Kcap][D]; lp[Kcap+1], w[Kcap+1]
+// (only used when a row has more than 32 candidates).
+__global__ void __launch_bounds__(32) rows_narrow_kernel(const RowsParams p) {
+    const cc_state& st = p.st;
+    const cc_row_work wk = p.work[blockIdx.x];
+    const int s = wk.chain, v = wk.view, n = wk.n;
+    const int R = st.R, C = st.C, Cp = st.Cp, Kcap = st.Kcap;
+    const int lane = threadIdx.x;
+    const size_t sv = sv_index(st, s, v);
+    const long long t_start = clock64();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* live = reinterpret_cast<int*>(smem_raw);
+    int* nk = live + Kcap;
+    int* cid = nk + Kcap;
+    double* tab = reinterpret_cast<double*>(cid + Kcap + (Kcap & 1));
+    // ---- the view's columns ----
+    const int32_t* zv = st.zv + (size_t)s * C;
+    int col0 = -1, col1 = -1, D = 0, alln = 1;
+    for (int q = 0; q < C; ++q)
+        if (zv[q] == v) {
+            if (D == 0) col0 = q; else if (D == 1) col1 = q;
+            if (st.ctype[q] != CC_NORMAL) alln = 0;
+            ++D;
+        }
+    if (D < 1 || D > 2 || !alln) {          // the caller's hint was wrong: nothing is touched
+        if (lane == 0) st.err[s] = CC_ERR_ARG;
+        return;
+    }
+    if (D == 1) col1 = col0;
+    const bool two = D == 2;
+    double* lpS = tab + (size_t)CC_NFIELD * Kcap * D;
+    double* wS = lpS + (Kcap + 1);
+    const int fs = Kcap * D;
+    const int pslot = Kcap - 1;
+    const double* gh = st.hyp + (size_t)s * C * 4;
+    const double m0 = gh[col0 * 4 + 0], r0 = gh[col0 * 4 + 1], s0 = gh[col0 * 4 + 2], nu0 = gh[col0 * 4 + 3];
+    const double m1 = gh[col1 * 4 + 0], r1 = gh[col1 * 4 + 1], s1 = gh[col1 * 4 + 2], nu1 = gh[col1 * 4 + 3];
+
+    int K = st.nclu[sv];
+    int32_t* g_live = st.live + sv * Kcap;
+    int32_t* g_nk = st.nk + sv * Kcap;
+    int32_t* g_cid = st.cid + sv * Kcap;
+    for (int i = lane; i < Kcap; i += 32) { nk[i] = 0; live[i] = (i < K) ? g_live[i] : -1; cid[i] = g_cid[i]; }
+    __syncwarp();
+    for (int i = lane; i < K; i += 32) nk[live[i]] = g_nk[live[i]];
+    for (int e = lane; e < (K + 1) * D; e += 32) {
+        const int pp = e / D, d = e - pp * D;
+        const int k = (pp < K) ? live[pp] : pslot;
+        const int q = d ? col1 : col0;
+#pragma unroll
+        for (int f = 0; f < CC_NFIELD; ++f) tab[f * fs + k * D + d] = stat_field(st, s, f)[(size_t)k * C + q];
+    }
+    __syncwarp();
+    int fh = 0;                               // lowest free slot
+    while (fh < Kcap - 1 && nk[fh] != 0) ++fh;
+    int nmoved = 0, err = 0;
+    const double alpha = st.view_alpha[sv];
+    int32_t* zr = st.zr + sv * R;
+    int32_t* moved = st.moved + sv * R;
+    uint8_t* movedflag = st.movedflag + sv * R;
+    double* trace = (p.trace && wk.trace_off >= 0) ? p.trace : nullptr;
+    const int32_t* order = st.order + sv * R;
+    const Philox rng(p.seed);
+    uint32_t bits = 1;
+    while ((1u << bits) < (uint32_t)n && bits < 31) ++bits;
+    const uint4 pkey = rng(p.counter, stream_id(2, s, v));
+    const uint64_t ustream = stream_id(1, s, v);
+
+    // lane l of a batch holds row (batch * 32 + l): id, current cluster, uniform, cells
+    int nr = 0, nz = 0;
+    double nu_ = 0.0, nx0 = 0.0, nx1 = 0.0;
+    auto fetch = [&](int i) {
+        if (i < n) {
+            int idx;
+            if (wk.perm_off >= 0) idx = p.perm[wk.perm_off + i];
+            else idx = (int)keyed_perm((uint32_t)i, (uint32_t)n, bits, pkey);
+            nr = wk.perm_is_index ? order[idx] : idx;
+            if (wk.u_off >= 0) nu_ = p.u[wk.u_off + i];
+            else { const uint4 w4 = rng(p.counter * 0x100000000ull + (uint64_t)i, ustream); nu_ = u01_from_words(w4.x, w4.y); }
+            nz = zr[nr];
+            const double* src = st.Xrm + (size_t)nr * Cp;
+            nx0 = src[col0];
+            nx1 = src[col1];
+        }
+    };
+    fetch(lane);
+    for (int b0 = 0; b0 < n; b0 += 32) {
+        const int br = nr, bz = nz;
+        const double bu = nu_, bx0 = nx0, bx1 = nx1;
+        fetch(b0 + 32 + lane);                                     // in flight while this batch is processed
+        const int cnt = min(32, n - b0);
+        for (int t = 0; t < cnt; ++t) {
+            const int i = b0 + t;
+            const int r = __shfl_sync(0xffffffffu, br, t);
+            const int z = __shfl_sync(0xffffffffu, bz, t);
+            const double uu = __shfl_sync(0xffffffffu, bu, t);
+            const double x0 = __shfl_sync(0xffffffffu, bx0, t);
+            const double x1 = __shfl_sync(0xffffffffu, bx1, t);
+            const int nkz = nk[z];
+            const bool singleton = nkz == 1;
+            const int ncand = K + (singleton ? 0 : 1);
+            // ---- scores: lane = candidate position (32 at a time) ----
+            double lpv = -INFINITY, wv = 0.0;
+            int ownpos = -1, drift = 0;
+            for (int base = 0; base < ncand; base += 32) {
+                const int pc = base + lane;
+                const bool active = pc < ncand;
+                const int k = (pc < K) ? live[pc] : pslot;
+                const bool own = (pc < K) && (k == z);
+                const int ke = (own && singleton) ? pslot : k;
+                const bool dn = own && !singleton;
+                double acc = 0.0;
+                int dr = 0;
+                if (active) {
+                    acc = normal_core(tab + ke * D, tab + k * D, fs, x0, nu0, r0, own, dn, dr,
+                                      [&](double& m, double& ss) { m = m0; ss = s0; });
+                    if (two) acc += normal_core(tab + ke * D + 1, tab + k * D + 1, fs, x1, nu1, r1, own, dn, dr,
+                                                [&](double& m, double& ss) { m = m1; ss = s1; });
+                }
+                // crp.py:111-124: n_k, n_k - 1 for the row's own table, alpha for a fresh / re-used singleton table
+                const double wc = (pc >= K) ? alpha : own ? (singleton ? alpha : (double)(nkz - 1)) : (double)nk[k];
+                const unsigned ob = __ballot_sync(0xffffffffu, own);
+                if (ob) { ownpos = base + __ffs(ob) - 1; drift = __shfl_sync(0xffffffffu, dr, __ffs(ob) - 1); }
+                if (ncand <= 32) { if (active) { lpv = acc; wv = wc; } }
+                else if (active) { lpS[pc] = acc; wS[pc] = wc; }
+            }
+            // ---- the draw: first j with prefix_j > u * total over w_j exp(lp_j - max) ----
+            int choice = -1;
+            if (ncand <= 32) {
+                float mf = (float)lpv;
+                asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mf) : "f"(mf));
+                const double dl = lpv - (double)mf;
+                double inc = (dl > -80.0) ? wv * exp(fmax(dl, -80.0)) : ((dl == dl) ? 0.0 : dl);
+                double tt;
+                tt = __shfl_up_sync(0xffffffffu, inc, 1); if (lane >= 1) inc += tt;
+                tt = __shfl_up_sync(0xffffffffu, inc, 2); if (lane >= 2) inc += tt;
+                if (ncand > 4) { tt = __shfl_up_sync(0xffffffffu, inc, 4); if (lane >= 4) inc += tt; }
+                if (ncand > 8) { tt = __shfl_up_sync(0xffffffffu, inc, 8); if (lane >= 8) inc += tt; }
+                if (ncand > 16) { tt = __shfl_up_sync(0xffffffffu, inc, 16); if (lane >= 16) inc += tt; }
+                const double tot = __shfl_sync(0xffffffffu, inc, ncand - 1);
+                const unsigned hit = __ballot_sync(0xffffffffu, lane < ncand && inc > uu * tot);
+                choice = hit ? (__ffs(hit) - 1) : -1;
+            } else {
+                __syncwarp();
+                double mx = -INFINITY;
+                for (int pc = lane; pc < ncand; pc += 32) mx = fmax(mx, lpS[pc]);
+                mx = warp_max(mx);
+                double carry = 0.0;
+                for (int base = 0; base < ncand; base += 32) {
+                    const int pc = base + lane;
+                    const double e = (pc < ncand) ? wS[pc] * exp(lpS[pc] - mx) : 0.0;
+                    carry += __shfl_sync(0xffffffffu, warp_incl_scan(e, lane), 31);
+                }
+                const double tot = carry;
+                carry = 0.0;
+                for (int base = 0; base < ncand && choice < 0; base += 32) {
+                    const int pc = base + lane;
+                    const double e = (pc < ncand) ? wS[pc] * exp(lpS[pc] - mx) : 0.0;
+                    const double inc = warp_incl_scan(e, lane) + carry;
+                    const unsigned hit = __ballot_sync(0xffffffffu, pc < ncand && inc > uu * tot);
+                    if (hit) choice = base + __ffs(hit) - 1;
+                    carry = __shfl_sync(0xffffffffu, inc, 31);
+                }
+            }
+            if (choice < 0) { choice = ownpos; err = CC_ERR_ARG; }      // NaN / all -inf: keep the row, flag the chain
+            if (trace) {
+                double* tr = trace + wk.trace_off + (size_t)i * p.trace_stride;
+                if (lane == 0) {
+                    tr[0] = (double)r;
+                    tr[1] = (double)ncand;
+                    tr[2] = (double)((choice < K) ? cid[live[choice]] : (cid[live[K - 1]] + 1));
+                }
+                if (ncand <= 32) { if (lane < ncand && lane + 3 < p.trace_stride) tr[3 + lane] = lpv + log(wv); }
+                else for (int pc = lane; pc < ncand && pc + 3 < p.trace_stride; pc += 32) tr[3 + pc] = lpS[pc] + log(wS[pc]);
+            }
+            bool newc = choice >= K;
+            int zb = newc ? fh : live[choice];
+            if (newc && zb >= Kcap - 1) { err = CC_ERR_CAPACITY; newc = false; zb = z; }     // no free slot: keep the row
+            if (zb != z) {
+                // ---- apply the move (view.py:424-429): lane = (column, old / new cluster) ----
+                const int d = lane >> 1;
+                const bool is_old = (lane & 1) == 0;
+                const bool fresh = !is_old && newc;
+                const double x = d ? x1 : x0;
+                const bool on = lane < 2 * D && !(is_old && singleton) && (!isnan(x) || fresh);
+                if (on) {
+                    const int k = is_old ? z : zb;
+                    double* pc_ = tab + k * D + d;
+                    const double m = d ? m1 : m0, rr = d ? r1 : r0, ss = d ? s1 : s0, nu = d ? nu1 : nu0;
+                    const double gP = tab[CC_F_GN * fs + pslot * D + d];
+                    const double N0 = fresh ? 0.0 : pc_[CC_F_N * fs];
+                    const double sx0 = fresh ? 0.0 : pc_[CC_F_SX * fs], sxx0 = fresh ? 0.0 : pc_[CC_F_SXX * fs];
+                    const double gn0 = fresh ? gP : pc_[CC_F_GN * fs], gm0 = pc_[CC_F_GM1 * fs];
+                    const double xx = __dmul_rn(x, x);
+                    double N, sx, sxx, gN, gM1;
+                    const bool nanx = isnan(x);
+                    // G of the changed count: G(N-2) for the cluster that loses the row, G(N+1) for the one that gains it
+                    const double garg = is_old ? N0 - 2.0 : N0 + 1.0;
+                    const double g = normal_G(fmax(garg, 0.0), rr, nu);
+                    if (is_old) {
+                        // scored against its own cluster first (-= x, += x: view.py:416-419), then removed
+                        N = N0 - 1.0;
+                        sx = __dsub_rn(__dadd_rn(__dsub_rn(sx0, x), x), x);
+                        sxx = __dsub_rn(__dadd_rn(__dsub_rn(sxx0, xx), xx), xx);
+                        gN = gm0;
+                        gM1 = (N >= 1.0) ? g : 0.0;
+                    } else if (nanx) {          // fresh cluster object, missing cell (normal.py:51-53)
+                        N = 0.0; sx = 0.0; sxx = 0.0; gN = gP; gM1 = 0.0;
+                    } else {                    // 0 + x, 0 + x*x for a fresh cluster object (normal.py:64-70)
+                        N = N0 + 1.0;
+                        sx = __dadd_rn(sx0, x);
+                        sxx = __dadd_rn(sxx0, xx);
+                        gM1 = gn0;
+                        gN = g;
+                    }
+                    const NormalCache cc = normal_cache_fast(N, sx, sxx, gN, m, rr, ss, nu);
+                    pc_[CC_F_N * fs] = N; pc_[CC_F_SX * fs] = sx; pc_[CC_F_SXX * fs] = sxx;
+                    pc_[CC_F_MN * fs] = cc.mn; pc_[CC_F_A * fs] = cc.a; pc_[CC_F_CST * fs] = cc.cst;
+                    pc_[CC_F_GN * fs] = gN; pc_[CC_F_GM1 * fs] = gM1;
+                }
+                // ---- bookkeeping of the row CRP (crp.py:45-59) ----
+                if (lane == 0) {
+                    zr[r] = zb;
+                    moved[nmoved] = r;
+                    movedflag[r] = 1;
+                    nk[z] = nkz - 1;
+                    if (newc) {
+                        cid[zb] = cid[live[K - 1]] + 1;              // crp.py:142 max(counts)+1
+                        live[K] = zb;
+                        nk[zb] = 1;
+                    } else {
+                        nk[zb] += 1;
+                    }
+                }
+                ++nmoved;
+                __syncwarp();
+                if (newc) {
+                    ++K;
+                    ++fh;
+                    while (fh < Kcap - 1 && nk[fh] != 0) ++fh;
+                }
+                if (singleton) {
+                    // the emptied cluster leaves the ascending-id list; its slot is free again
+                    for (int q0 = ownpos; q0 < K - 1; q0 += 32) {
+                        const int q = q0 + lane;
+                        const int nxt = (q < K - 1) ? live[q + 1] : -1;
+                        __syncwarp();
+                        if (q < K - 1) live[q] = nxt;
+                        __syncwarp();
+                    }
+                    if (lane == 0) live[K - 1] = -1;
+                    --K;
+                    if (z < fh) fh = z;
+                }
+                __syncwarp();
+            } else if (drift) {
+                // the row stays, but `-= x; += x` changed its cluster's sums in the last bit (view.py:416-419)
+                const double x = lane ? x1 : x0;
+                if (lane < D && !isnan(x)) {
+                    double* pc_ = tab + z * D + lane;
+                    const double sx0 = pc_[CC_F_SX * fs], sxx0 = pc_[CC_F_SXX * fs];
+                    const double xx = __dmul_rn(x, x);
+                    const double sx2 = __dadd_rn(__dsub_rn(sx0, x), x), sxx2 = __dadd_rn(__dsub_rn(sxx0, xx), xx);
+                    if (sx2 != sx0 || sxx2 != sxx0) {
+                        pc_[CC_F_SX * fs] = sx2;
+                        pc_[CC_F_SXX * fs] = sxx2;
+                        const NormalCache c2 = normal_cache_fast(pc_[CC_F_N * fs], sx2, sxx2, pc_[CC_F_GN * fs], lane ? m1 : m0,
+                                                                 lane ? r1 : r0, lane ? s1 : s0, lane ? nu1 : nu0);
+                        pc_[CC_F_MN * fs] = c2.mn; pc_[CC_F_A * fs] = c2.a; pc_[CC_F_CST * fs] = c2.cst;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    // ---- write back ----
+    __syncwarp();
+    for (int e = lane; e < K * D; e += 32) {
+        const int pp = e / D, d = e - pp * D;
+        const int k = live[pp], q = d ? col1 : col0;
+#pragma unroll
+        for (int f = 0; f < CC_NFIELD; ++f) stat_field(st, s, f)[(size_t)k * C + q] = tab[f * fs + k * D + d];
+    }
+    for (int i = lane; i < Kcap; i += 32) {
+        g_live[i] = (i < K) ? live[i] : -1;
+        g_nk[i] = nk[i];
+        g_cid[i] = cid[i];
+    }
+    if (lane == 0) {
+        st.nclu[sv] = K;
+        if (err) st.err[s] = err;
+        if (p.prof) {
+            int32_t* q = st.seq + sv * R;
+            q[0] = (int)((clock64() - t_start) >> 10); q[1] = D; q[2] = K; q[3] = nmoved; q[4] = 3;    // mode 3: single-warp kernel
+        }
+    }
+    // ---- member order of the view's CRP: re-seated rows move to the end, in the order they
+    //      were re-seated (OrderedDict pop + re-insert, crp.py:52,55) ----
+    if (nmoved > 0) {
+        __threadfence_block();
+        int32_t* ord = st.order + sv * R;
+        int base = 0;
+        for (int i0 = 0; i0 < R; i0 += 128) {
+            int rr[4], keep[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int i = i0 + q * 32 + lane; rr[q] = (i < R) ? ord[i] : -1; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) keep[q] = (rr[q] >= 0) ? !movedflag[rr[q]] : 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned bal = __ballot_sync(0xffffffffu, keep[q]);
+                if (keep[q]) ord[base + __popc(bal & ((1u << lane) - 1u))] = rr[q];
+                base += __popc(bal);
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < nmoved; i += 32) {
+            const int rr = moved[i];
+            ord[base + i] = rr;
+            movedflag[rr] = 0;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_work* work,
@@ -704,15 +1087,30 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
             return CC_ERR_ARG;
         }
     }
-    // Work items are split by view width: views wider than 16 columns get 8 consumer warps
-    // (each candidate cluster needs a full warp or more), the others 4.  The two launches run
-    // concurrently (the second on an internal stream ordered after / before `stream` by events).
+    // Work items are split three ways; the launches run concurrently (the extra ones on internal
+    // streams ordered after / before `stream` by events):
+    //   * views of one or two normal columns (the caller's n_cols / n_normal hints) -> one warp each
+    //     (rows_narrow_kernel)
+    //   * views wider than 16 columns -> 8 consumer warps (each candidate cluster needs a full warp or more)
+    //   * the others -> 4 consumer warps
+    const int Kcap_ = st->Kcap;
+    auto narrow_bytes = [&](int d) { return 12 * Kcap_ + 16 + 64 * Kcap_ * d + 16 * (Kcap_ + 1); };
+    const bool env_forced = getenv("CGPM_B200_ROWS_NT") != nullptr;
+    const bool narrow_ok = !env_forced && !getenv("CGPM_B200_ROWS_NO_NARROW") && !getenv("CGPM_B200_ROWS_SMEM_KB");
+    auto klass = [&](const cc_row_work& w) -> int {
+        if (narrow_ok && w.n_cols >= 1 && w.n_cols <= 2 && w.n_normal == w.n_cols && narrow_bytes(w.n_cols) <= 64 * 1024) return 0;
+        if (!env_forced && w.n_cols > 16) return 1;
+        return 2;
+    };
     std::vector<cc_row_work> sorted(work, work + n_work);
-    int n_wide = 0;
-    if (!getenv("CGPM_B200_ROWS_NT")) {
-        std::stable_partition(sorted.begin(), sorted.end(), [](const cc_row_work& w) { return w.n_cols > 16; });
-        for (int i = 0; i < n_work; ++i) n_wide += sorted[i].n_cols > 16;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](const cc_row_work& a, const cc_row_work& b) { return klass(a) < klass(b); });
+    int n_narrow = 0, n_wide = 0, dmax_narrow = 0;
+    for (int i = 0; i < n_work; ++i) {
+        const int k = klass(sorted[i]);
+        n_narrow += k == 0; n_wide += k == 1;
+        if (k == 0 && sorted[i].n_cols > dmax_narrow) dmax_narrow = sorted[i].n_cols;
     }
+    const int n_med = n_work - n_narrow - n_wide;
     cc_row_work* dwork = nullptr;
     CC_CUDA(cudaMallocAsync(&dwork, sizeof(cc_row_work) * n_work, stream));
     CC_CUDA(cudaMemcpyAsync(dwork, sorted.data(), sizeof(cc_row_work) * n_work, cudaMemcpyHostToDevice, stream));
@@ -722,13 +1120,21 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     CC_CUDA(cudaGetDevice(&dev));
     CC_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
     CC_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    static cudaStream_t side[64] = {nullptr};
-    static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64] = {nullptr};
-    if (n_wide > 0 && n_wide < n_work && dev >= 0 && dev < 64 && !side[dev]) {
-        CC_CUDA(cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking));
+    if (dev < 0 || dev >= 64) { cc_set_error("cc_transition_rows: device ordinal %d not supported", dev); return CC_ERR_ARG; }
+    static cudaStream_t side[64][2] = {{nullptr, nullptr}};
+    static cudaEvent_t ev_fork[64] = {nullptr}, ev_join[64][2] = {{nullptr, nullptr}};
+    if (!side[dev][0]) {
+        for (int q = 0; q < 2; ++q) {
+            CC_CUDA(cudaStreamCreateWithFlags(&side[dev][q], cudaStreamNonBlocking));
+            CC_CUDA(cudaEventCreateWithFlags(&ev_join[dev][q], cudaEventDisableTiming));
+        }
         CC_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
-        CC_CUDA(cudaEventCreateWithFlags(&ev_join[dev], cudaEventDisableTiming));
     }
+    // shared memory: the single-warp CTAs take what they need; the rest of each SM is divided among
+    // the multi-warp CTAs expected on it
+    const int narrow_need = n_narrow ? narrow_bytes(dmax_narrow) : 0;
+    const int reserve = ((n_narrow + nsm - 1) / nsm) * (narrow_need + 1024);
+    const int n_general = n_wide + n_med;
     int env_nt = 0;
     if (const char* e = getenv("CGPM_B200_ROWS_NT")) { const int v = atoi(e); env_nt = (v == 32 || v == 64 || v == 256) ? v : 128; }
 
@@ -757,7 +1163,9 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
         int per_sm = (total_ctas + nsm - 1) / nsm;
         if (per_sm < 1) per_sm = 1;
         if (per_sm > maxb) per_sm = maxb;
-        int budget = (max_smem + 1024) / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
+        int avail = max_smem + 1024 - reserve;
+        if (avail < (max_smem + 1024) / 2) avail = (max_smem + 1024) / 2;
+        int budget = avail / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
         const int xbytes = 2 * p.B * stagebytes;
         const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 16 + dmax * (p.wide ? 4 : 48) + 512 + 64 + 512 + xbytes;
         bool forced = false;
@@ -783,16 +1191,31 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
         return CC_OK;
     };
     int rc = CC_OK;
-    if (env_nt) rc = launch(sorted.data(), dwork, n_work, env_nt, n_work, stream);
-    else if (n_wide == 0) rc = launch(sorted.data(), dwork, n_work, 128, n_work, stream);
-    else if (n_wide == n_work) rc = launch(sorted.data(), dwork, n_work, 256, n_work, stream);
-    else {
-        CC_CUDA(cudaEventRecord(ev_fork[dev], stream));
-        CC_CUDA(cudaStreamWaitEvent(side[dev], ev_fork[dev], 0));
-        rc = launch(sorted.data(), dwork, n_wide, 256, n_work, side[dev]);
-        if (rc == CC_OK) rc = launch(sorted.data() + n_wide, dwork + n_wide, n_work - n_wide, 128, n_work, stream);
-        CC_CUDA(cudaEventRecord(ev_join[dev], side[dev]));
-        CC_CUDA(cudaStreamWaitEvent(stream, ev_join[dev], 0));
+    const int n_launch = (n_narrow > 0) + (n_wide > 0) + (n_med > 0);
+    if (n_launch > 1) CC_CUDA(cudaEventRecord(ev_fork[dev], stream));
+    int used_side = 0, launched = 0;
+    auto pick_stream = [&]() -> cudaStream_t {
+        if (++launched == n_launch) return stream;          // the last launch goes on the caller's stream
+        cudaStream_t sd = side[dev][used_side++];
+        cudaStreamWaitEvent(sd, ev_fork[dev], 0);
+        return sd;
+    };
+    if (n_wide > 0) rc = launch(sorted.data() + n_narrow, dwork + n_narrow, n_wide, 256, n_general, pick_stream());
+    if (n_narrow > 0 && rc == CC_OK) {
+        RowsParams p;
+        p.st = *st; p.work = dwork; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
+        p.seed = seed; p.counter = counter;
+        p.prof = getenv("CGPM_B200_ROWS_PROF") ? 1 : 0;
+        p.B = 32; p.bulk = 0; p.smem_bytes = narrow_need; p.wide = 0;
+        CC_CUDA(cudaFuncSetAttribute(rows_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, narrow_need));
+        rows_narrow_kernel<<<n_narrow, 32, narrow_need, pick_stream()>>>(p);
+        CC_CUDA(cudaGetLastError());
+    }
+    if (n_med > 0 && rc == CC_OK)
+        rc = launch(sorted.data() + n_narrow + n_wide, dwork + n_narrow + n_wide, n_med, env_nt ? env_nt : 128, n_general, pick_stream());
+    for (int q = 0; q < used_side; ++q) {
+        CC_CUDA(cudaEventRecord(ev_join[dev][q], side[dev][q]));
+        CC_CUDA(cudaStreamWaitEvent(stream, ev_join[dev][q], 0));
     }
     if (rc != CC_OK) return rc;
     CC_CUDA(cudaFreeAsync(dwork, stream));

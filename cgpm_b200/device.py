@@ -287,6 +287,7 @@ class DeviceChains(object):
             arr[i].u_off = w.get('u_off', -1)
             arr[i].trace_off = w.get('trace_off', -1)
             arr[i].n_cols = w.get('n_cols', 0)
+            arr[i].n_normal = w.get('n_normal', 0)
         rc = self.lib.cc_transition_rows(
             C.byref(self.st), n, arr,
             C.c_void_p(perm.data_ptr()) if perm is not None else None,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CC_ABI_VERSION 1
+#define CC_ABI_VERSION 2
 #define CC_NGRID 30          /* hyper-grid points, dim.py:176 n_grid=30        */
 #define CC_NFIELD 8          /* per (cluster, column) statistic fields          */
 
@@ -105,7 +105,8 @@ typedef struct cc_row_work {
     int64_t u_off;        /* into `u`,    or -1: Philox uniforms                  */
     int64_t trace_off;    /* into `trace`, or -1                                  */
     int32_t n_cols;       /* number of columns of the view if the caller knows it (sizes shared memory), else 0 */
-    int32_t _pad;
+    int32_t n_normal;     /* how many of them are normal columns, if the caller knows it, else 0: a view of one or
+                             two normal columns is swept by the single-warp kernel */
 } cc_row_work;
 
 const char* cc_last_error(void);

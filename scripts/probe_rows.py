@@ -30,7 +30,7 @@ for s in range(S):
 dev.rebuild(); dev.sync()
 print('setup %.1fs' % (time.time() - t0))
 nv = dev.t['nv'].cpu().numpy()
-work = [dict(chain=s, view=int(v), n=R, n_cols=int(nv[s][v])) for s in range(S) for v in np.nonzero(nv[s] > 0)[0]]
+work = [dict(chain=s, view=int(v), n=R, n_cols=int(nv[s][v]), n_normal=int(nv[s][v])) for s in range(S) for v in np.nonzero(nv[s] > 0)[0]]
 print('work items', len(work), 'views/chain', len(work) / S)
 print('score0', dev.logpdf_score().cpu().numpy()[:3])
 for it in range(sweeps):

@@ -37,9 +37,11 @@ def test_rebuild_and_score_match_oracle(n_rows, seed):
         assert abs(scores[s] - ref) <= 1e-10 * abs(ref), (scores[s], ref)
 
 
-def rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=False):
+def rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=False, hints=False):
     """One 'rows' kernel call with the host numpy stream injected, mirroring the
-    draw order of View.transition_rows (one permutation + one uniform per row)."""
+    draw order of View.transition_rows (one permutation + one uniform per row).
+    hints: pass the view widths / types (all-normal tables only), which routes views of
+    one or two columns to the single-warp kernel."""
     R = dev.R
     TS = 3 + dev.Kcap
     work, perms, us = [], [], []
@@ -50,6 +52,9 @@ def rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=False):
             us.append(rngs[s].random_sample(R))
             work.append(dict(chain=s, view=v, n=R, perm_is_index=1, perm_off=off, u_off=off,
                              trace_off=(len(work) * R * TS if trace else -1)))
+            if hints:
+                nc = len(list(o.views.values())[v].dims)
+                work[-1].update(n_cols=nc, n_normal=nc)
             off += R
     perm = torch.from_numpy(np.concatenate(perms)).to(dev.device)
     u = torch.from_numpy(np.concatenate(us)).to(dev.device)
@@ -105,3 +110,75 @@ def test_rows_trajectory_matches_oracle(n_rows, seed, kw):
     for s, o in enumerate(oracles):
         ref = o.logpdf_score()
         assert abs(scores[s] - ref) <= 1e-10 * abs(ref)
+
+
+def check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, tag):
+    for s, o in enumerate(oracles):
+        assert rngs[s].random_sample() == o.rng.random_sample()
+        got, dl = device_suffstats(dev, s, ctype)
+        for j, (vid, view) in enumerate(o.views.items()):
+            zr_dev = dl['cid_by_slot'][j][dl['zr'][j]]
+            zr_ref = np.array([view.Zr[i] for i in range(n_rows)])
+            assert np.array_equal(zr_dev, zr_ref), (tag, s, vid)
+            assert np.array_equal(dl['order'][j], np.array(list(view.Zr.keys()))), (tag, s, vid)
+        assert_suffstats_equal(oracle_suffstats(o), got)
+    wi = 0
+    for s, o in enumerate(oracles):
+        for vid in o.views:
+            for i, (rowid, K, logp, zb) in enumerate(otr[s][vid]):
+                rec = tr[wi, i]
+                assert int(rec[0]) == rowid and int(rec[1]) == len(K) and int(rec[2]) == zb, (tag, s, vid, i)
+                got = rec[3:3 + len(K)]
+                ref = np.asarray(logp)
+                assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))), (tag, s, vid, i)
+            wi += 1
+
+
+@pytest.mark.parametrize('n_rows,seed,n_init,narrow', [(60, 5, 3, True), (300, 6, 3, True), (200, 7, 45, True),
+                                                      (300, 6, 3, False), (200, 7, 45, False)])
+def test_rows_trajectory_narrow_views(n_rows, seed, n_init, narrow, monkeypatch):
+    """All-normal table whose views hold one or two columns: with the width / type hints these
+    views go to the single-warp kernel (narrow=True) -- with CGPM_B200_ROWS_NO_NARROW to the
+    general one; both must follow the oracle step by step (n_init = 45 starts from more than
+    32 clusters per view, the multi-pass path of the draw)."""
+    from cgpm_b200.device import DeviceChains
+    from cgpm_b200 import codec
+    from cgpm_b200.synth import gen_table
+    if not narrow:
+        monkeypatch.setenv('CGPM_B200_ROWS_NO_NARROW', '1')
+    monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
+    cct = ['normal'] * 5
+    da = [None] * 5
+    X, _, _ = gen_table(n_rows, cct, da, n_views=2, clusters_per_view=3, seed=seed)
+    rng0 = np.random.RandomState(seed)
+    for _ in range(n_rows // 10):
+        X[rng0.randint(n_rows), rng0.randint(5)] = np.nan
+    ctype, ncat = ctype_arrays(cct, da)
+    S = 2
+    dev = DeviceChains(X, ctype, ncat, S, Kcap=256)
+    oracles = []
+    Zv = {0: 0, 1: 1, 2: 1, 3: 2, 4: 2}
+    for s in range(S):
+        Zrv = {v: [int(z) for z in rng0.randint(n_init, size=n_rows)] for v in range(3)}
+        for v in range(3):                       # cluster ids must be 0..K-1 in order of appearance
+            _, inv = np.unique(Zrv[v], return_inverse=True)
+            Zrv[v] = [int(z) for z in inv]
+        o = co.OState(X, cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, rng=np.random.RandomState(seed * 100 + s))
+        dev.upload_chain(s, codec.pack_chain(oracle_spec(o), n_rows, 5))
+        oracles.append(o)
+    dev.rebuild()
+    dev.sync()
+    rngs = [np.random.RandomState(17 + s) for s in range(S)]
+    for s, o in enumerate(oracles):
+        o.rng.set_state(rngs[s].get_state())
+        for view in o.views.values():
+            view.rng = o.rng
+    views_order = [list(range(len(o.views))) for o in oracles]
+    for sweep in range(3):
+        otr = [dict() for _ in oracles]
+        for s, o in enumerate(oracles):
+            o.transition_view_rows(trace=otr[s])
+        work, tr = rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=True, hints=True)
+        modes = dev.t['seq'].cpu().numpy()[:, :3, 4]
+        assert np.all(modes == (3 if narrow else 0)), modes        # which kernel swept the views
+        check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, (sweep, narrow))
