@@ -72,12 +72,13 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
     // levels 1-3, else levels 2-3); the leaf level stays in the arena (L2)
     extern __shared__ int32_t s_tree[];
     {
-        const int per_warp = (p.smem_l1 ? n1 : 0) + n2 + 32;
+        const int per_warp = (p.smem_l1 ? n1 : 0) + n2 + 32 + 128;
         int32_t* sw = s_tree + (size_t)(threadIdx.x >> 5) * per_warp;
         if (p.smem_l1) { Lv[1] = sw; sw += n1; }
         Lv[2] = sw;
         Lv[3] = sw + n2;
     }
+    int32_t* zs = Lv[3] + 32;               // [128] table ids of the rows of one seating group (device stream only)
     const int nup = (p.smem_l1 ? n1 : 0) + n2 + 32;
     const Philox rng(p.seed);
 
@@ -95,90 +96,157 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         else { const uint4 r4 = rng(p.counter, stream_id(4, s, c)); ai = (int)(((uint64_t)r4.x * CC_NGRID) >> 32); }
         const double alpha = st.row_alpha_grid[ai];
         const long long t0 = clock64();
-        // ---- pass 1: sequential CRP-prior seating (crp.py:71-81) -------------------
-        for (int i = lane; i < (p.smem_l1 ? R : R + n1); i += 32) Lv[0][i] = 0;   // leaf (+ level 1 when it is in the arena)
-        {
-            int32_t* up = p.smem_l1 ? Lv[1] : Lv[2];
-            for (int i = lane; i < nup; i += 32) up[i] = 0;
-        }
-        (void)ntree;
-        __syncwarp();
+        // ---- pass 1: CRP-prior seating of all rows (crp.py:71-81) ----------------------------
         int K = 1;              // tables so far
         int P = 1;              // this lane's inclusive prefix of the counts of tables 0..31 (table 0 holds row 0)
         int reg_total = 1, mem_total = 0;
-        if (lane == 0) z[0] = 0;
-        const uint64_t ustream = stream_id(3, s, c);
-        // Rows are seated in batches of 32: every lane first turns its row's uniform into
-        // t = u (i + alpha) (crp.py:178-182 normalised by N + alpha) and keeps floor(t) and
-        // the "new table" bit t >= i, which do not depend on the seating; the sequential part
-        // of a row is then one shuffle, one integer compare and one ballot (table counts are
-        // integers, so prefix > t  <=>  prefix > floor(t)).
-        for (int i0 = 1; i0 < R; i0 += 32) {
-            const int ii = i0 + lane;
-            double uu = 0.0;
-            if (ii < R) {
-                if (p.u) uu = p.u[(size_t)w * (R - 1) + (ii - 1)];
-                else { const uint4 r4 = rng(p.counter * 0x100000000ull + (uint64_t)ii, ustream); uu = u01_from_words(r4.x, r4.y); }
-            }
-            const double tt = uu * ((double)ii + alpha);
-            int packed = (int)fmin(tt, 2.0e9);                    // floor(t), t >= 0
-            if (tt >= (double)ii) packed |= 0x80000000;           // new table
-            int zreg = 0;
-            const int nb = min(32, R - i0);
-            for (int l = 0; l < nb; ++l) {
-                const int pk = __shfl_sync(0xffffffffu, packed, l);
-                const int tl = pk & 0x7fffffff;
-                int j;
-                // Tables >= 32 live in a 32-ary tree whose nodes store the INCLUSIVE PREFIX of their
-                // children's counts (entries past the last table hold the node total), so a search is
-                // one load + one ballot per level and an update is `entry[lane] += (lane >= child)`.
-                if (pk < 0) {
-                    j = K;                                        // new table (index K)
-                    if (K < 32) { if (lane >= K) P += 1; reg_total += 1; }
-                    else {
-                        const int jp = K - 32;
-                        // a level comes into use when its first node fills up: everything seated so far
-                        // belongs to its child 0
-                        if (jp == 32) Lv[1][lane] = mem_total;
-                        if (jp == 1024) Lv[2][lane] = mem_total;
-                        if (jp == 32768) Lv[3][lane] = mem_total;
-                        __syncwarp();
-                        if (lane >= (jp & 31)) Lv[0][(jp & ~31) + lane] += 1;
-                        if (jp >= 32 && lane >= ((jp >> 5) & 31)) Lv[1][((jp >> 5) & ~31) + lane] += 1;
-                        if (jp >= 1024 && lane >= ((jp >> 10) & 31)) Lv[2][((jp >> 10) & ~31) + lane] += 1;
-                        if (jp >= 32768 && lane >= (jp >> 15)) Lv[3][lane] += 1;
-                        mem_total += 1;
-                        __syncwarp();
-                    }
-                    K += 1;
-                } else if (tl < reg_total) {
-                    const unsigned hit = __ballot_sync(0xffffffffu, P > tl);
-                    j = __ffs(hit) - 1;
-                    if (lane >= j) P += 1;
-                    reg_total += 1;
-                } else {
-                    int tr = tl - reg_total;
-                    const int Kp = K - 32;
-                    const int top = (Kp <= 32) ? 0 : (Kp <= 1024) ? 1 : (Kp <= 32768) ? 2 : 3;
-                    int idx = 0;
-                    for (int lev = top; lev >= 0; --lev) {
-                        int32_t* node = Lv[lev] + idx * 32;
-                        const int inc = node[lane];
-                        unsigned hit = __ballot_sync(0xffffffffu, inc > tr);
-                        if (!hit) hit = 0x80000000u;      // unreachable in exact arithmetic
-                        const int h = __ffs(hit) - 1;
-                        const int excl = __shfl_sync(0xffffffffu, inc, (h + 31) & 31);
-                        if (h > 0) tr -= excl;
-                        if (lane >= h) node[lane] = inc + 1;
-                        idx = idx * 32 + h;
-                    }
-                    __syncwarp();
-                    j = idx + 32;
-                    mem_total += 1;
+        const bool member_draw = (p.u == nullptr);
+        if (member_draw) {
+            // Device stream: row i opens a table with probability alpha / (i + alpha), otherwise it joins the
+            // table of a uniformly chosen earlier ROW -- the same law as choosing a table in proportion to its
+            // size (crp.py:178-182), from the same single uniform t = u (i + alpha): t >= i opens a table,
+            // else floor(t) is the row to join.  Nothing here depends on the table counts, so 128 rows are
+            // seated at a time: rows whose chosen row lies before the group read its table (one gather), the few
+            // that point into the group follow the chain through shared memory.  Table ids are in order of
+            // appearance, exactly as in the sequential draw.  Lv[0] receives the table sizes afterwards.
+            const uint64_t ustream = stream_id(3, s, c);
+            if (lane == 0) z[0] = 0;
+            __syncwarp();
+            for (int i0 = 1; i0 < R; i0 += 128) {
+                int par[4], zreg[4];
+                bool act[4];
+                int nnew_before = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int ii = i0 + q * 32 + lane;
+                    act[q] = ii < R;
+                    double uu = 0.0;
+                    if (act[q]) { const uint4 r4 = rng(p.counter * 0x100000000ull + (uint64_t)ii, ustream); uu = u01_from_words(r4.x, r4.y); }
+                    const double tt = uu * ((double)ii + alpha);
+                    const bool isnew = act[q] && tt >= (double)ii;
+                    par[q] = (int)fmin(tt, 2.0e9);
+                    const unsigned nb = __ballot_sync(0xffffffffu, isnew);
+                    zreg[q] = isnew ? K + nnew_before + __popc(nb & ((1u << lane) - 1u)) : -1;
+                    nnew_before += __popc(nb);
                 }
-                if (lane == l) zreg = j;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (act[q] && zreg[q] < 0 && par[q] < i0) zreg[q] = z[par[q]];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) zs[q * 32 + lane] = zreg[q];
+                __syncwarp();
+                for (;;) {
+                    bool pend = false;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (act[q] && zreg[q] < 0) {
+                            const int zp = zs[par[q] - i0];
+                            if (zp >= 0) zreg[q] = zp; else pend = true;
+                        }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) zs[q * 32 + lane] = zreg[q];
+                    __syncwarp();
+                    if (!__any_sync(0xffffffffu, pend)) break;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (act[q]) z[i0 + q * 32 + lane] = zreg[q];             // coalesced stores
+                K += nnew_before;
+                __syncwarp();
             }
-            if (ii < R) z[ii] = zreg;                             // coalesced store of the batch
+            // table sizes
+            for (int j = lane; j < K; j += 32) Lv[0][j] = 0;
+            __syncwarp();
+            for (int b0 = 0; b0 < R; b0 += 32) {
+                const int i = b0 + lane;
+                const int k = (i < R) ? z[i] : -1;
+                const unsigned peers = __match_any_sync(0xffffffffu, k);
+                if (k >= 0 && (peers >> lane) == 1u) Lv[0][k] += __popc(peers);      // the highest peer adds for the group
+                __syncwarp();
+            }
+        } else {
+            for (int i = lane; i < (p.smem_l1 ? R : R + n1); i += 32) Lv[0][i] = 0;   // leaf (+ level 1 when it is in the arena)
+            {
+                int32_t* up = p.smem_l1 ? Lv[1] : Lv[2];
+                for (int i = lane; i < nup; i += 32) up[i] = 0;
+            }
+            (void)ntree;
+            __syncwarp();
+            if (lane == 0) z[0] = 0;
+            const uint64_t ustream = stream_id(3, s, c);
+            // Rows are seated in batches of 32: every lane first turns its row's uniform into
+            // t = u (i + alpha) (crp.py:178-182 normalised by N + alpha) and keeps floor(t) and
+            // the "new table" bit t >= i, which do not depend on the seating; the sequential part
+            // of a row is then one shuffle, one integer compare and one ballot (table counts are
+            // integers, so prefix > t  <=>  prefix > floor(t)).
+            for (int i0 = 1; i0 < R; i0 += 32) {
+                const int ii = i0 + lane;
+                double uu = 0.0;
+                if (ii < R) {
+                    if (p.u) uu = p.u[(size_t)w * (R - 1) + (ii - 1)];
+                    else { const uint4 r4 = rng(p.counter * 0x100000000ull + (uint64_t)ii, ustream); uu = u01_from_words(r4.x, r4.y); }
+                }
+                const double tt = uu * ((double)ii + alpha);
+                int packed = (int)fmin(tt, 2.0e9);                    // floor(t), t >= 0
+                if (tt >= (double)ii) packed |= 0x80000000;           // new table
+                int zreg = 0;
+                const int nb = min(32, R - i0);
+                for (int l = 0; l < nb; ++l) {
+                    const int pk = __shfl_sync(0xffffffffu, packed, l);
+                    const int tl = pk & 0x7fffffff;
+                    int j;
+                    // Tables >= 32 live in a 32-ary tree whose nodes store the INCLUSIVE PREFIX of their
+                    // children's counts (entries past the last table hold the node total), so a search is
+                    // one load + one ballot per level and an update is `entry[lane] += (lane >= child)`.
+                    if (pk < 0) {
+                        j = K;                                        // new table (index K)
+                        if (K < 32) { if (lane >= K) P += 1; reg_total += 1; }
+                        else {
+                            const int jp = K - 32;
+                            // a level comes into use when its first node fills up: everything seated so far
+                            // belongs to its child 0
+                            if (jp == 32) Lv[1][lane] = mem_total;
+                            if (jp == 1024) Lv[2][lane] = mem_total;
+                            if (jp == 32768) Lv[3][lane] = mem_total;
+                            __syncwarp();
+                            if (lane >= (jp & 31)) Lv[0][(jp & ~31) + lane] += 1;
+                            if (jp >= 32 && lane >= ((jp >> 5) & 31)) Lv[1][((jp >> 5) & ~31) + lane] += 1;
+                            if (jp >= 1024 && lane >= ((jp >> 10) & 31)) Lv[2][((jp >> 10) & ~31) + lane] += 1;
+                            if (jp >= 32768 && lane >= (jp >> 15)) Lv[3][lane] += 1;
+                            mem_total += 1;
+                            __syncwarp();
+                        }
+                        K += 1;
+                    } else if (tl < reg_total) {
+                        const unsigned hit = __ballot_sync(0xffffffffu, P > tl);
+                        j = __ffs(hit) - 1;
+                        if (lane >= j) P += 1;
+                        reg_total += 1;
+                    } else {
+                        int tr = tl - reg_total;
+                        const int Kp = K - 32;
+                        const int top = (Kp <= 32) ? 0 : (Kp <= 1024) ? 1 : (Kp <= 32768) ? 2 : 3;
+                        int idx = 0;
+                        for (int lev = top; lev >= 0; --lev) {
+                            int32_t* node = Lv[lev] + idx * 32;
+                            const int inc = node[lane];
+                            unsigned hit = __ballot_sync(0xffffffffu, inc > tr);
+                            if (!hit) hit = 0x80000000u;      // unreachable in exact arithmetic
+                            const int h = __ffs(hit) - 1;
+                            const int excl = __shfl_sync(0xffffffffu, inc, (h + 31) & 31);
+                            if (h > 0) tr -= excl;
+                            if (lane >= h) node[lane] = inc + 1;
+                            idx = idx * 32 + h;
+                        }
+                        __syncwarp();
+                        j = idx + 32;
+                        mem_total += 1;
+                    }
+                    if (lane == l) zreg = j;
+                }
+                if (ii < R) z[ii] = zreg;                             // coalesced store of the batch
+            }
         }
         __syncwarp();
         const long long t1 = clock64();
@@ -191,7 +259,7 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             for (int b0 = 0; b0 < K; b0 += 32) {
                 const int j = b0 + lane;
                 int cn = 0;
-                if (j < K) cn = (b0 == 0) ? myc : (Lv[0][j - 32] - (((j - 32) & 31) ? Lv[0][j - 33] : 0));
+                if (j < K) cn = member_draw ? Lv[0][j] : (b0 == 0) ? myc : (Lv[0][j - 32] - (((j - 32) & 31) ? Lv[0][j - 33] : 0));
                 const int inc = warp_incl_scan_i(cn, lane);
                 if (j < K) { start[j] = carry + inc - cn; cursor[j] = carry + inc - cn; }
                 carry += __shfl_sync(0xffffffffu, inc, 31);
@@ -527,8 +595,8 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     CC_CUDA(cudaMemsetAsync(dq, 0, sizeof(int), stream));
     p.queue = dq;
     const int nw = tpb / 32;
-    p.smem_l1 = ((size_t)nw * (n1 + n2 + 32) * 4 <= 56 * 1024) ? 1 : 0;
-    const size_t smem = (size_t)nw * ((p.smem_l1 ? n1 : 0) + n2 + 32) * 4;
+    p.smem_l1 = ((size_t)nw * (n1 + n2 + 32 + 128) * 4 <= 56 * 1024) ? 1 : 0;
+    const size_t smem = (size_t)nw * ((p.smem_l1 ? n1 : 0) + n2 + 32 + 128) * 4;
     CC_CUDA(cudaFuncSetAttribute(aux_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     aux_kernel<<<blocks, tpb, smem, stream>>>(p);
     CC_CUDA(cudaGetLastError());

@@ -71,3 +71,82 @@ def test_columns_trace_logps(n_rows=60, seed=21):
         for o in oracles:
             o.transition(N=1, kernels=['rows', 'column_hypers'])
         compare(eng, oracles, ('trace', it))
+
+
+def test_aux_member_draw_partition_law_and_marginal():
+    """Device stream: the auxiliary view's partition is drawn by 'join the table of a uniformly
+    chosen earlier row' (columns.cu).  Check the structure (table ids in order of appearance,
+    stored K), the law (E[K] = sum_i alpha / (alpha + i), Var[K] = sum_i p_i (1 - p_i)), and the
+    column's marginal likelihood under the drawn partition against the oracle's Dim."""
+    import ctypes as C
+    from cgpm_b200.core import Chains
+    from cgpm_b200 import _lib as L
+    from cgpm_b200.synth import gen_table
+    R, S = 3000, 24
+    cct = ['normal', 'categorical', 'normal', 'normal']
+    da = [None, {'k': 3}, None, None]
+    X, _, _ = gen_table(R, cct, da, n_views=2, clusters_per_view=3, seed=3)
+    X[5, 0] = np.nan
+    ch = Chains(X, cctypes=cct, distargs=da, S=S, seed=11, stream='philox')
+    for s in range(S):
+        ch.init_chain(s, np.random.RandomState(50 + s), Zv={c: 0 for c in range(len(cct))}, Zrv={0: [0] * R},
+                      alpha=1.0, view_alphas={0: 1.0})
+    ch.finish_init()
+    dev, st, lib = ch.dev, C.byref(ch.dev.st), ch.dev.lib
+    ncol = len(cct)
+    ch._ensure_arena(S * ncol)
+    assert ch._ensure_aux_store()
+    _p = lambda a: a.ctypes.data_as(C.c_void_p)
+    hyp = dev.t['hyp'].cpu().numpy().reshape(S, ncol, 4)
+    for ai in (8, 15, 22):
+        a_ch = np.repeat(np.arange(S, dtype=np.int32), ncol)
+        a_co = np.tile(np.arange(ncol, dtype=np.int32), S)
+        a_ai = np.full(S * ncol, ai, np.int32)
+        L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), _p(a_ai), None, 2, C.c_uint64(123 + ai),
+                               C.c_uint64(7), dev.stream_ptr()), 'cc_col_aux')
+        dev.sync()
+        zr = dev.aux_zr_all.cpu().numpy().reshape(S, ncol, R)
+        K = dev.t['aux_K_all'].cpu().numpy().reshape(S, ncol)
+        alpha = dev.t['aux_alpha'].cpu().numpy().reshape(S, ncol)
+        colL = dev.t['colL'].cpu().numpy().reshape(S, ncol, dev.Vcap + 1)[:, :, dev.Vcap]
+        a = float(alpha[0, 0])
+        assert np.all(alpha == a)
+        i = np.arange(R)
+        pnew = a / (a + i)
+        mean, var = pnew.sum(), (pnew * (1 - pnew)).sum()
+        for s in range(S):
+            for c in range(ncol):
+                z = zr[s, c]
+                # ids appear in increasing order: a new maximum is always the next integer
+                run_max = np.maximum.accumulate(z)
+                assert z[0] == 0 and np.all(np.diff(run_max) <= 1) and run_max[-1] == K[s, c] - 1
+        ks = K.reshape(-1).astype(float)
+        assert abs(ks.mean() - mean) < 4.5 * np.sqrt(var / ks.size) + 1e-9, (ai, ks.mean(), mean)
+        assert 0.5 * var < ks.var() + 1e-9 < 1.8 * var + 1.0, (ai, ks.var(), var)
+        # marginal of a few (chain, column) pairs under their partition: the oracle's Dim
+        for s, c in [(0, 0), (1, 1), (2, 2), (S - 1, 3)]:
+            ref = oracle_marginal(X[:, c], zr[s, c], cct[c], da[c], hyp[s, c])
+            assert abs(colL[s, c] - ref) <= 1e-9 * max(1.0, abs(ref)), (ai, s, c, colL[s, c], ref)
+
+
+def oracle_marginal(x, z, cctype, distargs, hyp):
+    """Sum over tables of the cluster marginal likelihood (normal.py:175-181, categorical.py:144-155)."""
+    from math import lgamma, log, pi
+    tot = 0.0
+    for k in np.unique(z):
+        xs = x[z == k]
+        xs = xs[~np.isnan(xs)]
+        if cctype == 'normal':
+            m, r, s, nu = [float(v) for v in hyp]
+            N = len(xs); sx = float(np.sum(xs)); sxx = float(np.sum(xs * xs))
+            rn = r + N; nun = nu + N; mn = (r * m + sx) / rn
+            sn = s + sxx + r * m * m - rn * mn * mn
+            if sn == 0: sn = s
+            Z = lambda r_, s_, nu_: ((nu_ + 1.0) / 2.0) * log(2) + 0.5 * log(pi) - 0.5 * log(r_) - (nu_ / 2.0) * log(s_) + lgamma(nu_ / 2.0)
+            tot += -(N / 2.0) * log(2 * pi) + Z(rn, sn, nun) - Z(r, s, nu)
+        else:
+            a = float(hyp[0]); kc = int(distargs['k'])
+            cnt = np.bincount(xs.astype(int), minlength=kc)
+            N = cnt.sum(); A = kc * a
+            tot += lgamma(A) - lgamma(A + N) + sum(lgamma(c_ + a) for c_ in cnt) - kc * lgamma(a)
+    return tot
