@@ -93,11 +93,11 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
 // Everything a sweep needs, resolved once per CTA.
 struct Ctx {
     cc_state st;
-    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride, wide;
+    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride, wide, allnorm;
     size_t sv;
     // shared memory
     uint64_t *bar_full, *bar_empty;
-    int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice, 9 destination slot, 10 new-cluster flag
+    int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice, 9 destination slot, 10 new-cluster flag, 11 all-normal view
     int *live, *nk;
     double* lp;
     double* w;              // [Kcap+1] CRP weight of each candidate (written with lp)
@@ -118,25 +118,108 @@ struct Ctx {
 template <bool GT>
 struct Tab {
     const Ctx& c;
-    double* gf[CC_NFIELD];
+    double* f0;        // field 0 of (cluster 0, column 0)
+    size_t fs;         // distance between two fields of one (cluster, column) cell
     double* gcnt;
     __device__ __forceinline__ Tab(const Ctx& cx) : c(cx) {
         if (GT) {
-#pragma unroll
-            for (int f = 0; f < CC_NFIELD; ++f) gf[f] = stat_field(cx.st, cx.s, f);
+            f0 = stat_field(cx.st, cx.s, 0);
+            fs = (size_t)cx.st.Kcap * cx.st.C;
             gcnt = cx.st.cnt + (size_t)cx.s * cx.st.Kcap * cx.st.CT;
+        } else {
+            f0 = cx.tab;
+            fs = (size_t)cx.Kc * cx.D;
+            gcnt = nullptr;
         }
     }
-    __device__ __forceinline__ double& at(int f, int k, int j) const {
-        if (GT) return gf[f][(size_t)k * c.st.C + c.col[j]];
-        return c.tab[f * (c.Kc * c.D) + k * c.D + j];
+    // field f of the cell is cell(k, j)[f * fs]
+    __device__ __forceinline__ double* cell(int k, int j) const {
+        if (GT) return f0 + (size_t)k * c.st.C + c.col[j];
+        return f0 + k * c.D + j;
     }
+    __device__ __forceinline__ double& at(int f, int k, int j) const { return cell(k, j)[f * fs]; }
     __device__ __forceinline__ double* counts(int k, int j) const {
         if (GT) return gcnt + (size_t)k * c.st.CT + c.st.catoff[c.col[j]];
         return c.tab + CC_NFIELD * c.Kc * c.D + k * c.CTv + c.cto[j];
     }
     __device__ __forceinline__ int prior() const { return GT ? (c.st.Kcap - 1) : (c.Kc - 1); }
 };
+
+__device__ __forceinline__ double hyper(const Ctx& c, bool wide, const double* ghyp, int f, int j) {
+    return wide ? __ldg(&ghyp[c.col[j] * 4 + f]) : c.hyp[f * c.D + j];
+}
+
+// Normal cell of one row against one candidate cluster.
+//   other cluster: cst - b log(1 + a (x-mn)^2)   (Student-t form, cached a, mn, cst)
+//   own cluster  : the row is removed first (view.py:416-419).  With sn1 = sn - rn/(rn-1) (x-mn)^2 (the
+//     Normal-Gamma downdate; rn, mn, sn, a = rn/((rn+1) sn) of the cluster WITH the row) the predictive
+//     G(N-1) - b1 log sn + (b1-1/2) log sn1 becomes cst + G(N-1) - G(N) + (b1-1/2) log(1 - a (rn+1)/(rn-1)
+//     (x-mn)^2): the same loads and the same single log as for any other cluster.  Heavy cancellation
+//     (arg < 2^-20) takes the reference's posterior update of the decremented sums instead.  A singleton's
+//     own cluster without the row IS the empty cluster (the caller passes that cell as p).  The `-= x; += x`
+//     replay (view.py:416-419) is reported in `drift`: set if the sums come back changed.
+// p: the candidate's cell (field f at p[f * fs]); po: the cell of the row's own cluster (k), read only if `own`.
+// ms(m, s): loads the two hyperparameters only the rare exact branch needs.
+template <typename FS, typename MS>
+__device__ __forceinline__ double normal_core(const double* p, const double* po, FS fs, double x, double nu, double rr,
+                                              bool own, bool dn, int& drift, MS ms) {
+    const double Nf = p[CC_F_N * fs];
+    const double zz = x - p[CC_F_MN * fs];
+    double sc = p[CC_F_A * fs];
+    double bs = p[CC_F_CST * fs];
+    double coef = -0.5 * (nu + Nf + 1.0);
+    if (own) {
+        const double sx0 = po[CC_F_SX * fs], sxx0 = po[CC_F_SXX * fs];
+        const double xx = __dmul_rn(x, x);
+        const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
+        if (!isnan(x) && (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, xx) != sxx0)) drift = 1;
+        if (dn) {
+            const double rn = rr + Nf;
+            sc = -sc * ((rn + 1.0) * __drcp_rn(rn - 1.0));
+            coef = 0.5 * (nu + Nf - 1.0);
+            bs += p[CC_F_GM1 * fs] - p[CC_F_GN * fs];
+            if (!(fma(sc * zz, zz, 1.0) >= 0x1p-20)) {
+                double m, ss;
+                ms(m, ss);
+                const double N1 = Nf - 1.0;
+                const double rn1 = rr + N1;
+                const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
+                double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
+                                       __dmul_rn(__dmul_rn(rn1, mn1), mn1));
+                if (sn1 == 0.0) sn1 = ss;
+                const double b1 = 0.5 * (nu + N1 + 1.0);
+                bs = p[CC_F_GM1 * fs] - b1 * (2.0 * (p[CC_F_GN * fs] - p[CC_F_CST * fs]));
+                const double t = bs + coef * log(sn1);
+                return isnan(x) ? 0.0 : t;
+            }
+        }
+    }
+    const double t = bs + coef * log(fma(sc * zz, zz, 1.0));
+    return isnan(x) ? 0.0 : t;                                   // dim.py:130-132
+}
+
+
+template <bool GT>
+__device__ __forceinline__ double normal_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp,
+                                              const double* xrow, int j, int k, int ke, bool own, bool dn, int& drift) {
+    const double x = xrow[c.bulk ? c.col[j] : j];
+    return normal_core(T.cell(ke, j), T.cell(k, j), T.fs, x, hyper(c, wide, ghyp, 3, j), hyper(c, wide, ghyp, 1, j),
+                       own, dn, drift, [&](double& m, double& ss) { m = hyper(c, wide, ghyp, 0, j); ss = hyper(c, wide, ghyp, 2, j); });
+}
+
+// Categorical cell: log((a + count_x) / (N + a k)), counts without the row for its own cluster.
+template <bool GT>
+__device__ __forceinline__ double categorical_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp,
+                                                   const double* xrow, int j, int k, bool own, bool empty) {
+    const double x = xrow[c.bulk ? c.col[j] : j];
+    if (isnan(x)) return 0.0;
+    const double a = hyper(c, wide, ghyp, 0, j);
+    const int xi = (int)x, kc = wide ? c.st.ncat[c.col[j]] : c.ncat[j];
+    if (empty) return log(a) - log(a * kc);
+    const double cntx = T.counts(k, j)[xi];
+    if (!own) return log(a + cntx) - T.at(CC_F_CST, k, j);
+    return log(a + (cntx - 1.0)) - log((T.at(CC_F_N, k, j) - 1.0) + a * kc);
+}
 
 // One pass over rows [i_begin, n).  Returns n when finished, or the index of the row whose
 // move needs a cluster slot that does not fit in shared memory (GT = false only): the caller
@@ -152,12 +235,14 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
     const int pslot = T.prior();
     // per-column hyperparameters / types: shared memory, or global memory for very wide views
     const double* ghyp = c.st.hyp + (size_t)c.s * c.st.C * 4;
+    const bool wide = c.wide != 0;
+    const bool allnorm = c.allnorm != 0;
     auto H = [&](int f, int j) -> double { return c.wide ? __ldg(&ghyp[c.col[j] * 4 + f]) : c.hyp[f * D + j]; };
     auto CTYPE = [&](int j) -> int { return c.wide ? c.st.ctype[c.col[j]] : c.ctype[j]; };
     auto NCAT = [&](int j) -> int { return c.wide ? c.st.ncat[c.col[j]] : c.ncat[j]; };
 
     const int lgB = 31 - __clz(B);                 // B is a power of two
-    const int gmask = ngroups - 1;                 // so is ngroups
+    const int gmask = ngroups - 1;                 // highest group index (ngroups is 7, 14, ... for NT = 224)
     for (int i = i_begin; i < n; ++i) {
         const int b = i >> lgB, slot = i & (B - 1), buf = b & 1;
         if (slot == 0 || i == i_begin) mbar_wait(&c.bar_full[buf], (b >> 1) & 1);
@@ -178,49 +263,27 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
             const bool active = pc < ncand;
             const int k = (active && pc < K) ? c.live[pc] : pslot;
             const bool own = active && (pc < K) && (k == z);
+            // a singleton's own cluster without the row IS the empty cluster (exactly)
+            const int ke = (own && singleton) ? pslot : k;
+            const bool dn = own && !singleton;
+            int drift = 0;               // (the `-= x; += x` replay itself is step 2 here)
             double acc = 0.0;
-            for (int j = gl; active && j < D; j += G) {
-                const double x = xrow[c.bulk ? c.col[j] : j];
-                if (isnan(x)) continue;                                  // dim.py:130-132
-                if (CTYPE(j) == CC_NORMAL) {
-                    // Both cases end in ONE log of a different argument, so the own cluster's group does
-                    // not serialise a second transcendental against the other groups of its warp:
-                    //   other cluster: cst - b log(1 + a (x-mn)^2)            (Student-t form, cached a, mn, cst)
-                    //   own cluster  : G(N1) - b1 log sn + (b1 - 1/2) log sn1 (view.py:416-419: the row is removed
-                    //                  first; sn1 from the reference's posterior update of the decremented sums,
-                    //                  log sn = 2 (G(N) - cst) is cached; the re-incorporation is step 2)
-                    const double nu = H(3, j);
-                    double arg, coef, base;
-                    if (!own) {
-                        const double zz = x - T.at(CC_F_MN, k, j);
-                        arg = fma(T.at(CC_F_A, k, j) * zz, zz, 1.0);
-                        coef = -0.5 * (nu + T.at(CC_F_N, k, j) + 1.0);
-                        base = T.at(CC_F_CST, k, j);
-                    } else {
-                        const double N1 = T.at(CC_F_N, k, j) - 1.0;
-                        const double sx1 = __dsub_rn(T.at(CC_F_SX, k, j), x);
-                        const double sxx1 = __dsub_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
-                        const double m = H(0, j), rr = H(1, j), ss = H(2, j);
-                        const double rn1 = rr + N1;
-                        const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
-                        double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
-                                               __dmul_rn(__dmul_rn(rn1, mn1), mn1));
-                        if (sn1 == 0.0) sn1 = ss;
-                        const double b1 = 0.5 * (nu + N1 + 1.0);
-                        arg = sn1;
-                        coef = b1 - 0.5;
-                        base = T.at(CC_F_GM1, k, j) - b1 * (2.0 * (T.at(CC_F_GN, k, j) - T.at(CC_F_CST, k, j)));
+            if (active) {
+                if (allnorm && D > G) {
+                    // two columns per lane and trip: independent chains, so the two logs overlap
+                    for (int j = gl; j < D; j += 2 * G) {
+                        const int j2 = j + G;
+                        const double t1 = normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
+                        const double t2 = normal_term<GT>(c, T, wide, ghyp, xrow, j2 < D ? j2 : j, k, ke, own, dn, drift);
+                        acc += t1;
+                        if (j2 < D) acc += t2;
                     }
-                    acc += base + coef * log(arg);
+                } else if (allnorm) {
+                    if (gl < D) acc = normal_term<GT>(c, T, wide, ghyp, xrow, gl, k, ke, own, dn, drift);
                 } else {
-                    const double a = H(0, j);
-                    const int xi = (int)x, kc = NCAT(j);
-                    if (pc >= K) acc += log(a) - log(a * kc);            // empty cluster
-                    else {
-                        const double cntx = T.counts(k, j)[xi];
-                        if (!own) acc += log(a + cntx) - T.at(CC_F_CST, k, j);
-                        else acc += log(a + (cntx - 1.0)) - log((T.at(CC_F_N, k, j) - 1.0) + a * kc);
-                    }
+                    for (int j = gl; j < D; j += G)
+                        acc += (CTYPE(j) == CC_NORMAL) ? normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift)
+                                                       : categorical_term<GT>(c, T, wide, ghyp, xrow, j, k, own, pc >= K);
                 }
             }
             for (int o = G >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -299,7 +362,7 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
                 c.scal[8] = choice; c.scal[9] = dst; c.scal[10] = nc;
             }
         }
-        if (gid == gmask - (c.scal[4] & gmask)) {
+        if (gid == gmask - ((NT & (NT - 1)) ? (c.scal[4] % ngroups) : (c.scal[4] & gmask))) {
             // view.py:419: incorporate the row back; the sums may differ from before in the last bit
             for (int j = gl; j < D; j += G) {
                 if (CTYPE(j) != CC_NORMAL) continue;
@@ -471,10 +534,11 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     const size_t tab_avail = (p.smem_bytes > (int)off) ? (size_t)p.smem_bytes - off : 0;
 
     if (tid == 0) {
-        int j = 0, ct = 0;
+        int j = 0, ct = 0, alln = 1;
         for (int q = 0; q < C; ++q)
             if (zv[q] == v) {
                 c.col[j] = q;
+                if (st.ctype[q] != CC_NORMAL) alln = 0;
                 if (!p.wide) {
                     c.cto[j] = ct;
                     c.ctype[j] = st.ctype[q];
@@ -484,6 +548,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
                 ++j;
             }
         c.scal[6] = ct;
+        c.scal[11] = alln;
         c.scal[3] = 0;
         c.scal[7] = 0;
     }
@@ -504,6 +569,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     __syncthreads();
     const int CTv = c.scal[6];
     c.CTv = CTv;
+    c.allnorm = c.scal[11];
     c.K0 = K0;
     // shared-table capacity: Kc cluster slots (the empty-cluster record sits at slot Kc-1)
     const size_t per_cluster = (size_t)(CC_NFIELD * D + CTv) * sizeof(double);
@@ -682,56 +748,6 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         }
     }
 }
-
-// Normal cell of one row against one candidate cluster.
-//   other cluster: cst - b log(1 + a (x-mn)^2)   (Student-t form, cached a, mn, cst)
-//   own cluster  : the row is removed first (view.py:416-419).  With sn1 = sn - rn/(rn-1) (x-mn)^2 (the
-//     Normal-Gamma downdate; rn, mn, sn, a = rn/((rn+1) sn) of the cluster WITH the row) the predictive
-//     G(N-1) - b1 log sn + (b1-1/2) log sn1 becomes cst + G(N-1) - G(N) + (b1-1/2) log(1 - a (rn+1)/(rn-1)
-//     (x-mn)^2): the same loads and the same single log as for any other cluster.  Heavy cancellation
-//     (arg < 2^-20) takes the reference's posterior update of the decremented sums instead.  A singleton's
-//     own cluster without the row IS the empty cluster (the caller passes that cell as p).  The `-= x; += x`
-//     replay (view.py:416-419) is reported in `drift`: set if the sums come back changed.
-// p: the candidate's cell (field f at p[f * fs]); po: the cell of the row's own cluster (k), read only if `own`.
-// ms(m, s): loads the two hyperparameters only the rare exact branch needs.
-template <typename FS, typename MS>
-__device__ __forceinline__ double normal_core(const double* p, const double* po, FS fs, double x, double nu, double rr,
-                                              bool own, bool dn, int& drift, MS ms) {
-    const double Nf = p[CC_F_N * fs];
-    const double zz = x - p[CC_F_MN * fs];
-    double sc = p[CC_F_A * fs];
-    double bs = p[CC_F_CST * fs];
-    double coef = -0.5 * (nu + Nf + 1.0);
-    if (own) {
-        const double sx0 = po[CC_F_SX * fs], sxx0 = po[CC_F_SXX * fs];
-        const double xx = __dmul_rn(x, x);
-        const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
-        if (!isnan(x) && (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, xx) != sxx0)) drift = 1;
-        if (dn) {
-            const double rn = rr + Nf;
-            sc = -sc * ((rn + 1.0) * __drcp_rn(rn - 1.0));
-            coef = 0.5 * (nu + Nf - 1.0);
-            bs += p[CC_F_GM1 * fs] - p[CC_F_GN * fs];
-            if (!(fma(sc * zz, zz, 1.0) >= 0x1p-20)) {
-                double m, ss;
-                ms(m, ss);
-                const double N1 = Nf - 1.0;
-                const double rn1 = rr + N1;
-                const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
-                double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
-                                       __dmul_rn(__dmul_rn(rn1, mn1), mn1));
-                if (sn1 == 0.0) sn1 = ss;
-                const double b1 = 0.5 * (nu + N1 + 1.0);
-                bs = p[CC_F_GM1 * fs] - b1 * (2.0 * (p[CC_F_GN * fs] - p[CC_F_CST * fs]));
-                const double t = bs + coef * log(sn1);
-                return isnan(x) ? 0.0 : t;
-            }
-        }
-    }
-    const double t = bs + coef * log(fma(sc * zz, zz, 1.0));
-    return isnan(x) ? 0.0 : t;                                   // dim.py:130-132
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // Narrow views (one or two normal columns): one warp per (chain, view), no CTA barriers at all.
@@ -1091,7 +1107,8 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     // streams ordered after / before `stream` by events):
     //   * views of one or two normal columns (the caller's n_cols / n_normal hints) -> one warp each
     //     (rows_narrow_kernel)
-    //   * views wider than 16 columns -> 8 consumer warps (each candidate cluster needs a full warp or more)
+    //   * views wider than 16 columns -> 7 consumer warps (each candidate cluster needs a full warp or more;
+    //     with the producer warp that is 256 threads, i.e. 128 registers each at two CTAs per SM)
     //   * the others -> 4 consumer warps
     const int Kcap_ = st->Kcap;
     auto narrow_bytes = [&](int d) { return 12 * Kcap_ + 16 + 64 * Kcap_ * d + 16 * (Kcap_ + 1); };
@@ -1181,8 +1198,8 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
             CC_CUDA(cudaFuncSetAttribute(rows_kernel<64, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             rows_kernel<64, 5><<<cnt, 96, budget, strm>>>(p);
         } else if (nt == 256) {
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            rows_kernel<256, 2><<<cnt, 288, budget, strm>>>(p);
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<224, 2><<<cnt, 256, budget, strm>>>(p);
         } else {
             CC_CUDA(cudaFuncSetAttribute(rows_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             rows_kernel<128, 3><<<cnt, 160, budget, strm>>>(p);
