@@ -128,6 +128,52 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
     const double h0 = hyp[0], h1 = hyp[1], h2 = hyp[2], h3 = hyp[3];
     const double* X = st.Xrm + c;
 
+    if (p.marginal && __syncthreads_and(!act || ctype == CC_NORMAL)) {
+        // MARGINAL mode, all-normal tile: the marginals are proposal weights (state.py:1065-1072), compared
+        // with the reference to 1e-5, so a cluster's sums need not follow the member order bit by bit.  All
+        // NW warps share every cluster: contiguous eighths of its member list, partial sums combined in warp
+        // order (deterministic).  A view with one dominant cluster no longer waits for a single warp.
+        __shared__ double s_p[NW][3][32];
+        double tot = 0.0;
+        for (int pos = 0; pos < K; ++pos) {
+            const int k = live[pos];
+            const int beg = start[k], end = start[k + 1];
+            const int chunk = (((end - beg) + NW - 1) / NW + 7) & ~7;
+            int i = beg + warp * chunk;
+            const int e = min(end, i + chunk);
+            double N = 0.0, sx = 0.0, sxx = 0.0;
+            for (; i + 8 <= e; i += 8) {
+                int rr[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) rr[q] = grouped[i + q];
+                if (act) {
+                    double xv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) xv[q] = X[(size_t)rr[q] * Cp];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (!isnan(xv[q])) { N += 1.0; sx = __dadd_rn(sx, xv[q]); sxx = __dadd_rn(sxx, __dmul_rn(xv[q], xv[q])); }
+                }
+            }
+            for (; i < e; ++i) {
+                const int r0 = grouped[i];
+                if (act) {
+                    const double x0 = X[(size_t)r0 * Cp];
+                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                }
+            }
+            s_p[warp][0][lane] = N; s_p[warp][1][lane] = sx; s_p[warp][2][lane] = sxx;
+            __syncthreads();
+            if (warp == 0 && act) {
+                double tN = 0.0, tsx = 0.0, tsxx = 0.0;
+                for (int q = 0; q < NW; ++q) { tN += s_p[q][0][lane]; tsx += s_p[q][1][lane]; tsxx += s_p[q][2][lane]; }
+                tot += normal_marginal(tN, tsx, tsxx, h0, h1, h2, h3);
+            }
+            __syncthreads();
+        }
+        if (warp == 0 && act) st.colL[((size_t)s * C + c) * (st.Vcap + 1) + v] = tot;
+        return;
+    }
     double lacc = 0.0;     // MARGINAL: this warp's partial over its clusters
     for (int pos = warp; pos < K + (p.marginal ? 0 : 1); pos += NW) {
         // pos == K (TABLE mode): the prior (empty-cluster) record at slot Kcap-1
