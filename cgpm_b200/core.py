@@ -457,7 +457,7 @@ class Chains(object):
         R = self.R
         n1 = (R + 31) >> 5
         n2 = (n1 + 31) >> 5
-        per = (R + (R + n1 + n2 + 32) + (R + 1) + R + R + 3) & ~3
+        per = (max(R + (R + n1 + n2 + 32) + (R + 1) + R + R, ((R + 7) & ~7) + 8 * R) + 7) & ~7      # columns.cu: cc_col_aux
         want = min(max(n_pairs, 1), 148 * 32)
         free, _total = torch.cuda.mem_get_info(dev.device)
         budget = max(int(free * 0.5), per * 4)

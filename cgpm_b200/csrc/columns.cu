@@ -155,10 +155,10 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                 K += nnew_before;
                 __syncwarp();
             }
-            // table sizes
-            for (int j = lane; j < K; j += 32) Lv[0][j] = 0;
+            // table sizes (only the grouped statistics pass of categorical columns needs them)
+            if (st.ctype[c] != CC_NORMAL) for (int j = lane; j < K; j += 32) Lv[0][j] = 0;
             __syncwarp();
-            for (int b0 = 0; b0 < R; b0 += 32) {
+            for (int b0 = 0; st.ctype[c] != CC_NORMAL && b0 < R; b0 += 32) {
                 const int i = b0 + lane;
                 const int k = (i < R) ? z[i] : -1;
                 const unsigned peers = __match_any_sync(0xffffffffu, k);
@@ -250,6 +250,58 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         }
         __syncwarp();
         const long long t1 = clock64();
+        if (member_draw && st.ctype[c] == CC_NORMAL) {
+            // ---- pass 2, normal column on the device stream: rows in their natural order, one 32-byte record
+            //      (sum_x, sum_x_sq, count of present cells) per table.  The lowest lane of each group of rows
+            //      that share a table loads the record, adds the group's cells in row order and stores it, so
+            //      every table's sums are accumulated in row order exactly as before -- without the grouping
+            //      pass, the table-size pass and the gathers through it (one random record per row instead of
+            //      five random accesses).
+            double* rec = reinterpret_cast<double*>(base + ((R + 7) & ~7));
+            for (int e = lane; e < 4 * K; e += 32) rec[e] = 0.0;
+            if (p.write_zr == 1 && lane == 0) st.aux_K[s] = K;
+            if (p.write_zr == 2 && lane == 0) st.aux_K_all[(size_t)s * st.C + c] = K;
+            __syncwarp();
+            const double* xc = st.Xcm + (size_t)c * R;
+            for (int b0 = 0; b0 < R; b0 += 32) {
+                const int i = b0 + lane;
+                const bool act = i < R;
+                const int k = act ? z[i] : -1;
+                const double x = act ? xc[i] : CUDART_NAN;
+                if (act && p.write_zr == 1) st.aux_zr[(size_t)s * R + i] = k;
+                if (act && p.write_zr == 2) st.aux_zr_all[((size_t)s * st.C + c) * R + i] = k;
+                const unsigned peers = __match_any_sync(0xffffffffu, k);
+                const bool leader = act && (__ffs(peers) - 1 == lane);
+                double sx = 0.0, sxx = 0.0, cn = 0.0;
+                if (leader) { sx = rec[4 * k]; sxx = rec[4 * k + 1]; cn = rec[4 * k + 2]; }
+                if (__all_sync(0xffffffffu, !act || peers == (1u << lane))) {
+                    if (leader && !isnan(x)) { cn += 1.0; sx = __dadd_rn(sx, x); sxx = __dadd_rn(sxx, __dmul_rn(x, x)); }
+                } else {
+                    for (int l = 0; l < 32; ++l) {
+                        const int kl = __shfl_sync(0xffffffffu, k, l);
+                        const double xl = __shfl_sync(0xffffffffu, x, l);
+                        if (leader && kl == k && !isnan(xl)) { cn += 1.0; sx = __dadd_rn(sx, xl); sxx = __dadd_rn(sxx, __dmul_rn(xl, xl)); }
+                    }
+                }
+                if (leader) { rec[4 * k] = sx; rec[4 * k + 1] = sxx; rec[4 * k + 2] = cn; }
+                __syncwarp();
+            }
+            const double* hyp = st.hyp + ((size_t)s * st.C + c) * 4;
+            const double h0 = hyp[0], h1 = hyp[1], h2 = hyp[2], h3 = hyp[3];
+            double lsum = 0.0;
+            for (int j = lane; j < K; j += 32) lsum += normal_marginal(rec[4 * j + 2], rec[4 * j], rec[4 * j + 1], h0, h1, h2, h3);
+            lsum = warp_sum(lsum);
+            if (lane == 0) {
+                st.colL[((size_t)s * st.C + c) * (st.Vcap + 1) + st.Vcap] = lsum;
+                st.aux_alpha[(size_t)s * st.C + c] = alpha;
+                if (p.prof) {
+                    int32_t* q = st.seq + ((size_t)s * st.C + c) * 4;
+                    q[0] = (int)((t1 - t0) >> 10); q[1] = (int)((clock64() - t1) >> 10); q[2] = K; q[3] = ai;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         // ---- pass 2: ordered per-table statistics of column c, marginal ------------
         // counts -> start offsets
         {
@@ -570,7 +622,9 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     const int R = st->R;
     const size_t n1 = (R + 31) >> 5, n2 = (n1 + 31) >> 5;
     size_t per = (size_t)R + (R + n1 + n2 + 32) + (R + 1) + R + R;
-    per = (per + 3) & ~(size_t)3;
+    const size_t per_direct = (((size_t)R + 7) & ~(size_t)7) + 8 * (size_t)R;      // z + one 32-byte record per table
+    if (per_direct > per) per = per_direct;
+    per = (per + 7) & ~(size_t)7;
     const size_t avail = (size_t)st->arena_bytes / sizeof(int32_t);
     if (!st->arena || avail < per) { cc_set_error("cc_col_aux: arena too small (%lld bytes, need %lld per worker)", (long long)st->arena_bytes, (long long)(per * 4)); return CC_ERR_ARG; }
     int nworkers = (int)(avail / per);
