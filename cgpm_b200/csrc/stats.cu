@@ -19,16 +19,18 @@
 namespace {
 
 // ---------------------------------------------------------------------------
-// One warp per (chain, view): rows grouped by cluster slot, members of a
-// cluster in `order` order.  grouped = st.moved (scratch), gstart = st.seq[0..Kcap)
-// of the same (chain, view) is NOT used (seq may be shorter than Kcap); the
-// start offsets go to `gstart` [n_work][Kcap+1].
+// One CTA per (chain, view): rows grouped by cluster slot, members of a cluster in `order`
+// order (a stable counting sort).  The NW warps take contiguous chunks of the member order:
+// each counts its chunk per cluster, the counts are scanned over (cluster, warp) on top of the
+// clusters' start offsets, and each warp scatters its chunk from its own cursors -- so rows of
+// a cluster keep their relative order within and across chunks.  grouped = st.moved (scratch);
+// the start offsets go to `gstart` [n_work][Kcap+1].  Shared memory: NW * Kcap ints.
 __global__ void group_kernel(const cc_state st, int n_work, const int32_t* __restrict__ chains,
                              const int32_t* __restrict__ views, int32_t* __restrict__ gstart) {
     const int w = blockIdx.x;
     if (w >= n_work) return;
     const int s = chains[w], v = views[w];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const size_t sv = sv_index(st, s, v);
     const int R = st.R, Kcap = st.Kcap;
     const int32_t* order = st.order + sv * R;
@@ -36,35 +38,56 @@ __global__ void group_kernel(const cc_state st, int n_work, const int32_t* __res
     const int32_t* nk = st.nk + sv * Kcap;
     int32_t* grouped = st.moved + sv * R;
     int32_t* start = gstart + (size_t)w * (Kcap + 1);
-    extern __shared__ int s_cursor[];                  // [Kcap]
-    // exclusive scan of nk over slots (serial chunks of 32)
-    int carry = 0;
-    for (int base = 0; base < Kcap; base += 32) {
-        const int k = base + lane;
-        const int c = (k < Kcap) ? nk[k] : 0;
-        int inc = c;
+    extern __shared__ int s_cnt[];                     // [NW][Kcap] chunk counts, then cursors
+    int* mine = s_cnt + warp * Kcap;
+    for (int k = lane; k < Kcap; k += 32) mine[k] = 0;
+    // start offsets: exclusive scan of nk over slots (warp 0, serial chunks of 32)
+    if (warp == 0) {
+        int carry = 0;
+        for (int base = 0; base < Kcap; base += 32) {
+            const int k = base + lane;
+            const int c = (k < Kcap) ? nk[k] : 0;
+            int inc = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (k < Kcap) start[k] = carry + inc - c;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (k < Kcap) { start[k] = carry + inc - c; s_cursor[k] = carry + inc - c; }
-        carry += __shfl_sync(0xffffffffu, inc, 31);
+        if (lane == 0) start[Kcap] = carry;
     }
-    if (lane == 0) start[Kcap] = carry;
     __syncwarp();
-    // stable scatter
-    for (int base = 0; base < R; base += 32) {
+    // this warp's chunk of the member order (a multiple of 32 rows)
+    const int per = (((R + NW - 1) / NW) + 31) & ~31;
+    const int lo = warp * per, hi = min(R, lo + per);
+    for (int base = lo; base < hi; base += 32) {
         const int i = base + lane;
-        const bool act = i < R;
+        const int k = (i < hi) ? zr[order[i]] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, k);
+        if (k >= 0 && (peers >> lane) == 1u) mine[k] += __popc(peers);      // the highest peer adds for the group
+        __syncwarp();
+    }
+    __syncthreads();
+    // cursors: start[k] + the counts of the earlier chunks
+    for (int k = threadIdx.x; k < Kcap; k += blockDim.x) {
+        int run = start[k];
+        for (int q = 0; q < NW; ++q) { const int c = s_cnt[q * Kcap + k]; s_cnt[q * Kcap + k] = run; run += c; }
+    }
+    __syncthreads();
+    // stable scatter of the chunk
+    for (int base = lo; base < hi; base += 32) {
+        const int i = base + lane;
+        const bool act = i < hi;
         int r = 0, k = -1;
         if (act) { r = order[i]; k = zr[r]; }
         const unsigned peers = __match_any_sync(0xffffffffu, k);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         int pos = 0;
-        if (act) pos = s_cursor[k] + rank;
+        if (act) pos = mine[k] + rank;
         __syncwarp();
-        if (act && rank == __popc(peers) - 1) s_cursor[k] = pos + 1;   // last peer advances the cursor
+        if (act && rank == __popc(peers) - 1) mine[k] = pos + 1;   // last peer advances the cursor
         if (act) grouped[pos] = r;
         __syncwarp();
     }
@@ -481,7 +504,10 @@ int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, con
     if (n_work == 0) return CC_OK;
     int32_t* gstart = nullptr;
     CC_CUDA(cudaMallocAsync(&gstart, sizeof(int32_t) * (size_t)n_work * (st->Kcap + 1), stream));
-    group_kernel<<<n_work, 32, sizeof(int) * st->Kcap, stream>>>(*st, n_work, d_chains, d_views, gstart);
+    // as many warps per (chain, view) as 48 KB of per-warp cluster counters allow (8 at Kcap <= 1536)
+    int gw = (48 * 1024) / ((int)sizeof(int) * st->Kcap);
+    gw = gw > 8 ? 8 : (gw < 1 ? 1 : gw);
+    group_kernel<<<n_work, 32 * gw, sizeof(int) * st->Kcap * gw, stream>>>(*st, n_work, d_chains, d_views, gstart);
     CC_CUDA(cudaGetLastError());
     StatsParams p;
     p.st = *st; p.n_work = n_work; p.chains = d_chains; p.views = d_views; p.gstart = gstart;
