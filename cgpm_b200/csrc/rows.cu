@@ -71,7 +71,7 @@ __device__ __forceinline__ NormalCache normal_cache_fast(double N, double sx, do
     NormalCache c;
     c.mn = mn;
     c.a = rn * __drcp_rn((rn + 1.0) * sn);
-    c.cst = gN - 0.5 * log(sn);
+    c.cst = gN - 0.5 * ((sn > 0.0) ? cc_log_pos(sn) : log(sn));
     return c;
 }
 
@@ -194,7 +194,7 @@ __device__ __forceinline__ double normal_core(const double* p, const double* po,
             }
         }
     }
-    const double t = bs + coef * log(fma(sc * zz, zz, 1.0));
+    const double t = bs + coef * cc_log_pos(fma(sc * zz, zz, 1.0));     // argument in [2^-20, inf): no special cases
     return isnan(x) ? 0.0 : t;                                   // dim.py:130-132
 }
 
