@@ -35,23 +35,10 @@
 #include <cstdlib>
 #include <vector>
 #include "cc_common.cuh"
+#include "rows_params.h"
 
 namespace {
 
-struct RowsParams {
-    cc_state st;
-    const cc_row_work* work;
-    const int32_t* perm;
-    const double* u;
-    double* trace;
-    int trace_stride;
-    uint64_t seed, counter;
-    int B;          // rows per staged batch (power of two, <= 32)
-    int bulk;       // 1: stage whole rows with cp.async.bulk
-    int smem_bytes; // dynamic shared memory given to the CTA
-    int wide;       // 1: very wide views -- per-column hypers / types stay in global memory, tables too
-    int prof;       // debug: per-CTA cycles / D / K / moves into st.seq[(chain, view)][0..3]
-};
 
 template <int NT>
 __device__ __forceinline__ void consumer_sync() {
@@ -1197,6 +1184,15 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
         } else if (nt == 64) {
             CC_CUDA(cudaFuncSetAttribute(rows_kernel<64, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             rows_kernel<64, 5><<<cnt, 96, budget, strm>>>(p);
+        } else if (nt == 256 && !getenv("CGPM_B200_ROWS_NO_PIPE") && !env_forced) {
+            // wide views: two rows in flight (rows_wide.cu); its fixed shared region is a little larger
+            const int fixed2 = cc_rows_wide_fixed_smem(st->Kcap, dmax, p.wide, xbytes);
+            if (!forced && p.smem_bytes < fixed2 + 4096) p.smem_bytes = fixed2 + 4096;
+            if (forced) p.smem_bytes += fixed2 - fixed;
+            if (p.smem_bytes > max_smem) p.smem_bytes = max_smem;
+            if (fixed2 > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed2, max_smem); return CC_ERR_ARG; }
+            const int rcw = cc_launch_rows_wide(p, cnt, strm);
+            if (rcw != CC_OK) return rcw;
         } else if (nt == 256) {
             CC_CUDA(cudaFuncSetAttribute(rows_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             rows_kernel<224, 2><<<cnt, 256, budget, strm>>>(p);
