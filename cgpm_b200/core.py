@@ -21,6 +21,7 @@ Two random-stream modes:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import sys
 import time
 from collections import OrderedDict
@@ -112,6 +113,8 @@ class Chains(object):
         self.diagnostics = [self._fresh_diag() for _ in range(S)]
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.counter = 1
+        self._aux_pre = None          # auxiliary views launched beside a rows sweep (see _prelaunch_aux)
+        self._aux_stream = None
         self._ci_dev = None
         self._mirror = None
         self.events = None          # bench instrumentation: list of (kernel name, start event, end event)
@@ -249,6 +252,11 @@ class Chains(object):
             'columns': lambda: self.transition_dims(chains, cols=cols),
         }
         funcs = [self._timed(k, table[k]) for k in kernels]
+        if self.stream == 'philox' and not os.environ.get('CGPM_B200_NO_AUX_OVERLAP'):
+            # rows immediately followed by columns: generate the column sweep's auxiliary views beside the rows sweep
+            for j, k in enumerate(kernels):
+                if k == 'rows' and kernels[(j + 1) % len(kernels)] == 'columns' and len(kernels) > 1:
+                    funcs[j] = self._rows_then_aux(funcs[j], chains, cols)
         if N is None and S is None:
             N = 1
         if progress is None:
@@ -483,6 +491,58 @@ class Chains(object):
         dev.st.aux_zr_all = dev.aux_zr_all.data_ptr()
         return True
 
+    def _rows_then_aux(self, rows_func, chains, cols):
+        def run():
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev.device))
+            rows_func()
+            self._prelaunch_aux(chains, cols, ev)
+        return run
+
+    def _column_order(self, chains, cidx, counter):
+        """Column visiting order of every chain: rng.permutation(cols) (state.py:807)."""
+        perm = np.zeros((len(chains), len(cidx)), np.int32)
+        for i, s in enumerate(chains):
+            if self.stream == 'numpy':
+                perm[i] = np.asarray(self.rngs[s].permutation(cidx), dtype=np.int32)
+            else:
+                perm[i] = np.asarray(np.random.RandomState((self.seed * 31 + counter * 1009 + s) % (2 ** 32))
+                                     .permutation(cidx), dtype=np.int32)
+        return perm
+
+    def _launch_aux(self, ch_h, perm, counter, stored, stream_ptr):
+        """cc_col_aux for every (chain, column) of a device-stream column sweep."""
+        a_ch = np.repeat(ch_h, perm.shape[1]).astype(np.int32)
+        a_co = perm.reshape(-1).astype(np.int32)
+        # the cost of a pair grows with its alpha (number of tables): hand out the expensive ones first
+        cost = np.argsort(-aux_alpha_index(self.seed, counter, a_ch, a_co), kind='stable')
+        a_ch = np.ascontiguousarray(a_ch[cost]); a_co = np.ascontiguousarray(a_co[cost])
+        L.check(self.dev.lib.cc_col_aux(C.byref(self.dev.st), len(a_ch), _p(a_ch), _p(a_co), None, None, 2 if stored else 0,
+                                        C.c_uint64(self.seed), C.c_uint64(counter), stream_ptr), 'cc_col_aux')
+
+    def _prelaunch_aux(self, chains, cols, ev_before_rows):
+        """The auxiliary views of the NEXT column sweep depend on the data, the hyperparameters and their own
+        random stream only -- not on the row partitions -- so on the device stream they are generated on a side
+        stream while the rows kernels (latency-bound, most of the GPU idle) are still running.  transition_dims
+        picks the result up if it is called next with the same chains and columns."""
+        dev = self.dev
+        cidx = [self.col_index[c] for c in cols] if cols is not None else list(range(self.C))
+        if not cidx or not chains:
+            return
+        counter = self.counter + 1                  # the counter transition_dims will draw
+        self._ensure_arena(len(chains) * len(cidx))
+        stored = self._ensure_aux_store()
+        perm = self._column_order(chains, cidx, counter)
+        if self._aux_stream is None:
+            self._aux_stream = torch.cuda.Stream(device=dev.device)
+        side = self._aux_stream
+        side.wait_event(ev_before_rows)
+        with torch.cuda.stream(side):
+            self._launch_aux(np.ascontiguousarray(chains, dtype=np.int32), perm, counter, stored, dev.stream_ptr())
+            done = torch.cuda.Event()
+            done.record(side)
+        self._aux_pre = {'counter': counter, 'key': (tuple(chains), tuple(cidx)), 'perm': perm, 'done': done}
+
     def transition_dims(self, chains, cols=None, trace=None):
         """State.transition_dims (state.py:804-810) for the selected chains."""
         dev, lib, st = self.dev, self.dev.lib, C.byref(self.dev.st)
@@ -496,13 +556,15 @@ class Chains(object):
         seed = C.c_uint64(self.seed)
         ci_off, ci_adj = (self._ci_dev if self._ci_dev else (None, None))
         # column visiting order: rng.permutation(cols) (state.py:807)
-        perm = np.zeros((nch, ncols), np.int32)
-        for i, s in enumerate(chains):
-            if self.stream == 'numpy':
-                perm[i] = np.asarray(self.rngs[s].permutation(cidx), dtype=np.int32)
-            else:
-                perm[i] = np.asarray(np.random.RandomState((self.seed * 31 + counter * 1009 + s) % (2 ** 32))
-                                     .permutation(cidx), dtype=np.int32)
+        pre = self._aux_pre
+        self._aux_pre = None
+        if pre is not None and (pre['counter'] != counter or pre['key'] != (tuple(chains), tuple(cidx))):
+            pre['done'].synchronize()          # a prelaunched auxiliary pass nobody will use: let it finish
+            pre = None
+        if pre is not None:
+            perm = pre['perm']
+        else:
+            perm = self._column_order(chains, cidx, counter)
         ch_h = np.ascontiguousarray(chains, dtype=np.int32)
         ch_d = torch.from_numpy(ch_h).to(dev.device)
         ts = trace['stride'] if trace is not None else 0
@@ -515,13 +577,10 @@ class Chains(object):
             pos_d = torch.zeros(nch, dtype=torch.int32, device=dev.device)
             pend_d = torch.full((nch,), -1, dtype=torch.int32, device=dev.device)
             # auxiliary views of every (chain, column) and marginals under every live view
-            a_ch = np.repeat(ch_h, ncols).astype(np.int32)
-            a_co = perm.reshape(-1).astype(np.int32)
-            # the cost of a pair grows with its alpha (number of tables): hand out the expensive ones first
-            cost = np.argsort(-aux_alpha_index(self.seed, counter, a_ch, a_co), kind='stable')
-            a_ch = np.ascontiguousarray(a_ch[cost]); a_co = np.ascontiguousarray(a_co[cost])
-            L.check(lib.cc_col_aux(st, len(a_ch), _p(a_ch), _p(a_co), None, None, 2 if stored else 0, seed,
-                                   C.c_uint64(counter), sp()), 'cc_col_aux')
+            if pre is not None:
+                torch.cuda.current_stream(dev.device).wait_event(pre['done'])     # launched beside the rows sweep
+            else:
+                self._launch_aux(ch_h, perm, counter, stored, sp())
             m = self.mirror()
             w_ch = np.ascontiguousarray([s for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)
             w_vw = np.ascontiguousarray([v for s in chains for v in np.nonzero(m['nv'][s] > 0)[0]], dtype=np.int32)

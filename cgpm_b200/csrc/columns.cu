@@ -635,6 +635,7 @@ extern "C" int cc_col_aux(const cc_state* st, int n, const int32_t* chains, cons
     const int wpb = 4;
     int blocks = (nworkers + wpb - 1) / wpb;
     if (blocks > nsm * 8) blocks = nsm * 8;
+    if (const char* e = getenv("CGPM_B200_AUX_BLOCKS")) { const int v = atoi(e); if (v > 0 && v < blocks) blocks = v; }
     if (blocks * wpb > nworkers) blocks = nworkers / wpb > 0 ? nworkers / wpb : 1;
     int tpb = (blocks == 1 && nworkers < wpb) ? nworkers * 32 : wpb * 32;
     AuxParams p;
