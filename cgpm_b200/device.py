@@ -47,6 +47,7 @@ def crp_grid(n, n_grid=L.NGRID):
 
 
 # CUDA kernels launched per C-ABI call (for the bench's gpu_launches count)
+# kernels per C-ABI call (a lower bound: cc_transition_rows launches one kernel per view class present, up to three)
 KERNELS_PER_CALL = {'cc_rebuild': 2, 'cc_refresh_tables': 1, 'cc_logpdf_score': 1, 'cc_transition_rows': 1, 'cc_col_aux': 1,
                     'cc_col_marginals': 2, 'cc_col_scan': 1, 'cc_col_install': 1,
                     'cc_transition_col_hypers': 1, 'cc_transition_alphas': 1, 'cc_logpdf_bulk': 1,
