@@ -177,10 +177,10 @@ __device__ __forceinline__ double categorical_term(const Ctx& c, const Tab<GT>& 
     if (isnan(x)) return 0.0;
     const double a = hyper(c, wide, ghyp, 0, j);
     const int xi = (int)x, kc = wide ? c.st.ncat[c.col[j]] : c.ncat[j];
-    if (empty) return log(a) - log(a * kc);
+    if (empty) return cc_log_pos(a) - cc_log_pos(a * kc);
     const double cntx = T.counts(k, j)[xi];
-    if (!own) return log(a + cntx) - T.at(CC_F_CST, k, j);
-    return log(a + (cntx - 1.0)) - log((T.at(CC_F_N, k, j) - 1.0) + a * kc);
+    if (!own) return cc_log_pos(a + cntx) - T.at(CC_F_CST, k, j);      // arguments are positive: branch-free log
+    return cc_log_pos(a + (cntx - 1.0)) - cc_log_pos((T.at(CC_F_N, k, j) - 1.0) + a * kc);
 }
 
 // One pass over rows [i_begin, n).  Returns n when finished, or the index of the row whose
