@@ -389,7 +389,13 @@ __device__ __forceinline__ int sweep(const Ctx& c, int i_begin, bool resume) {
         if (tid >= 32) eval_row(i_begin);
         consumer_sync<NT>();
     }
+    // Speculation pays while rows rarely move: every move (or drift) costs a second scoring of the next row.
+    // Each thread keeps the same exponential average of the re-done fraction (all see the same outcomes) and
+    // the CTA falls back to score-after-draw, the plain sequential order, while more than ~1/4 of the recent
+    // rows were re-done (the first sweeps after a random initialisation).
+    int redo_avg = 0;                              // 65536 * fraction, time constant 16 rows
     for (int i = i_begin; i < n; ++i) {
+        const bool speculate = redo_avg < 16384;
         const int b = i >> lgB, slot = i & (B - 1), buf = b & 1;
         if (slot == 0 || i == i_begin) mbar_wait(&c.bar_full[buf], (b >> 1) & 1);
         const int r = c.rowidx[buf * 32 + slot];
@@ -402,7 +408,7 @@ __device__ __forceinline__ int sweep(const Ctx& c, int i_begin, bool resume) {
         // ---- stage i: draw row i  ||  score row i+1 (speculatively) ------------------------
         if (!(resume && i == i_begin)) {
             if (tid < 32) draw_row(i, r, z, K, K + (singleton ? 0 : 1), buf, slot);
-            else if (i + 1 < n) eval_row(i + 1);
+            else if (speculate && i + 1 < n) eval_row(i + 1);
             consumer_sync<NT>();
         }
         const int* pub = c.scal + 16 + (i & 1) * 8;
@@ -518,12 +524,11 @@ __device__ __forceinline__ int sweep(const Ctx& c, int i_begin, bool resume) {
             }
             redo = true;
         }
-        if (redo) {
+        redo_avg += (redo ? 4096 : 0) - (redo_avg >> 4);
+        if (redo) consumer_sync<NT>();
+        if ((redo || !speculate) && i + 1 < n) {
+            if (tid >= 32) eval_row(i + 1);              // not scored yet, or the speculative scores are stale
             consumer_sync<NT>();
-            if (i + 1 < n) {
-                if (tid >= 32) eval_row(i + 1);          // the speculative scores of row i+1 are stale
-                consumer_sync<NT>();
-            }
         }
         if ((slot == B - 1 || i == n - 1) && tid == 0) mbar_arrive(&c.bar_empty[buf]);
     }
