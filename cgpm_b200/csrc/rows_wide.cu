@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_pipe_kernel(const RowsPara
         if (p.prof) {
             int32_t* q = st.seq + sv * R;
             q[0] = (int)((clock64() - t_start) >> 10); q[1] = D; q[2] = K; q[3] = c.scal[3];
-            q[4] = start_global ? 1 : (in_global ? 2 : 0);      // table mode: shared / global / migrated mid-sweep
+            q[4] = 4 + (start_global ? 1 : (in_global ? 2 : 0));      // two-rows-in-flight kernel; table mode: shared / global / migrated mid-sweep
         }
     }
     // ---- member order of the view's CRP: re-seated rows move to the end, in the

@@ -23,13 +23,15 @@ def pair(X, cct, da, seed, S=2, **kw):
 def test_global_table_mode_and_mid_sweep_migration(monkeypatch):
     """The per-(cluster, column) tables live in shared memory when they fit.  With the
     shared tables capped (env override used only here), (1) a 60-column view with 30
-    clusters starts in global-table mode, (2) a 4-column view that grows from 2 to many
-    clusters migrates from shared to global memory mid-sweep.  Both must follow the oracle
-    exactly (partitions, bit-identical statistics)."""
+    clusters starts in global-table mode (two-rows-in-flight kernel, mode 5), (2) a 4-column
+    view that grows from 2 to many clusters migrates from shared to global memory mid-sweep
+    (sequential kernel, mode 2), (3) so does a 20-column view (two-rows-in-flight kernel,
+    mode 6).  All must follow the oracle exactly (partitions, bit-identical statistics)."""
     from cgpm_b200 import synth
     monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
     modes = set()
-    cases = (('global', 60, 64, np.arange(90) % 30, 5.0), ('migrate', 4, 1, np.arange(90) % 2, 150.0))
+    cases = (('global', 60, 64, np.arange(90) % 30, 5.0), ('migrate', 4, 1, np.arange(90) % 2, 150.0),
+             ('migrate_wide', 20, 5, np.arange(90) % 2, 1e40))
     for name, C, kb, Zr, alpha in cases:
         monkeypatch.setenv('CGPM_B200_ROWS_SMEM_KB', str(kb))
         cct = ['normal'] * C
@@ -44,7 +46,7 @@ def test_global_table_mode_and_mid_sweep_migration(monkeypatch):
             compare(eng, oracles, (name, it))
             seq = eng._ch.dev.t['seq'].cpu().numpy()
             modes |= set(int(seq[s, 0, 4]) for s in range(2))
-    assert {1, 2} <= modes, modes          # both the global start and the mid-sweep migration ran
+    assert {5, 2, 6} <= modes, modes       # the global start and both mid-sweep migrations ran
 
 
 def test_row_and_column_subsets_and_views_argument():

@@ -182,3 +182,77 @@ def test_rows_trajectory_narrow_views(n_rows, seed, n_init, narrow, monkeypatch)
         modes = dev.t['seq'].cpu().numpy()[:, :3, 4]
         assert np.all(modes == (3 if narrow else 0)), modes        # which kernel swept the views
         check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, (sweep, narrow))
+
+
+@pytest.mark.parametrize('n_rows,seed,mixed,pipe', [(150, 11, False, True), (120, 12, True, True), (150, 11, False, False)])
+def test_rows_trajectory_wide_view(n_rows, seed, mixed, pipe, monkeypatch):
+    """A view of 20 columns (with the width hint) is swept by the two-rows-in-flight kernel of
+    rows_wide.cu (pipe=True; CGPM_B200_ROWS_NO_PIPE selects the sequential sweep): both must
+    follow the oracle step by step -- partitions, member order, bit-identical statistics and
+    per-step conditionals -- including rows that move and make the next row's speculative
+    scores stale."""
+    from cgpm_b200.device import DeviceChains
+    from cgpm_b200 import codec
+    from cgpm_b200.synth import gen_table
+    if not pipe:
+        monkeypatch.setenv('CGPM_B200_ROWS_NO_PIPE', '1')
+    monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
+    widths = (20, 3)
+    ncol = sum(widths)
+    cct = ['normal'] * ncol
+    da = [None] * ncol
+    if mixed:
+        for c in (2, 7, 13, 21):
+            cct[c] = 'categorical'; da[c] = {'k': 3 + (c % 3)}
+    X, _, _ = gen_table(n_rows, cct, da, n_views=2, clusters_per_view=3, seed=seed)
+    rng0 = np.random.RandomState(seed)
+    for _ in range(n_rows // 5):
+        X[rng0.randint(n_rows), rng0.randint(ncol)] = np.nan
+    ctype, ncat = ctype_arrays(cct, da)
+    S = 2
+    dev = DeviceChains(X, ctype, ncat, S, Kcap=64)
+    Zv = {}
+    for v, wd in enumerate(widths):
+        for _ in range(wd):
+            Zv[len(Zv)] = v
+    oracles = []
+    for s in range(S):
+        Zrv = {}
+        for v in range(len(widths)):
+            _, inv = np.unique(rng0.randint(5, size=n_rows), return_inverse=True)
+            Zrv[v] = [int(z) for z in inv]
+        o = co.OState(X, cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, rng=np.random.RandomState(seed * 100 + s))
+        dev.upload_chain(s, codec.pack_chain(oracle_spec(o), n_rows, ncol))
+        oracles.append(o)
+    dev.rebuild()
+    dev.sync()
+    rngs = [np.random.RandomState(27 + s) for s in range(S)]
+    for s, o in enumerate(oracles):
+        o.rng.set_state(rngs[s].get_state())
+        for view in o.views.values():
+            view.rng = o.rng
+    views_order = [list(range(len(o.views))) for o in oracles]
+    for sweep in range(3):
+        otr = [dict() for _ in oracles]
+        for s, o in enumerate(oracles):
+            o.transition_view_rows(trace=otr[s])
+        R = dev.R
+        TS = 3 + dev.Kcap
+        work, perms, us, off = [], [], [], 0
+        for s, o in enumerate(oracles):
+            for v in views_order[s]:
+                perms.append(rngs[s].permutation(R).astype(np.int32))
+                us.append(rngs[s].random_sample(R))
+                nc = len(list(o.views.values())[v].dims)
+                work.append(dict(chain=s, view=v, n=R, perm_is_index=1, perm_off=off, u_off=off,
+                                 trace_off=len(work) * R * TS, n_cols=nc, n_normal=0))
+                off += R
+        perm = torch.from_numpy(np.concatenate(perms)).to(dev.device)
+        u = torch.from_numpy(np.concatenate(us)).to(dev.device)
+        tr = torch.zeros(len(work) * R * TS, dtype=torch.float64, device=dev.device)
+        dev.transition_rows(work, perm=perm, u=u, trace=tr, trace_stride=TS)
+        dev.sync()
+        dev.check_errors()
+        trh = tr.cpu().numpy().reshape(len(work), R, TS)
+        assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == (4 if pipe else 0))      # which kernel swept the wide view
+        check_against_oracle(dev, oracles, ctype, n_rows, otr, trh, rngs, (sweep, mixed, pipe))
