@@ -207,7 +207,22 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
         uint32_t lc[CC_MAXCAT];
         if (act && ctype == CC_CATEGORICAL) for (int q = 0; q < kc; ++q) lc[q] = 0;
         int i = beg;
-        // ordered accumulation: loads are batched 8 deep (independent), the adds stay sequential
+        // ordered accumulation: loads are batched 16 (then 8) deep (independent), the adds stay sequential
+        if (ctype == CC_NORMAL) {
+            for (; i + 16 <= end; i += 16) {
+                int rr[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) rr[q] = grouped[i + q];
+                if (act) {
+                    double xv[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) xv[q] = X[(size_t)rr[q] * Cp];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (!isnan(xv[q])) { N += 1.0; sx = __dadd_rn(sx, xv[q]); sxx = __dadd_rn(sxx, __dmul_rn(xv[q], xv[q])); }
+                }
+            }
+        }
         for (; i + 8 <= end; i += 8) {
             int rr[8];
 #pragma unroll
