@@ -42,8 +42,7 @@ namespace {
 
 template <int NT>
 __device__ __forceinline__ void consumer_sync() {
-    if (NT == 32) __syncwarp();                       // single consumer warp: no block barrier at all
-    else asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
 
 // cached predictive constants for the rows kernel: same formulas as normal_cache, with the two
@@ -376,12 +375,10 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
         if (zb != z) {
             if (!GT && newc && zb >= c.Kc - 1) return i;     // needs the global-memory tables
             // the lower half of the CTA updates the old cluster, the upper half the new one (different
-            // warps whenever NT > 32, so the two divergent update paths run side by side)
-            const int half = (NT > 32) ? NT / 2 : NT;
-            const bool is_old_half = (NT > 32) ? (tid < half) : true;
-            for (int t = (NT > 32) ? (tid % half) : tid; t < ((NT > 32) ? D : 2 * D); t += half) {
-                const int j = (NT > 32) ? t : ((t < D) ? t : t - D);
-                const bool is_old = (NT > 32) ? is_old_half : (t < D);
+            // warps, so the two divergent update paths run side by side)
+            const int half = NT / 2;
+            const bool is_old = tid < half;
+            for (int j = tid % half; j < D; j += half) {
                 if (is_old && singleton) continue;            // the emptied cluster is dropped
                 const double x = xrow[c.bulk ? c.col[j] : j];
                 const int k = is_old ? z : zb;
@@ -1140,7 +1137,7 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     const int reserve = ((n_narrow + nsm - 1) / nsm) * (narrow_need + 1024);
     const int n_general = n_wide + n_med;
     int env_nt = 0;
-    if (const char* e = getenv("CGPM_B200_ROWS_NT")) { const int v = atoi(e); env_nt = (v == 32 || v == 64 || v == 256) ? v : 128; }
+    if (const char* e = getenv("CGPM_B200_ROWS_NT")) { const int v = atoi(e); env_nt = (v == 256) ? v : 128; }
 
     auto launch = [&](const cc_row_work* hw, const cc_row_work* dw, int cnt, int nt, int total_ctas, cudaStream_t strm) -> int {
         RowsParams p;
@@ -1163,7 +1160,7 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
         p.B = 32;
         while (p.B > 1 && 2 * p.B * stagebytes > 32 * 1024) p.B >>= 1;
         // CTAs per SM wanted: enough to co-schedule all work items of both launches
-        const int maxb = (nt == 32) ? 8 : (nt == 64) ? 5 : (nt == 256) ? 2 : 3;
+        const int maxb = (nt == 256) ? 2 : 3;
         int per_sm = (total_ctas + nsm - 1) / nsm;
         if (per_sm < 1) per_sm = 1;
         if (per_sm > maxb) per_sm = maxb;
@@ -1178,13 +1175,7 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
         if (budget > max_smem) budget = max_smem;
         if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }
         p.smem_bytes = budget;
-        if (nt == 32) {
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<32, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            rows_kernel<32, 8><<<cnt, 64, budget, strm>>>(p);
-        } else if (nt == 64) {
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<64, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            rows_kernel<64, 5><<<cnt, 96, budget, strm>>>(p);
-        } else if (nt == 256 && !getenv("CGPM_B200_ROWS_NO_PIPE") && !env_forced) {
+        if (nt == 256 && !getenv("CGPM_B200_ROWS_NO_PIPE") && !env_forced) {
             // wide views: two rows in flight (rows_wide.cu); its fixed shared region is a little larger
             const int fixed2 = cc_rows_wide_fixed_smem(st->Kcap, dmax, p.wide, xbytes);
             if (!forced && p.smem_bytes < fixed2 + 4096) p.smem_bytes = fixed2 + 4096;
