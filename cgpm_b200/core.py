@@ -283,6 +283,7 @@ class Chains(object):
             if checkpoint and iters % checkpoint == 0:
                 self._increment_diagnostics(chains)
         self.dev.sync()
+        self._aux_pre = None           # auxiliary views generated ahead are only valid within this call
         self.dev.check_errors()
         if progress:
             print('\rCompleted: %d iterations in %f seconds.' % (iters, time.time() - start))
