@@ -255,7 +255,7 @@ class Chains(object):
         if self.stream == 'philox' and not os.environ.get('CGPM_B200_NO_AUX_OVERLAP'):
             # rows immediately followed by columns: generate the column sweep's auxiliary views beside the rows sweep
             for j, k in enumerate(kernels):
-                if k == 'rows' and kernels[(j + 1) % len(kernels)] == 'columns' and len(kernels) > 1:
+                if k == 'rows' and j + 1 < len(kernels) and kernels[j + 1] == 'columns':
                     funcs[j] = self._rows_then_aux(funcs[j], chains, cols)
         if N is None and S is None:
             N = 1
