@@ -287,7 +287,7 @@ def ours_main(args):
                     'what': 'host table + dense chain state -> device, table rebuild, transition(N=1), state + scores -> host'},
             'gpu_launches': int(launches),
             'clocks': clocks,
-            'roofline': {'bound': 'hbm', 'kernel': 'rows phase: rows_pipe_kernel<224> + rows_kernel<128> + rows_narrow_kernel (concurrent)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': 'rows phase: rows_kernel<224, PIPE> + rows_kernel<128> + rows_narrow_kernel (concurrent)', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': (3.75e9 if (R, Cn, S) == (100000, 50, 64) else None), 'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback',
                          'ms_per_launch': rows_avg, 'alg_bytes_per_launch': alg_bytes,
                          'traffic_source': 'profiles/r01_rows_pipe_kernel_v7_raw.csv + r01_rows_kernel_v7_raw.csv + r01_rows_narrow_kernel_v7_raw.csv: dram__bytes_read.sum + dram__bytes_write.sum of the three concurrent launches of one rows phase at this workload',

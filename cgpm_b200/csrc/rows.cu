@@ -35,183 +35,17 @@
 #include <cstdlib>
 #include <vector>
 #include "cc_common.cuh"
-#include "rows_params.h"
+#include "rows_common.cuh"
+#include "rows_sweep_pipe.cuh"
 
 namespace {
 
-
-template <int NT>
-__device__ __forceinline__ void consumer_sync() {
-    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
-}
-
-// cached predictive constants for the rows kernel: same formulas as normal_cache, with the two
-// divisions replaced by reciprocals (the values feed log-densities only, never the statistics)
-__device__ __forceinline__ NormalCache normal_cache_fast(double N, double sx, double sxx, double gN, double m,
-                                                         double r, double s, double nu) {
-    const double rn = r + N;
-    const double irn = __drcp_rn(rn);
-    const double mn = (r * m + sx) * irn;
-    double sn = __dsub_rn(__dadd_rn(__dadd_rn(s, sxx), __dmul_rn(__dmul_rn(r, m), m)), __dmul_rn(__dmul_rn(rn, mn), mn));
-    if (sn == 0.0) sn = s;
-    NormalCache c;
-    c.mn = mn;
-    c.a = rn * __drcp_rn((rn + 1.0) * sn);
-    c.cst = gN - 0.5 * ((sn > 0.0) ? cc_log_pos(sn) : log(sn));
-    return c;
-}
-
-// bijection on [0, 2^bits) from add / odd-multiply / xorshift rounds, walked
-// until the value falls below n: a keyed pseudo-random permutation of [0, n).
-__device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t bits, uint4 key) {
-    const uint32_t mask = (bits >= 32) ? 0xFFFFFFFFu : ((1u << bits) - 1u);
-    const uint32_t sh = (bits + 1) >> 1;
-    uint32_t x = i;
-    do {
-        x = (x + key.x) & mask; x = (x * 0x9E3779B1u) & mask; x ^= x >> sh;
-        x = (x + key.y) & mask; x = (x * 0x85EBCA6Bu) & mask; x ^= x >> sh;
-        x = (x + key.z) & mask; x = (x * 0xC2B2AE35u) & mask; x ^= x >> sh;
-        x = (x + key.w) & mask; x = (x * 0x27D4EB2Fu) & mask; x ^= x >> sh;
-    } while (x >= n);
-    return x;
-}
-
-// Everything a sweep needs, resolved once per CTA.
-struct Ctx {
-    cc_state st;
-    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride, wide, allnorm;
-    size_t sv;
-    // shared memory
-    uint64_t *bar_full, *bar_empty;
-    int *scal;              // 0 K, 2 free head, 3 nmoved, 4 own position, 5 start in global, 6 CTv, 7 error, 8 choice, 9 destination slot, 10 new-cluster flag, 11 all-normal view
-    int *live, *nk;
-    double* lp;
-    double* w;              // [Kcap+1] CRP weight of each candidate (written with lp)
-    int *col, *cto, *ctype, *ncat;
-    double* hyp;            // [4][D]
-    int *rowidx, *zrow;
-    double *u, *x, *tab;
-    // global
-    int32_t *zr, *moved, *g_cid;
-    uint8_t* movedflag;
-    double alpha;
-    double* trace;
-    int trace_stride;
-    long long trace_off;
-};
-
-// table access, specialised on the address space (GT = tables in global memory)
-template <bool GT>
-struct Tab {
-    const Ctx& c;
-    double* f0;        // field 0 of (cluster 0, column 0)
-    size_t fs;         // distance between two fields of one (cluster, column) cell
-    double* gcnt;
-    __device__ __forceinline__ Tab(const Ctx& cx) : c(cx) {
-        if (GT) {
-            f0 = stat_field(cx.st, cx.s, 0);
-            fs = (size_t)cx.st.Kcap * cx.st.C;
-            gcnt = cx.st.cnt + (size_t)cx.s * cx.st.Kcap * cx.st.CT;
-        } else {
-            f0 = cx.tab;
-            fs = (size_t)cx.Kc * cx.D;
-            gcnt = nullptr;
-        }
-    }
-    // field f of the cell is cell(k, j)[f * fs]
-    __device__ __forceinline__ double* cell(int k, int j) const {
-        if (GT) return f0 + (size_t)k * c.st.C + c.col[j];
-        return f0 + k * c.D + j;
-    }
-    __device__ __forceinline__ double& at(int f, int k, int j) const { return cell(k, j)[f * fs]; }
-    __device__ __forceinline__ double* counts(int k, int j) const {
-        if (GT) return gcnt + (size_t)k * c.st.CT + c.st.catoff[c.col[j]];
-        return c.tab + CC_NFIELD * c.Kc * c.D + k * c.CTv + c.cto[j];
-    }
-    __device__ __forceinline__ int prior() const { return GT ? (c.st.Kcap - 1) : (c.Kc - 1); }
-};
-
-__device__ __forceinline__ double hyper(const Ctx& c, bool wide, const double* ghyp, int f, int j) {
-    return wide ? __ldg(&ghyp[c.col[j] * 4 + f]) : c.hyp[f * c.D + j];
-}
-
-// Normal cell of one row against one candidate cluster.
-//   other cluster: cst - b log(1 + a (x-mn)^2)   (Student-t form, cached a, mn, cst)
-//   own cluster  : the row is removed first (view.py:416-419).  With sn1 = sn - rn/(rn-1) (x-mn)^2 (the
-//     Normal-Gamma downdate; rn, mn, sn, a = rn/((rn+1) sn) of the cluster WITH the row) the predictive
-//     G(N-1) - b1 log sn + (b1-1/2) log sn1 becomes cst + G(N-1) - G(N) + (b1-1/2) log(1 - a (rn+1)/(rn-1)
-//     (x-mn)^2): the same loads and the same single log as for any other cluster.  Heavy cancellation
-//     (arg < 2^-20) takes the reference's posterior update of the decremented sums instead.  A singleton's
-//     own cluster without the row IS the empty cluster (the caller passes that cell as p).  The `-= x; += x`
-//     replay (view.py:416-419) is reported in `drift`: set if the sums come back changed.
-// p: the candidate's cell (field f at p[f * fs]); po: the cell of the row's own cluster (k), read only if `own`.
-// ms(m, s): loads the two hyperparameters only the rare exact branch needs.
-template <typename FS, typename MS>
-__device__ __forceinline__ double normal_core(const double* p, const double* po, FS fs, double x, double nu, double rr,
-                                              bool own, bool dn, int& drift, MS ms) {
-    const double Nf = p[CC_F_N * fs];
-    const double zz = x - p[CC_F_MN * fs];
-    double sc = p[CC_F_A * fs];
-    double bs = p[CC_F_CST * fs];
-    double coef = -0.5 * (nu + Nf + 1.0);
-    if (own) {
-        const double sx0 = po[CC_F_SX * fs], sxx0 = po[CC_F_SXX * fs];
-        const double xx = __dmul_rn(x, x);
-        const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
-        if (!isnan(x) && (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, xx) != sxx0)) drift = 1;
-        if (dn) {
-            const double rn = rr + Nf;
-            sc = -sc * ((rn + 1.0) * __drcp_rn(rn - 1.0));
-            coef = 0.5 * (nu + Nf - 1.0);
-            bs += p[CC_F_GM1 * fs] - p[CC_F_GN * fs];
-            if (!(fma(sc * zz, zz, 1.0) >= 0x1p-20)) {
-                double m, ss;
-                ms(m, ss);
-                const double N1 = Nf - 1.0;
-                const double rn1 = rr + N1;
-                const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
-                double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
-                                       __dmul_rn(__dmul_rn(rn1, mn1), mn1));
-                if (sn1 == 0.0) sn1 = ss;
-                const double b1 = 0.5 * (nu + N1 + 1.0);
-                bs = p[CC_F_GM1 * fs] - b1 * (2.0 * (p[CC_F_GN * fs] - p[CC_F_CST * fs]));
-                const double t = bs + coef * log(sn1);
-                return isnan(x) ? 0.0 : t;
-            }
-        }
-    }
-    const double t = bs + coef * cc_log_pos(fma(sc * zz, zz, 1.0));     // argument in [2^-20, inf): no special cases
-    return isnan(x) ? 0.0 : t;                                   // dim.py:130-132
-}
-
-
-template <bool GT>
-__device__ __forceinline__ double normal_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp,
-                                              const double* xrow, int j, int k, int ke, bool own, bool dn, int& drift) {
-    const double x = xrow[c.bulk ? c.col[j] : j];
-    return normal_core(T.cell(ke, j), T.cell(k, j), T.fs, x, hyper(c, wide, ghyp, 3, j), hyper(c, wide, ghyp, 1, j),
-                       own, dn, drift, [&](double& m, double& ss) { m = hyper(c, wide, ghyp, 0, j); ss = hyper(c, wide, ghyp, 2, j); });
-}
-
-// Categorical cell: log((a + count_x) / (N + a k)), counts without the row for its own cluster.
-template <bool GT>
-__device__ __forceinline__ double categorical_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp,
-                                                   const double* xrow, int j, int k, bool own, bool empty) {
-    const double x = xrow[c.bulk ? c.col[j] : j];
-    if (isnan(x)) return 0.0;
-    const double a = hyper(c, wide, ghyp, 0, j);
-    const int xi = (int)x, kc = wide ? c.st.ncat[c.col[j]] : c.ncat[j];
-    if (empty) return cc_log_pos(a) - cc_log_pos(a * kc);
-    const double cntx = T.counts(k, j)[xi];
-    if (!own) return cc_log_pos(a + cntx) - T.at(CC_F_CST, k, j);      // arguments are positive: branch-free log
-    return cc_log_pos(a + (cntx - 1.0)) - cc_log_pos((T.at(CC_F_N, k, j) - 1.0) + a * kc);
-}
 
 // One pass over rows [i_begin, n).  Returns n when finished, or the index of the row whose
 // move needs a cluster slot that does not fit in shared memory (GT = false only): the caller
 // migrates the tables to global memory and continues there with the same row.
 template <int NT, bool GT>
-__device__ int sweep(const Ctx& c, int i_begin, bool resume) {
+__device__ int sweep_seq(const Ctx& c, int i_begin, bool resume) {
     const Tab<GT> T(c);
     const int tid = threadIdx.x, lane = tid & 31;
     const int D = c.D, B = c.B, n = c.n, Kcap = c.st.Kcap;
@@ -464,7 +298,8 @@ __device__ int sweep(const Ctx& c, int i_begin, bool resume) {
     return n;
 }
 
-template <int NT, int MINB>
+// PIPE: two rows in flight (rows_sweep_pipe.cuh) instead of the sequential sweep
+template <int NT, int MINB, bool PIPE>
 __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p) {
     const cc_state& st = p.st;
     const cc_row_work wk = p.work[blockIdx.x];
@@ -482,10 +317,10 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     // ---- fixed shared region ----------------------------------------------------
     c.bar_full = reinterpret_cast<uint64_t*>(smem_raw);               // [2]
     c.bar_empty = c.bar_full + 2;                                     // [2]
-    c.scal = reinterpret_cast<int*>(c.bar_empty + 2);                 // [16]
-    c.live = c.scal + 16;                                             // [Kcap]
+    c.scal = reinterpret_cast<int*>(c.bar_empty + 2);                 // [32]
+    c.live = c.scal + 32;                                             // [Kcap]
     c.nk = c.live + Kcap;                                             // [Kcap]
-    c.lp = reinterpret_cast<double*>(c.nk + Kcap);                    // [Kcap+1]
+    c.lp = reinterpret_cast<double*>(c.nk + Kcap);                    // [Kcap+1], twice with two rows in flight
     const int32_t* zv = st.zv + (size_t)s * C;
     __shared__ int s_D_tmp;
     if (tid == 0) {
@@ -500,8 +335,8 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     const int D = s_D_tmp;
     c.D = D;
     c.wide = p.wide;
-    c.w = c.lp + (Kcap + 1);                                          // [Kcap+1]
-    c.hyp = c.w + (Kcap + 1);                                         // [4][D] (not in wide mode)
+    c.w = c.lp + (PIPE ? 2 : 1) * (Kcap + 1);                         // same shape
+    c.hyp = c.w + (PIPE ? 2 : 1) * (Kcap + 1);                                         // [4][D] (not in wide mode)
     c.u = c.hyp + (p.wide ? 0 : 4 * D);                               // [2][32]
     c.col = reinterpret_cast<int*>(c.u + 64);                         // [D]
     c.cto = c.col + D;                                                // [D]   (these three not in wide mode)
@@ -645,7 +480,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     // ============================== consumers ===============================
     int done = 0;
     if (!start_global) {
-        done = sweep<NT, false>(c, 0, false);
+        done = PIPE ? sweep_pipe<NT, false>(c, 0, false) : sweep_seq<NT, false>(c, 0, false);
         if (done < n) {
             // migrate the shared tables to global memory (L2) and continue there with the same row
             const int K = c.scal[0];
@@ -666,7 +501,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         }
     }
     const bool in_global = start_global || done < n;
-    if (in_global) sweep<NT, true>(c, done, !start_global);
+    if (in_global) { if (PIPE) sweep_pipe<NT, true>(c, done, !start_global); else sweep_seq<NT, true>(c, done, !start_global); }
 
     // ---- write back ---------------------------------------------------------------
     consumer_sync<NT>();
@@ -695,7 +530,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         if (p.prof) {
             int32_t* q = st.seq + sv * R;
             q[0] = (int)((clock64() - t_start) >> 10); q[1] = D; q[2] = K; q[3] = c.scal[3];
-            q[4] = start_global ? 1 : (in_global ? 2 : 0);      // table mode: shared / global / migrated mid-sweep
+            q[4] = (PIPE ? 4 : 0) + (start_global ? 1 : (in_global ? 2 : 0));      // sweep variant; table mode: shared / global / migrated mid-sweep
         }
     }
     // ---- member order of the view's CRP: re-seated rows move to the end, in the
@@ -1168,28 +1003,23 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
         if (avail < (max_smem + 1024) / 2) avail = (max_smem + 1024) / 2;
         int budget = avail / per_sm - 1024 - 256;      // 1 KB per-CTA system reservation
         const int xbytes = 2 * p.B * stagebytes;
-        const int fixed = 64 + 64 + st->Kcap * 8 + (st->Kcap + 2) * 16 + dmax * (p.wide ? 4 : 48) + 512 + 64 + 512 + xbytes;
+        const bool pipe = nt == 256 && !getenv("CGPM_B200_ROWS_NO_PIPE") && !env_forced;       // wide views: two rows in flight
+        const int fixed = 64 + 128 + st->Kcap * 8 + (st->Kcap + 2) * (pipe ? 32 : 16) + dmax * (p.wide ? 4 : 48) + 512 + 64 + 512 + xbytes;
         bool forced = false;
         if (const char* e = getenv("CGPM_B200_ROWS_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) { budget = fixed + kb * 1024; forced = true; } }   // tests: force small tables
         if (!forced && budget < fixed + 4096) budget = fixed + 4096;
         if (budget > max_smem) budget = max_smem;
         if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }
         p.smem_bytes = budget;
-        if (nt == 256 && !getenv("CGPM_B200_ROWS_NO_PIPE") && !env_forced) {
-            // wide views: two rows in flight (rows_wide.cu); its fixed shared region is a little larger
-            const int fixed2 = cc_rows_wide_fixed_smem(st->Kcap, dmax, p.wide, xbytes);
-            if (!forced && p.smem_bytes < fixed2 + 4096) p.smem_bytes = fixed2 + 4096;
-            if (forced) p.smem_bytes += fixed2 - fixed;
-            if (p.smem_bytes > max_smem) p.smem_bytes = max_smem;
-            if (fixed2 > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed2, max_smem); return CC_ERR_ARG; }
-            const int rcw = cc_launch_rows_wide(p, cnt, strm);
-            if (rcw != CC_OK) return rcw;
+        if (pipe) {
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<224, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<224, 2, true><<<cnt, 256, budget, strm>>>(p);
         } else if (nt == 256) {
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            rows_kernel<224, 2><<<cnt, 256, budget, strm>>>(p);
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<224, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<224, 2, false><<<cnt, 256, budget, strm>>>(p);
         } else {
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            rows_kernel<128, 3><<<cnt, 160, budget, strm>>>(p);
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<128, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<128, 3, false><<<cnt, 160, budget, strm>>>(p);
         }
         CC_CUDA(cudaGetLastError());
         return CC_OK;

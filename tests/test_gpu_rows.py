@@ -187,7 +187,7 @@ def test_rows_trajectory_narrow_views(n_rows, seed, n_init, narrow, monkeypatch)
 @pytest.mark.parametrize('n_rows,seed,mixed,pipe', [(150, 11, False, True), (120, 12, True, True), (150, 11, False, False)])
 def test_rows_trajectory_wide_view(n_rows, seed, mixed, pipe, monkeypatch):
     """A view of 20 columns (with the width hint) is swept by the two-rows-in-flight kernel of
-    rows_wide.cu (pipe=True; CGPM_B200_ROWS_NO_PIPE selects the sequential sweep): both must
+    rows_sweep_pipe.cuh (pipe=True; CGPM_B200_ROWS_NO_PIPE selects the sequential sweep): both must
     follow the oracle step by step -- partitions, member order, bit-identical statistics and
     per-step conditionals -- including rows that move and make the next row's speculative
     scores stale."""
