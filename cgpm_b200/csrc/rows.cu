@@ -7,7 +7,12 @@
 //
 // One persistent CTA per (chain, view).  The scan over rows is strictly
 // sequential, exactly as in the reference; parallelism inside a step is over
-// (candidate cluster x column).  Warp roles:
+// (candidate cluster x column).  Three kernels share the per-row arithmetic
+// (rows_common.cuh) and are launched side by side by cc_transition_rows:
+//   rows_kernel<128, 3, false>   views of up to 16 columns: the sequential sweep below
+//   rows_kernel<224, 2, true>    wider views: two rows in flight (rows_sweep_pipe.cuh)
+//   rows_narrow_kernel           views of one or two normal columns: one warp, lane = candidate
+// Warp roles of rows_kernel:
 //   * NT consumer threads.  Step 1: groups of G lanes evaluate one candidate
 //     cluster each (lanes over the view's columns, shuffle-reduce).  Step 2:
 //     warp 0 does the max / w*exp / inclusive-scan / inverse-CDF draw over the
