@@ -931,16 +931,18 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     // streams ordered after / before `stream` by events):
     //   * views of one or two normal columns (the caller's n_cols / n_normal hints) -> one warp each
     //     (rows_narrow_kernel)
-    //   * views wider than 16 columns -> 7 consumer warps (each candidate cluster needs a full warp or more;
+    //   * views wider than 12 columns -> 7 consumer warps (each candidate cluster needs a full warp or more;
     //     with the producer warp that is 256 threads, i.e. 128 registers each at two CTAs per SM)
     //   * the others -> 4 consumer warps
     const int Kcap_ = st->Kcap;
     auto narrow_bytes = [&](int d) { return 12 * Kcap_ + 16 + 64 * Kcap_ * d + 16 * (Kcap_ + 1); };
     const bool env_forced = getenv("CGPM_B200_ROWS_NT") != nullptr;
     const bool narrow_ok = !env_forced && !getenv("CGPM_B200_ROWS_NO_NARROW") && !getenv("CGPM_B200_ROWS_SMEM_KB");
+    int wide_min = 12;          // views wider than this get the 7-warp, two-rows-in-flight kernel (measured: 16 -> 12 is 2 % faster, 8 much slower)
+    if (const char* e = getenv("CGPM_B200_ROWS_WIDE_MIN")) { const int v = atoi(e); if (v >= 2) wide_min = v; }
     auto klass = [&](const cc_row_work& w) -> int {
         if (narrow_ok && w.n_cols >= 1 && w.n_cols <= 2 && w.n_normal == w.n_cols && narrow_bytes(w.n_cols) <= 64 * 1024) return 0;
-        if (!env_forced && w.n_cols > 16) return 1;
+        if (!env_forced && w.n_cols > wide_min) return 1;
         return 2;
     };
     std::vector<cc_row_work> sorted(work, work + n_work);
