@@ -24,6 +24,7 @@ Reference map (all paths relative to /root/reference/src):
   dim routing/NaN  mixtures/dim.py:95-132,152-184     ODim
   normal           primitives/normal.py:64-76,128-139,165-200
   categorical      primitives/categorical.py:53-66,110-114,144-155
+  lognormal        primitives/lognormal.py:56-102,151-157 (oracle only so far: the product accepts normal / categorical)
   sampling         utils/general.py:80-86,123-157,203-205
   scheduler        crosscat/state.py:727-810,866-914
   queries          crosscat/sampling.py:37-116, crosscat/state.py:384-387,538-554
@@ -142,6 +143,16 @@ def normal_grids(X, n_grid=30):
         ('r', log_linspace(1. / N, N, n_grid)),
         ('s', log_linspace(ssqdev / 100., ssqdev, n_grid)),
         ('nu', log_linspace(1., N, n_grid)),
+    ])
+
+
+def lognormal_grids(X, n_grid=30):
+    """lognormal.py:151-157 (X = the column's non-NaN values, on the original scale)."""
+    return OrderedDict([
+        ('m', log_linspace(1e-4, max(X), n_grid)),
+        ('r', log_linspace(.1, float(len(X)), n_grid)),
+        ('nu', log_linspace(.1, float(len(X)), n_grid)),
+        ('s', log_linspace(.1, float(len(X)), n_grid)),
     ])
 
 
@@ -272,12 +283,13 @@ class ODim(object):
         self.col = col
         self.cctype = cctype
         self.distargs = dict(distargs) if distargs else {}
-        if cctype not in ('normal', 'categorical'):
-            raise ValueError('oracle covers normal/categorical only: %s' % cctype)
+        if cctype not in ('normal', 'categorical', 'lognormal'):
+            raise ValueError('oracle covers normal/categorical/lognormal only: %s' % cctype)
         self.k = int(self.distargs['k']) if cctype == 'categorical' else 0
         self.hypers = OrderedDict(hypers) if hypers else OrderedDict()
         clean = [x for x in xcol if not math.isnan(x)]
         self.grids = normal_grids(clean) if cctype == 'normal' \
+            else lognormal_grids(clean) if cctype == 'lognormal' \
             else categorical_grids(clean)
         if not self.hypers:                                   # dim.py:180-183
             for h in self.grids:
@@ -286,8 +298,8 @@ class ODim(object):
 
     # sufficient statistics ---------------------------------------------------
     def _empty(self):
-        if self.cctype == 'normal':
-            return [0, 0, 0]                                  # N, sum_x, sum_x_sq
+        if self.cctype in ('normal', 'lognormal'):
+            return [0, 0, 0]                                  # N, sum_x, sum_x_sq (of log x for lognormal)
         return [0, np.zeros(self.k)]                          # N, counts
 
     def _add(self, st, x):
@@ -295,6 +307,12 @@ class ODim(object):
             st[0] += 1.
             st[1] += x
             st[2] += x*x
+        elif self.cctype == 'lognormal':                      # lognormal.py:56-64
+            if x <= 0:
+                raise ValueError('Invalid Lognormal: %s' % str(x))
+            st[0] += 1
+            st[1] += math.log(x)
+            st[2] += math.log(x) * math.log(x)
         else:                                                 # categorical.py:53-61
             if not categorical_valid(x, self.k):
                 raise ValueError('Invalid Categorical(%d): %s' % (self.k, x))
@@ -306,6 +324,10 @@ class ODim(object):
             st[0] -= 1
             st[1] -= x
             st[2] -= x*x
+        elif self.cctype == 'lognormal':                      # lognormal.py:66-70
+            st[0] -= 1
+            st[1] -= math.log(x)
+            st[2] -= math.log(x) * math.log(x)
         else:
             st[0] -= 1
             st[1][int(x)] -= 1
@@ -334,6 +356,11 @@ class ODim(object):
         if self.cctype == 'normal':
             return normal_predictive(x, st[0], st[1], st[2],
                                      h['m'], h['r'], h['s'], h['nu'])
+        if self.cctype == 'lognormal':                        # lognormal.py:72-80
+            if x <= 0:
+                return NEG_INF
+            return - math.log(x) + normal_predictive(math.log(x), st[0], st[1], st[2],
+                                                     h['m'], h['r'], h['s'], h['nu'])
         if not categorical_valid(x, self.k):
             return NEG_INF
         return categorical_predictive(int(x), st[0], st[1], h['alpha'])
@@ -343,6 +370,9 @@ class ODim(object):
         if self.cctype == 'normal':
             return normal_marginal(st[0], st[1], st[2],
                                    h['m'], h['r'], h['s'], h['nu'])
+        if self.cctype == 'lognormal':                        # lognormal.py:98-102
+            return -st[1] + normal_marginal(st[0], st[1], st[2],
+                                            h['m'], h['r'], h['s'], h['nu'])
         return categorical_marginal(st[0], st[1], h['alpha'])
 
     def logpdf(self, x, k):
@@ -377,6 +407,8 @@ class ODim(object):
         def pack(st):
             if self.cctype == 'normal':
                 return {'N': st[0], 'sum_x': st[1], 'sum_x_sq': st[2]}
+            if self.cctype == 'lognormal':                    # lognormal.py:131-133
+                return {'N': st[0], 'sum_log_x': st[1], 'sum_log_x_sq': st[2]}
             return {'N': st[0], 'counts': list(st[1])}
         if not self.clusters:
             return [(0, pack(self._empty()))]

@@ -31,6 +31,8 @@ def ref_snapshot(state):
         for k, st in col:
             if 'counts' in st:
                 items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
+            elif 'sum_log_x' in st:        # lognormal: the same slots hold the sums of log x
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_log_x']), 'sum_x_sq': hx(st['sum_log_x_sq'])}])
             else:
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
         out['suffstats'].append(sorted(items))
@@ -85,4 +87,31 @@ def test_incremental_edits():
     both(tr(['rows', 'columns', 'alpha', 'view_alphas', 'column_hypers'], N=2))
     both(lambda s: s.unincorporate_dim(2))
     both(tr(['rows', 'columns']))
+    assert o.rng.random_sample() == ref.rng.random_sample()
+
+
+@pytest.mark.parametrize('seed', [5, 6])
+def test_oracle_equals_reference_with_lognormal_columns(seed):
+    """SURVEY 8(f) rank 3, first step: the oracle's lognormal column (normal on log x with its own hyper
+    grids and the -log x Jacobian, lognormal.py:56-102,151-157) replayed against the reference."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from cgpm.crosscat.state import State
+    X, cct, da = small_table(50, seed)
+    X = np.array(X)
+    for c in (2, 5):                                   # two of the normal columns become positive, skewed
+        X[:, c] = np.exp(0.4 * X[:, c])
+        cct[c] = 'lognormal'
+    ref = State(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed))
+    o = co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed))
+    assert snapshot_oracle(o) == ref_snapshot(ref)
+    kernels = ['alpha', 'view_alphas', 'column_hypers', 'rows', 'columns']
+    for it in range(3):
+        ref.transition(N=1, kernels=kernels, progress=False)
+        o.transition(N=1, kernels=kernels)
+        assert snapshot_oracle(o) == ref_snapshot(ref)
+        assert o.logpdf_score() == ref.logpdf_score()
+    q = ({0: 1.0, 2: 1.7}, {5: 0.8, 1: 2})
+    assert o.logpdf(-1, *q) == ref.logpdf(-1, *q)
+    assert o.logpdf(-1, {2: -1.0}) == ref.logpdf(-1, {2: -1.0}) == float('-inf')
     assert o.rng.random_sample() == ref.rng.random_sample()
