@@ -21,6 +21,7 @@ Two random-stream modes:
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import sys
 import time
@@ -34,7 +35,20 @@ from . import codec
 from . import hostmath as hm
 from .device import DeviceChains
 
-CCTYPES = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL}
+# lognormal (src/primitives/lognormal.py) is a normal column on log x: the device sees the transformed column, the
+# host keeps the original values, the column's own hyper grids, the -log x Jacobian of densities and scores,
+# and the reference's order of the hyperparameter dict (m, r, nu, s: lognormal.py:151-157).
+CCTYPES = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL, 'lognormal': L.NORMAL}
+LOGNORMAL_HYPERS = ['m', 'r', 'nu', 's']
+
+
+def lognormal_grids(xcol, n_grid=L.NGRID):
+    """Lognormal.construct_hyper_grids (lognormal.py:151-157) of the column's positive, non-NaN values, laid out in
+    the device's canonical hyper order (m, r, s, nu)."""
+    clean = [float(x) for x in xcol if not math.isnan(x)]
+    g = {'m': hm.log_linspace(1e-4, max(clean), n_grid), 'r': hm.log_linspace(.1, float(len(clean)), n_grid),
+         'nu': hm.log_linspace(.1, float(len(clean)), n_grid), 's': hm.log_linspace(.1, float(len(clean)), n_grid)}
+    return np.stack([g[n] for n in codec.HYPER_NAMES[L.NORMAL]])
 KERNELS = ['alpha', 'view_alphas', 'column_params', 'column_hypers', 'rows', 'columns']
 
 
@@ -88,7 +102,7 @@ class Chains(object):
         distargs = [dict(d) if d else {} for d in (distargs or [None] * Cn)]
         bad = [c for c in cctypes if c not in CCTYPES]
         if bad:                                           # same rule as state.py:817-820
-            raise ValueError('Only normal and categorical cgpms supported by cgpm_b200: %s' % (cctypes,))
+            raise ValueError('Only normal, lognormal and categorical cgpms supported by cgpm_b200: %s' % (cctypes,))
         for ct, d in zip(cctypes, distargs):
             if ct == 'categorical' and 'k' not in d:
                 raise ValueError('Categorical requires distarg `k`.')
@@ -104,12 +118,29 @@ class Chains(object):
         self.col_index = {c: i for i, c in enumerate(self.outputs)}
         if Vcap is None:
             Vcap = min(Cn, 32) if R * min(Cn, 32) <= (1 << 24) else min(Cn, 16)
+        # lognormal columns: log x on the device (math.log, as the reference computes it: lognormal.py:60-63)
+        self.lognormal = np.array([c == 'lognormal' for c in cctypes], dtype=bool)
+        self.X_raw = X
+        self._ln_const = 0.0
+        if self.lognormal.any():
+            X = X.copy()
+            grids = list(grids) if grids is not None else [None] * Cn
+            mlog = np.frompyfunc(math.log, 1, 1)
+            for i in np.nonzero(self.lognormal)[0]:
+                col = self.X_raw[:, i]
+                ok = ~np.isnan(col)
+                if np.any(col[ok] <= 0):
+                    raise ValueError('Invalid Lognormal: %s' % (col[ok][col[ok] <= 0][0],))
+                X[ok, i] = mlog(col[ok]).astype(np.float64)
+                if grids[i] is None:
+                    grids[i] = lognormal_grids(col)
+                self._ln_const -= float(np.sum(X[ok, i]))          # sum over rows of -log x (lognormal.py:98-102)
         self.dev = DeviceChains(X, self.ctype, self.ncat, S, Vcap=Vcap, Kcap=Kcap, device=device, grids=grids,
                                 row_alpha_grid=row_alpha_grid, col_alpha_grid=col_alpha_grid)
         self.R, self.C, self.S = R, Cn, S
         self.rngs = [None] * S
         self.views_order = [[] for _ in range(S)]
-        self.hyper_order = [[list(codec.HYPER_NAMES[int(t)]) for t in self.ctype] for _ in range(S)]
+        self.hyper_order = [[self._default_hyper_order(i) for i in range(Cn)] for _ in range(S)]
         self.diagnostics = [self._fresh_diag() for _ in range(S)]
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.counter = 1
@@ -122,6 +153,11 @@ class Chains(object):
             self._build_ci()
 
     # ------------------------------------------------------------------ set-up
+    def _default_hyper_order(self, i):
+        """Key order of the column's hyperparameter dict in the reference (= the order of its grid dict, in which
+        a fresh Dim draws them: dim.py:180-183)."""
+        return list(LOGNORMAL_HYPERS) if self.lognormal[i] else list(codec.HYPER_NAMES[int(self.ctype[i])])
+
     @staticmethod
     def _fresh_diag():
         return {'iterations': {}, 'logscore': [], 'column_crp_alpha': [], 'column_partition': []}
@@ -184,9 +220,9 @@ class Chains(object):
                     for n in names:
                         hyp[i, names.index(n)] = float(given[n])
                 else:
-                    names_all[i] = names
-                    for hi, n in enumerate(names):              # dim.py:180-183
-                        hyp[i, hi] = rng.choice(dev.grids_h[i][hi])
+                    names_all[i] = self._default_hyper_order(i)
+                    for n in names_all[i]:                      # dim.py:180-183
+                        hyp[i, names.index(n)] = rng.choice(dev.grids_h[i][names.index(n)])
         spec = {'Zv': [Zv_od[c] for c in self.outputs], 'views': views, 'alpha': float(alpha), 'hyp': hyp}
         dev.upload_chain(s, codec.pack_chain(spec, R, Cn))
         self.views_order[s] = list(range(len(views)))
@@ -690,7 +726,7 @@ class Chains(object):
     # ------------------------------------------------------------------ queries
     def logpdf_score(self):
         out = self.dev.logpdf_score()
-        return out.cpu().numpy()
+        return out.cpu().numpy() + self._ln_const
 
     def Zv_items(self, s):
         m = self.mirror()

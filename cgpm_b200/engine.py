@@ -75,14 +75,16 @@ def _chain_metadata(ch, s, X_list=None):
             cid = int(vw['cid'][pos])
             N = float(dl['stat'][L.F_N, k, i])
             if ch.ctype[i] == L.NORMAL:
-                items.append((cid, {'N': N, 'sum_x': float(dl['stat'][L.F_SX, k, i]),
-                                    'sum_x_sq': float(dl['stat'][L.F_SXX, k, i])}))
+                sx, sxx = (('sum_log_x', 'sum_log_x_sq') if ch.lognormal[i] else ('sum_x', 'sum_x_sq'))
+                items.append((cid, {'N': N, sx: float(dl['stat'][L.F_SX, k, i]),
+                                    sxx: float(dl['stat'][L.F_SXX, k, i])}))
             else:
                 o0 = ch.dev.catoff_h[i]
                 items.append((cid, {'N': int(N), 'counts': [float(x) for x in dl['cnt'][k, o0:o0 + ch.ncat[i]]]}))
         top = max(int(c) for c in vw['cid']) + 1
         if ch.ctype[i] == L.NORMAL:
-            items.append((top, {'N': 0, 'sum_x': 0, 'sum_x_sq': 0}))
+            sx, sxx = (('sum_log_x', 'sum_log_x_sq') if ch.lognormal[i] else ('sum_x', 'sum_x_sq'))
+            items.append((top, {'N': 0, sx: 0, sxx: 0}))
         else:
             items.append((top, {'N': 0, 'counts': [0.0] * int(ch.ncat[i])}))
         md['suffstats'].append(items)

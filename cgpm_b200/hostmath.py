@@ -22,6 +22,11 @@ def logsumexp(array):
     return m + math.log(sum(math.exp(a - m) for a in array))
 
 
+def log_linspace(a, b, n):
+    """src/utils/general.py:203-205."""
+    return np.exp(np.linspace(math.log(a), math.log(b), n))
+
+
 def logmeanexp(array):
     """src/utils/general.py:159-182."""
     if len(array) == 0:

@@ -6,6 +6,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import math
+
 import numpy as np
 import torch
 
@@ -24,7 +26,7 @@ def _validate(ch, rowid, targets, constraints, simulate):
     for c in list(tcols) + list(constraints):
         if c not in ch.col_index:
             raise ValueError('Unknown column: %s' % (c,))
-    X = ch.dev.X_h
+    X = ch.X_raw
     if not fresh and not simulate and any(not np.isnan(X[rowid, ch.col_index[q]]) for q in tcols):
         raise ValueError('Cannot constrain observed cell.')
     if constraints:
@@ -46,6 +48,23 @@ def _encode(ch, rowids, targets_list, constraints_list, simulate):
     rid = np.full(Q, -1, np.int32)
     off = np.zeros(Q + 1, np.int32)
     cols, vals, roles = [], [], []
+    jac = np.zeros(Q)                       # lognormal targets: - log x (lognormal.py:72-80)
+    dead = np.zeros(Q, dtype=bool)          # a lognormal target <= 0 has density 0
+
+    def on_device(c, x, q, target):
+        i = ch.col_index[c]
+        x = float(x)
+        if not ch.lognormal[i]:
+            return x
+        if x <= 0:
+            if not target:
+                raise ValueError('Zero density constraints: %s' % ({c: x},))
+            dead[q] = True
+            return 0.0
+        if target:
+            jac[q] -= math.log(x)
+        return math.log(x)
+
     for q in range(Q):
         t = targets_list[q]
         cns = constraints_list[q] or {}
@@ -56,9 +75,9 @@ def _encode(ch, rowids, targets_list, constraints_list, simulate):
                 cols.append(ch.col_index[c]); vals.append(0.0); roles.append(0)
         else:
             for c, x in t.items():
-                cols.append(ch.col_index[c]); vals.append(float(x)); roles.append(0)
+                cols.append(ch.col_index[c]); vals.append(on_device(c, x, q, True)); roles.append(0)
         for c, x in cns.items():
-            cols.append(ch.col_index[c]); vals.append(float(x)); roles.append(1)
+            cols.append(ch.col_index[c]); vals.append(on_device(c, x, q, False)); roles.append(1)
         off[q + 1] = len(cols)
     dev = ch.dev.device
     enc = {
@@ -66,7 +85,7 @@ def _encode(ch, rowids, targets_list, constraints_list, simulate):
         'col': torch.from_numpy(np.asarray(cols or [0], np.int32)).to(dev),
         'val': torch.from_numpy(np.asarray(vals or [0.0], np.float64)).to(dev),
         'role': torch.from_numpy(np.asarray(roles or [0], np.uint8)).to(dev),
-        'constraints': constraints_list,
+        'constraints': constraints_list, 'jac': jac, 'dead': dead,
     }
     return enc
 
@@ -94,6 +113,8 @@ def logpdf_bulk_encoded(ch, chains, enc):
     if bad.any():
         q = int(np.nonzero(bad.any(axis=0))[0][0])
         raise ValueError('Zero density constraints: %s' % (enc['constraints'][q],))   # sampling.py:78-79
+    res = res + enc['jac'][None, :]
+    res[:, enc['dead']] = -np.inf
     return res
 
 
@@ -138,9 +159,11 @@ def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=No
         for q in range(Q):
             tcols = list(targets_list[q])
             is_cat = [ch.ctype[ch.col_index[c]] == L.CATEGORICAL for c in tcols]
+            is_ln = [bool(ch.lognormal[ch.col_index[c]]) for c in tcols]
             samples = []
             for r in range(soff[q], soff[q + 1]):
-                samples.append({c: (int(vals[i, r, j]) if is_cat[j] else float(vals[i, r, j]))
+                samples.append({c: (int(vals[i, r, j]) if is_cat[j] else
+                                    math.exp(vals[i, r, j]) if is_ln[j] else float(vals[i, r, j]))
                                 for j, c in enumerate(tcols)})
             per_chain.append(samples)
         res.append(per_chain)

@@ -24,7 +24,7 @@ Reference map (all paths relative to /root/reference/src):
   dim routing/NaN  mixtures/dim.py:95-132,152-184     ODim
   normal           primitives/normal.py:64-76,128-139,165-200
   categorical      primitives/categorical.py:53-66,110-114,144-155
-  lognormal        primitives/lognormal.py:56-102,151-157 (oracle only so far: the product accepts normal / categorical)
+  lognormal        primitives/lognormal.py:56-102,151-157
   sampling         utils/general.py:80-86,123-157,203-205
   scheduler        crosscat/state.py:727-810,866-914
   queries          crosscat/sampling.py:37-116, crosscat/state.py:384-387,538-554

@@ -147,6 +147,8 @@ def snapshot_engine(eng, s):
         for k, st in col:
             if 'counts' in st:
                 items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
+            elif 'sum_log_x' in st:        # lognormal: the same slots hold the sums of log x
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_log_x']), 'sum_x_sq': hx(st['sum_log_x_sq'])}])
             else:
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
         out['suffstats'].append(sorted(items))
