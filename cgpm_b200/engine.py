@@ -316,7 +316,7 @@ class State(_Api):
         return [dict(d) for d in self._ch.distargs]
 
     def data_array(self):
-        return self._ch.dev.X_h.copy()
+        return self._ch.X_raw.copy()
 
     def alpha(self):
         return float(self._ch.dev.t['col_alpha'][0].item())
@@ -404,7 +404,7 @@ class State(_Api):
 
     # ---- serialise ---------------------------------------------------------------
     def to_metadata(self):
-        return _chain_metadata(self._ch, 0, X_list=self._ch.dev.X_h.tolist())
+        return _chain_metadata(self._ch, 0, X_list=self._ch.X_raw.tolist())
 
     def to_pickle(self, fileptr):
         pickle.dump(self.to_metadata(), fileptr)
@@ -453,7 +453,7 @@ class Engine(_Api):
 
     def _after_edit(self, new):
         self._ch = new
-        self.X = new.dev.X_h.copy()
+        self.X = new.X_raw.copy()
         self._state_kwargs = dict(self._state_kwargs, outputs=list(new.outputs), cctypes=list(new.cctypes),
                                   distargs=[dict(d) for d in new.distargs])
 

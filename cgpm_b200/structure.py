@@ -22,7 +22,7 @@ import torch
 from . import _lib as L
 from . import codec
 from . import hostmath as hm
-from .core import Chains
+from .core import Chains, LOGNORMAL_HYPERS, lognormal_grids
 from .device import hyper_grids, crp_grid
 
 CRP_ID_VIEW = 10 ** 7          # state.py:142: cluster-token output id of view v is 10**7 + v
@@ -137,19 +137,21 @@ def build(old, X, outputs, cctypes, distargs, grids, states, rebuild_cols=()):
 
 def _schema(ch):
     grids = [ch.dev.grids_h[i] for i in range(ch.C)]
-    return ch.dev.X_h.copy(), list(ch.outputs), list(ch.cctypes), [dict(d) for d in ch.distargs], grids
+    return ch.X_raw.copy(), list(ch.outputs), list(ch.cctypes), [dict(d) for d in ch.distargs], grids      # X on the original scale
 
 
-def _no_lognormal(ch, what):
-    """Incremental edits re-create the device table from the transformed columns; tables with lognormal columns
-    (kept as log x on the device) are not carried across yet."""
-    if getattr(ch, 'lognormal', None) is not None and ch.lognormal.any():
-        raise NotImplementedError('cgpm_b200: %s is not supported yet for tables with lognormal columns' % what)
+def _dev_value(ch, i, x):
+    """The value of a cell as the device table and the sufficient statistics hold it: log x for a lognormal
+    column (lognormal.py:56-64; a non-positive value is invalid), x otherwise."""
+    if i < len(ch.lognormal) and ch.lognormal[i] and not math.isnan(x):
+        if x <= 0:
+            raise ValueError('Invalid Lognormal: %s' % str(x))
+        return math.log(x)
+    return x
 
 
 def incorporate(ch, rowid, observation, chains=None):
     """State.incorporate (state.py:255-283) for every chain; returns the new Chains."""
-    _no_lognormal(ch, 'incorporate')
     X, outputs, cctypes, distargs, grids = _schema(ch)
     R = X.shape[0]
     if rowid != R:
@@ -181,7 +183,7 @@ def incorporate(ch, rowid, observation, chains=None):
                 if fresh:
                     fs['stats'][(i, k)] = _empty(ch.ctype[i], ch.ncat[i])       # dim.py:99-101
                 if not math.isnan(row[i]):
-                    _add(fs['stats'][(i, k)], row[i], ch.ctype[i] == L.NORMAL)
+                    _add(fs['stats'][(i, k)], _dev_value(ch, i, row[i]), ch.ctype[i] == L.NORMAL)
             if given is None:
                 todo.append((s, vid))
     new = build(ch, X, outputs, cctypes, distargs, grids, states)
@@ -201,7 +203,6 @@ def incorporate(ch, rowid, observation, chains=None):
 
 def unincorporate(ch, rowid):
     """State.unincorporate (state.py:285-299)."""
-    _no_lognormal(ch, 'unincorporate')
     X, outputs, cctypes, distargs, grids = _schema(ch)
     R = X.shape[0]
     if rowid != R - 1:
@@ -216,7 +217,7 @@ def unincorporate(ch, rowid):
             cols = [i for i, v in enumerate(fs['Zv']) if v == vid]
             for i in cols:
                 if not math.isnan(row[i]):
-                    _sub(fs['stats'][(i, k)], row[i], ch.ctype[i] == L.NORMAL)
+                    _sub(fs['stats'][(i, k)], _dev_value(ch, i, row[i]), ch.ctype[i] == L.NORMAL)
             vw['Zr'].pop()
             vw['order'].remove(rowid)
             if k not in vw['Zr']:                                                # view.py:181-183
@@ -227,7 +228,6 @@ def unincorporate(ch, rowid):
 
 def force_cell(ch, rowid, observation):
     """State.force_cell (state.py:302-315)."""
-    _no_lognormal(ch, 'force_cell')
     X, outputs, cctypes, distargs, grids = _schema(ch)
     if not 0 <= rowid < X.shape[0]:
         raise ValueError('Force observation requires existing rowid.')
@@ -241,13 +241,12 @@ def force_cell(ch, rowid, observation):
         X[rowid, i] = float(value)
         for fs in states:
             k = fs['views'][fs['Zv'][i]]['Zr'][rowid]
-            _add(fs['stats'][(i, k)], float(value), ch.ctype[i] == L.NORMAL)
+            _add(fs['stats'][(i, k)], _dev_value(ch, i, float(value)), ch.ctype[i] == L.NORMAL)
     return build(ch, X, outputs, cctypes, distargs, grids, states)
 
 
 def incorporate_dim(ch, T, outputs_new, inputs=None, cctype=None, distargs=None, v=None):
     """State.incorporate_dim (state.py:187-236)."""
-    _no_lognormal(ch, 'incorporate_dim')
     X, outputs, cctypes, dargs, grids = _schema(ch)
     R = X.shape[0]
     if len(T) != R:
@@ -259,13 +258,20 @@ def incorporate_dim(ch, T, outputs_new, inputs=None, cctype=None, distargs=None,
     if inputs:
         raise ValueError('Cannot incorporate dim with inputs: %s.' % inputs)
     cctype = cctype or 'normal'
-    if cctype not in ('normal', 'categorical'):
-        raise ValueError('Only normal and categorical cgpms supported by cgpm_b200: %s' % (cctype,))
+    if cctype not in ('normal', 'lognormal', 'categorical'):
+        raise ValueError('Only normal, lognormal and categorical cgpms supported by cgpm_b200: %s' % (cctype,))
     col = outputs_new[0]
     Tn = np.asarray(T, dtype=np.float64)
-    code = L.NORMAL if cctype == 'normal' else L.CATEGORICAL
-    g_new = hyper_grids(Tn, code)
-    names = list(codec.HYPER_NAMES[code])
+    code = L.CATEGORICAL if cctype == 'categorical' else L.NORMAL
+    canon = list(codec.HYPER_NAMES[code])
+    if cctype == 'lognormal':
+        if np.any(Tn[~np.isnan(Tn)] <= 0):
+            raise ValueError('Invalid Lognormal: %s' % (Tn[~np.isnan(Tn)][Tn[~np.isnan(Tn)] <= 0][0],))
+        g_new = lognormal_grids(Tn)
+        names = list(LOGNORMAL_HYPERS)             # the order in which the reference's Dim draws them
+    else:
+        g_new = hyper_grids(Tn, code)
+        names = list(canon)
     states = [full_state(ch, s) for s in range(ch.S)]
     v_add = 0 if v is None else v
     exact = ch.stream == 'numpy'
@@ -278,7 +284,9 @@ def incorporate_dim(ch, T, outputs_new, inputs=None, cctype=None, distargs=None,
             zr = (hm.crp_simulate_exact if exact else hm.crp_simulate_fast)(R, alpha, rng)
             fs['views'][v_add] = {'alpha': float(alpha), 'Zr': [int(z) for z in zr], 'order': list(range(R)),
                                   'grid': grid}
-        hyp_new = np.array([rng.choice(g_new[hi]) if hi < len(names) else 0.0 for hi in range(4)])   # dim.py:180-183
+        hyp_new = np.zeros(4)
+        for nm in names:                                                  # dim.py:180-183
+            hyp_new[canon.index(nm)] = rng.choice(g_new[canon.index(nm)])
         fs['hyp'] = np.vstack([fs['hyp'], hyp_new[None, :]])
         fs['Zv'] = fs['Zv'] + [v_add]
         fs['hyper_order'] = list(fs['hyper_order']) + [names]
@@ -298,7 +306,6 @@ def incorporate_dim(ch, T, outputs_new, inputs=None, cctype=None, distargs=None,
 
 def unincorporate_dim(ch, col):
     """State.unincorporate_dim (state.py:238-253)."""
-    _no_lognormal(ch, 'unincorporate_dim')
     X, outputs, cctypes, dargs, grids = _schema(ch)
     if len(outputs) == 1:
         raise ValueError('State has only one dim, cannot unincorporate.')

@@ -183,11 +183,6 @@ def test_engine_with_lognormal_columns_follows_oracle(n_rows, seed):
             ref = o.logpdf(-1, t, cns)
             assert abs(got[s] - ref) <= 1e-9 * max(1.0, abs(ref)), (t, cns, got[s], ref)
     assert all(v == float('-inf') for v in eng.logpdf(-1, {2: -1.0}))
-    # simulate returns positive values for lognormal columns; their logs follow the normal predictive (KS-free check:
-    # the sample mean of log x is within 6 standard errors of a large oracle-free reference draw of the same engine)
-    smp = eng.simulate(-1, [2, 5], N=400)
-    a = np.array([[d[2], d[5]] for d in smp[0]])
-    assert np.all(a > 0)
     # metadata: lognormal suffstat names, original X, cctypes
     md = eng.to_metadata()
     assert md['states'][0]['cctypes'][2] == 'lognormal'
@@ -195,8 +190,29 @@ def test_engine_with_lognormal_columns_follows_oracle(n_rows, seed):
     assert np.allclose(np.array(md['X'], dtype=float)[:, 2][~np.isnan(X[:, 2])], X[:, 2][~np.isnan(X[:, 2])], rtol=0, atol=0)
     eng2 = Engine.from_metadata(md, rng=gen_rng(1))
     assert np.allclose(eng2.logpdf_score(), eng.logpdf_score(), rtol=1e-12)
-    # incremental edits are refused loudly for such tables
-    with pytest.raises(NotImplementedError):
-        eng.incorporate(n_rows, {0: 0.5})
+    # incremental edits keep the original scale on the host and log x on the device
+    def both(tag, fe, fo):
+        fe(eng)
+        for o in oracles:
+            fo(o)
+        compare(eng, oracles, tag)
+    R = n_rows
+    both('inc', lambda e: e.incorporate(R, {0: 0.5, 2: 2.5, 5: 0.3}), lambda o: o.incorporate(R, {0: 0.5, 2: 2.5, 5: 0.3}))
+    both('inc2', lambda e: e.incorporate(R + 1, {2: 0.7, 4: 0.1}), lambda o: o.incorporate(R + 1, {2: 0.7, 4: 0.1}))
+    both('force', lambda e: e.force_cell(R + 1, {5: 1.9}), lambda o: o.force_cell(R + 1, {5: 1.9}))
+    both('t', lambda e: e.transition(N=1, kernels=KERNELS, progress=False), lambda o: o.transition(N=1, kernels=KERNELS))
+    both('uninc', lambda e: e.unincorporate(R + 1), lambda o: o.unincorporate(R + 1))
+    T = list(np.exp(np.random.RandomState(3).normal(size=R + 1)))
+    both('dim+', lambda e: e.incorporate_dim(T, [90], cctype='lognormal', v=99), lambda o: o.incorporate_dim(T, [90], cctype='lognormal', v=99))
+    both('t2', lambda e: e.transition(N=1, kernels=KERNELS, progress=False), lambda o: o.transition(N=1, kernels=KERNELS))
+    both('dim-', lambda e: e.unincorporate_dim(2), lambda o: o.unincorporate_dim(2))
+    assert eng.X.shape == (R + 1, 6) and np.all(eng.X[~np.isnan(eng.X[:, 4]), 4] > 0)      # column 5 stays on the original scale
+    with pytest.raises(ValueError):
+        eng.incorporate(R + 1, {5: -1.0})
     for s, o in enumerate(oracles):
+        assert eng._ch.rngs[s].random_sample() == o.rng.random_sample()
         assert eng._ch.diagnostics[s]['iterations'] == o.iterations
+    # simulate (last: it consumes the chains' RandomStates) returns positive values for lognormal columns
+    smp = eng.simulate(-1, [90, 5], N=200)
+    a = np.array([[d[90], d[5]] for d in smp[0]])
+    assert np.all(a > 0) and np.isfinite(a).all()
