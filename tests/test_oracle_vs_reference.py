@@ -114,4 +114,19 @@ def test_oracle_equals_reference_with_lognormal_columns(seed):
     q = ({0: 1.0, 2: 1.7}, {5: 0.8, 1: 2})
     assert o.logpdf(-1, *q) == ref.logpdf(-1, *q)
     assert o.logpdf(-1, {2: -1.0}) == ref.logpdf(-1, {2: -1.0}) == float('-inf')
+    # incremental edits on a table with lognormal columns
+
+    def both(f):
+        f(ref); f(o)
+        assert snapshot_oracle(o) == ref_snapshot(ref)
+    both(lambda s: s.incorporate(50, {0: 0.5, 2: 2.5, 5: 0.3}))
+    both(lambda s: s.incorporate(51, {2: 0.7, 4: 0.1}))
+    both(lambda s: s.force_cell(51, {5: 1.9}))
+    both(lambda s: s.unincorporate(51))
+    T = list(np.exp(np.random.RandomState(3).normal(size=51)))
+    both(lambda s: s.incorporate_dim(T, [90], cctype='lognormal', distargs=None, v=99))
+    ref.transition(N=1, kernels=kernels, progress=False)
+    o.transition(N=1, kernels=kernels)
+    assert snapshot_oracle(o) == ref_snapshot(ref)
+    assert o.logpdf_score() == ref.logpdf_score()
     assert o.rng.random_sample() == ref.rng.random_sample()
