@@ -18,6 +18,8 @@ from __future__ import annotations
 import pickle
 from collections import OrderedDict
 
+import math
+
 import numpy as np
 
 from . import _lib as L
@@ -178,12 +180,33 @@ class _Api(object):
         return (acc / len(slots)).cpu().numpy()
 
     def _relevance_probability(self, s, rowid_target, rowid_query, col, hypotheticals=None):
-        """state.py:599-633 without hypothetical rows."""
-        if hypotheticals:
-            raise NotImplementedError('cgpm_b200: relevance_probability with hypothetical rows is out of scope.')
+        """state.py:599-629.  Hypothetical rows are incorporated into the column's view with one Gibbs step each
+        (view.py:149-172), consuming the chain's RandomState like the reference; this is done on a temporary copy
+        of the chain, so -- unlike the reference, whose incorporate / unincorporate pair may change the view's sums
+        in the last bit -- the live chain's statistics are untouched."""
         if col not in self._ch.col_index:
             raise ValueError('Unknown column: %s' % (col,))
-        view = self._views(s)[self._Zv(s)[col]]
+        vid = self._Zv(s)[col]
+        view = self._views(s)[vid]
+        hyps = []
+        for h in (hypotheticals or []):
+            q = {d: float(h[d]) for d in view.dims if d in h and not math.isnan(h[d])}
+            if q:
+                hyps.append(q)
+        rowid_query = list(rowid_query)
+        if hyps:
+            from .structure import CRP_ID_VIEW
+            md = _chain_metadata(self._ch, s, X_list=self._ch.X_raw.tolist())
+            opts = dict(getattr(self, '_opts', {}) or {})
+            opts['stream'] = self._ch.stream
+            tmp = State.from_metadata(md, rng=self._ch.rngs[s], **opts)
+            R = tmp._ch.R
+            # the other views keep the row out of the way: seated at an existing table, no Gibbs step, no cells
+            tokens = {CRP_ID_VIEW + w: int(vw.Zr(0)) for w, vw in tmp.views.items() if w != vid}
+            for j, q in enumerate(hyps):
+                tmp.incorporate(R + j, dict(q, **tokens))
+            view = tmp.views[vid]
+            rowid_query = rowid_query + list(range(R, R + len(hyps)))
         return int(all(view.Zr(rowid_target) == view.Zr(rq) for rq in rowid_query)) if rowid_query else 0
 
     def _mutual_information(self, s, col0, col1, constraints=None, T=None, N=None):

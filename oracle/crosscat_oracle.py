@@ -810,6 +810,27 @@ class OState(object):
         lp_tgt = [self._row_logpdf(view, targets, k) for k in K]
         return logsumexp(np.add(lp_cluster, lp_tgt))
 
+    def relevance_probability(self, rowid_target, rowid_query, col, hypotheticals=None):
+        """state.py:599-629: hypothetical rows are incorporated into the column's view (one Gibbs step each),
+        the answer is read off the partition, and they are removed again."""
+        view = self.views[self.Zv[col]]
+        hyps = []
+        for h in (hypotheticals or []):
+            q = {d: h.get(d, float('nan')) for d in view.dims}
+            if not all(math.isnan(v) for v in q.values()):
+                hyps.append(q)
+        rowid_hyp = list(range(self.n_rows, self.n_rows + len(hyps)))
+        for rowid, query in zip(rowid_hyp, hyps):
+            for d in view.dims:
+                self.X[d].append(query[d])
+            view.incorporate(rowid, query)
+        rowid_all = list(rowid_query) + rowid_hyp
+        relevance = all(view.Zr[rowid_target] == view.Zr[rq] for rq in rowid_all) if rowid_all else 0
+        for rowid in reversed(rowid_hyp):
+            view._popped = {d: self.X[d].pop() for d in view.dims}
+            view.unincorporate(rowid)
+        return int(relevance)
+
     def dependence_probability(self, c0, c1):
         return float(self.Zv[c0] == self.Zv[c1])
 

@@ -175,3 +175,20 @@ def test_row_similarity_relevance_and_mutual_information():
         w = (ga[1] - ga[0]) * (gb[1] - gb[0])
         ref = float(np.sum(np.exp(pab) * (pab - pa[:, None] - pb[None, :])) * w)
         assert abs(est - ref) < 0.12 + 0.15 * abs(ref), (est, ref)
+
+
+def test_relevance_probability_with_hypothetical_rows():
+    """state.py:599-629: hypothetical rows are incorporated into the column's view with one Gibbs step each; the
+    engine (numpy stream) gives the oracle's answers and consumes the chains' RandomStates identically."""
+    X, cct, da, eng, oracles = make(n_rows=60, seed=71, S=2, iters=3)
+    hyp = [{0: 0.3, 2: -0.2}, {4: 1.0}, {1: 2, 3: 0}, {0: float('nan')}]
+    cases = [(3, [5, 8], 0), (3, [], 2), (10, [11], 4), (0, [1, 2, 3], 1), (7, [7], 5)]
+    for tgt, qry, col in cases:
+        got = eng.relevance_probability(tgt, qry, col, hypotheticals=hyp)
+        for s, o in enumerate(oracles):
+            assert got[s] == o.relevance_probability(tgt, qry, col, hyp), (tgt, qry, col, s)
+    for s, o in enumerate(oracles):
+        assert eng._ch.rngs[s].random_sample() == o.rng.random_sample()
+    st = eng.get_state(0)
+    assert st.relevance_probability(3, [5], 0, hypotheticals=[{0: 0.1}]) in (0, 1)
+    assert eng.num_states() == 2 and eng.X.shape == (60, len(cct))          # nothing was left behind

@@ -130,3 +130,21 @@ def test_oracle_equals_reference_with_lognormal_columns(seed):
     assert snapshot_oracle(o) == ref_snapshot(ref)
     assert o.logpdf_score() == ref.logpdf_score()
     assert o.rng.random_sample() == ref.rng.random_sample()
+
+
+def test_relevance_probability_with_hypothetical_rows():
+    """state.py:599-629 against the oracle: same answers, same statistics and stream position afterwards."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from cgpm.crosscat.state import State
+    X, cct, da = small_table(60, 7)
+    ref = State(X, cctypes=cct, distargs=da, rng=np.random.RandomState(7))
+    o = co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(7))
+    for s in (ref, o):
+        s.transition(N=2, kernels=['rows', 'columns'], **({'progress': False} if s is ref else {}))
+    hyp = [{0: 0.3, 2: -0.2}, {4: 1.0}, {1: 2, 3: 0}]
+    for tgt, qry, col in [(3, [5, 8], 0), (3, [], 2), (10, [11], 4), (0, [1, 2, 3], 1)]:
+        assert o.relevance_probability(tgt, qry, col, hyp) == ref.relevance_probability(tgt, list(qry), col, hyp)
+        assert o.relevance_probability(tgt, qry, col) == ref.relevance_probability(tgt, list(qry), col)
+    assert snapshot_oracle(o) == ref_snapshot(ref)
+    assert o.rng.random_sample() == ref.rng.random_sample()
