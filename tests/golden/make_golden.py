@@ -52,19 +52,26 @@ def snapshot(state):
         for k, st in col:
             if 'counts' in st:
                 items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
+            elif 'sum_log_x' in st:      # lognormal: the same slots hold the sums of log x
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_log_x']), 'sum_x_sq': hx(st['sum_log_x_sq'])}])
             else:
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
         out['suffstats'].append(sorted(items))
     return out
 
 
-def trajectory():
+def trajectory(lognormal=False):
     cct = ['normal', 'categorical', 'normal', 'categorical', 'normal', 'normal']
     da = [None, {'k': 4}, None, {'k': 3}, None, None]
     T, _Zv, _Zc = tu.gen_data_table(
         40, [.5, .5], [[.3, .7], [.2, .3, .5]], cct, da, [.9] * 6, rng=gu.gen_rng(0))
     X = T.T.copy()
     X[3, 0] = X[7, 1] = X[10, 2] = X[11, 3] = X[20, 5] = np.nan
+    if lognormal:                  # columns 2 and 5 become positive and lognormal
+        cct = list(cct)
+        for c in (2, 5):
+            X[:, c] = np.exp(0.5 * X[:, c])
+            cct[c] = 'lognormal'
     seed, S, N = 17, 2, 4
     eng = Engine(X, num_states=S, rng=gu.gen_rng(seed), cctypes=cct, distargs=da, multiprocess=0)
     g = {
@@ -77,7 +84,7 @@ def trajectory():
         eng.transition(N=1, kernels=KERNELS, progress=False, multiprocess=0)
         g['after'].append([snapshot(s) for s in eng.states])
     queries = [[-1, {'0': 1.2}, {}], [-1, {'0': 1.2, '1': 2}, {'2': 0.3}],
-               [-1, {'3': 1, '5': -0.5}, {'0': 2., '4': 1., '1': 0}], [3, {'0': 0.5}, {}]]
+               [-1, {'3': 1, '5': -0.5 if not lognormal else 0.6}, {'0': 2., '4': 1., '1': 0}], [3, {'0': 0.5}, {}]]
     for rowid, t, c in queries:
         tt = {int(k): v for k, v in t.items()}
         cc = {int(k): v for k, v in c.items()}
@@ -122,4 +129,6 @@ if __name__ == '__main__':
         json.dump(trajectory(), f)
     with open(os.path.join(HERE, 'primitive_kats.json'), 'w') as f:
         json.dump(kats(), f, indent=1)
+    with open(os.path.join(HERE, 'trajectory_lognormal_40x6.json'), 'w') as f:
+        json.dump(trajectory(lognormal=True), f)
     print('golden vectors written')

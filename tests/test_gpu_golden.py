@@ -9,9 +9,10 @@ from helpers import load_golden, golden_table, snapshot_engine, assert_snapshot_
 pytestmark = pytest.mark.gpu
 
 
-def test_engine_reproduces_reference_golden_trajectory():
+@pytest.mark.parametrize('fixture', ['trajectory_40x6.json', 'trajectory_lognormal_40x6.json'])
+def test_engine_reproduces_reference_golden_trajectory(fixture):
     from cgpm_b200.engine import Engine, gen_rng
-    g = load_golden('trajectory_40x6.json')
+    g = load_golden(fixture)
     X, cct, da = golden_table(g)
     S = g['num_states']
     eng = Engine(X, num_states=S, rng=gen_rng(g['engine_seed']), cctypes=cct, distargs=da, stream='numpy')

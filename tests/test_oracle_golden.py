@@ -11,8 +11,9 @@ import crosscat_oracle as co
 from helpers import load_golden, golden_table, snapshot_oracle, assert_snapshot_equal
 
 
-def test_oracle_reproduces_reference_trajectory_bit_for_bit():
-    g = load_golden('trajectory_40x6.json')
+@pytest.mark.parametrize('fixture', ['trajectory_40x6.json', 'trajectory_lognormal_40x6.json'])
+def test_oracle_reproduces_reference_trajectory_bit_for_bit(fixture):
+    g = load_golden(fixture)
     X, cct, da = golden_table(g)
     seeds = np.random.RandomState(g['engine_seed']).randint(low=1, high=2 ** 32 - 1, size=g['num_states'])
     states = [co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(sd)) for sd in seeds]
