@@ -16,6 +16,8 @@ NFIELD = 8
 NORMAL, CATEGORICAL = 0, 1
 F_N, F_SX, F_SXX, F_MN, F_A, F_CST, F_GN, F_GM1 = range(8)
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3
+ROWS_DONE, ROWS_HANDOVER, ROWS_GROW = 0, 1, 2
+ABI_VERSION = 3
 
 
 class cc_state(C.Structure):
@@ -29,7 +31,7 @@ class cc_state(C.Structure):
         ('view_id', C.c_void_p), ('col_alpha', C.c_void_p), ('view_alpha', C.c_void_p), ('view_grid', C.c_void_p),
         ('nclu', C.c_void_p), ('live', C.c_void_p), ('cid', C.c_void_p), ('nk', C.c_void_p),
         ('zr', C.c_void_p), ('order', C.c_void_p), ('stat', C.c_void_p), ('cnt', C.c_void_p),
-        ('err', C.c_void_p),
+        ('err', C.c_void_p), ('rows_prog', C.c_void_p),
         ('seq', C.c_void_p), ('moved', C.c_void_p), ('movedflag', C.c_void_p),
         ('colL', C.c_void_p), ('aux_zr', C.c_void_p), ('aux_K', C.c_void_p),
         ('aux_alpha', C.c_void_p), ('aux_zr_all', C.c_void_p), ('aux_K_all', C.c_void_p),
@@ -42,6 +44,7 @@ class cc_row_work(C.Structure):
         ('chain', C.c_int32), ('view', C.c_int32), ('n', C.c_int32),
         ('perm_is_index', C.c_int32), ('perm_off', C.c_int64), ('u_off', C.c_int64),
         ('trace_off', C.c_int64), ('n_cols', C.c_int32), ('n_normal', C.c_int32),
+        ('resume', C.c_int32), ('_pad', C.c_int32),
     ]
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define CC_ABI_VERSION 2
+#define CC_ABI_VERSION 3
 #define CC_NGRID 30          /* hyper-grid points, dim.py:176 n_grid=30        */
 #define CC_NFIELD 8          /* per (cluster, column) statistic fields          */
 
@@ -45,6 +45,11 @@ extern "C" {
 #define CC_F_CST  5   /* cached constant: normal G(N) - log(sn)/2 ; categorical log(N + alpha k) */
 #define CC_F_GN   6   /* cached G(N)   = lgamma((nu+N+1)/2)-lgamma((nu+N)/2)+log((r+N)/(r+N+1))/2-log(pi)/2 */
 #define CC_F_GM1  7   /* cached G(N-1)                               */
+
+/* rows_prog[..][2] */
+#define CC_ROWS_DONE      0
+#define CC_ROWS_HANDOVER  1
+#define CC_ROWS_GROW      2
 
 #define CC_OK            0
 #define CC_ERR_ARG       1   /* invalid argument -> Python ValueError           */
@@ -80,6 +85,13 @@ typedef struct cc_state {
     double*  stat;       /* [S][CC_NFIELD][Kcap][C]                               */
     double*  cnt;        /* [S][Kcap][CT]   categorical counts                    */
     int32_t* err;        /* [S]  sticky per-chain error code (CC_ERR_CAPACITY)    */
+    int32_t* rows_prog;  /* [S][Vcap][4]  progress of the view's rows sweep: {next row position, rows re-seated so
+                            far, status, -}.  status CC_ROWS_DONE after a complete sweep; CC_ROWS_HANDOVER while a
+                            sweep is passed from the shared-memory kernel to the large-K kernel inside one
+                            cc_transition_rows call; CC_ROWS_GROW when the sweep stopped in front of a move that
+                            needs a cluster slot beyond Kcap: the caller re-allocates the per-cluster arrays with a
+                            larger Kcap and calls cc_transition_rows again with `resume` = 1 (same seed, counter
+                            and injected buffers) -- the sweep continues with the same row, nothing is lost */
     /* ---- scratch (caller-allocated, contents undefined between calls) ----- */
     int32_t* seq;        /* [S][Vcap][R]  spare scratch (per-CTA / per-pair cycle counters of the debug probes) */
     int32_t* moved;      /* [S][Vcap][R]  rows re-seated in the current sweep, in order */
@@ -105,8 +117,10 @@ typedef struct cc_row_work {
     int64_t u_off;        /* into `u`,    or -1: Philox uniforms                  */
     int64_t trace_off;    /* into `trace`, or -1                                  */
     int32_t n_cols;       /* number of columns of the view if the caller knows it (sizes shared memory), else 0 */
-    int32_t n_normal;     /* how many of them are normal columns, if the caller knows it, else 0: a view of one or
-                             two normal columns is swept by the single-warp kernel */
+    int32_t n_normal;     /* how many of them are normal columns, if the caller knows it, else 0 */
+    int32_t resume;       /* 0: a fresh sweep; 1: continue the sweep recorded in rows_prog (items whose status is
+                             CC_ROWS_DONE are skipped) */
+    int32_t _pad;
 } cc_row_work;
 
 const char* cc_last_error(void);
@@ -141,7 +155,9 @@ int cc_logpdf_score(const cc_state* st, double* out, void* stream);
 
 /* View.transition_rows for every work item (src/mixtures/view.py:247-252,
  * 393-429).  `perm`, `u`, `trace` are device buffers (may be NULL when no work
- * item refers to them).  seed/counter key the device generator. */
+ * item refers to them).  seed/counter key the device generator.  A sweep that
+ * runs out of cluster slots stops with rows_prog status CC_ROWS_GROW (see
+ * cc_state.rows_prog); callers whose Kcap is below R + 1 check it after the call. */
 int cc_transition_rows(const cc_state* st, int n_work, const cc_row_work* work /*host*/,
                        const int32_t* perm, const double* u, double* trace,
                        int trace_stride, uint64_t seed, uint64_t counter,

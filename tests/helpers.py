@@ -88,8 +88,19 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
 def load_golden(name):
+    if name.endswith('.gz'):
+        import gzip
+        with gzip.open(os.path.join(GOLDEN, name), 'rt') as f:
+            return json.load(f)
     with open(os.path.join(GOLDEN, name)) as f:
         return json.load(f)
+
+
+def snapshot_digest(snap):
+    """sha256 of the canonical snapshot (tests/golden/make_golden_c1.py: digest)."""
+    import hashlib
+    body = {k: snap[k] for k in ('Zv', 'Zrv', 'row_order', 'alpha', 'view_alphas', 'hypers', 'suffstats')}
+    return hashlib.sha256(json.dumps(body, sort_keys=True).encode()).hexdigest()
 
 
 def golden_table(g):

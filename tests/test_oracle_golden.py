@@ -34,6 +34,27 @@ def test_oracle_reproduces_reference_trajectory_bit_for_bit(fixture):
         assert o.rng.random_sample() == g['stream_check'][s]
 
 
+def test_oracle_reproduces_reference_c1_trajectory():
+    """BASELINE.json configs[0] (1 000 x 10 mixed, 4 chains, reference-faithful CRP-prior initialisation with
+    up to ~500 clusters per view, kernels rows/columns/view_alphas/alpha/column_hypers): the first iterations of
+    the trajectory generated from the reference (tests/golden/make_golden_c1.py), bit for bit.  The GPU test
+    (test_gpu_golden.py) follows all of them."""
+    from helpers import snapshot_digest
+    g = load_golden('trajectory_c1_1000x10.json.gz')
+    X, cct, da = golden_table(g)
+    seeds = np.random.RandomState(g['engine_seed']).randint(low=1, high=2 ** 32 - 1, size=g['num_states'])
+    chains = (0, 3)                  # the cheapest and the largest initial state (K up to 504); all four on the GPU
+    states = {s: co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seeds[s])) for s in chains}
+    for s, o in states.items():
+        assert_snapshot_equal(snapshot_oracle(o), g['full']['init'][s], ('init', s))
+    for it in range(2):
+        for s, o in states.items():
+            o.transition(N=1, kernels=g['kernels'])
+            assert snapshot_digest(snapshot_oracle(o)) == g['digests'][it][s], (it, s)
+            if it == 0:
+                assert_snapshot_equal(snapshot_oracle(o), g['full']['0'][s], (it, s))
+
+
 def test_primitive_known_answers():
     k = load_golden('primitive_kats.json')
     for args, ref in k['normal_predictive']:
