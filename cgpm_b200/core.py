@@ -117,7 +117,14 @@ class Chains(object):
         self.stream = stream
         self.col_index = {c: i for i, c in enumerate(self.outputs)}
         if Vcap is None:
-            Vcap = min(Cn, 32) if R * min(Cn, 32) <= (1 << 24) else min(Cn, 16)
+            # a chain can hold up to C views (state.py:1125-1154); give every chain C view slots when the per-slot
+            # arrays (17 bytes per row) stay within a quarter of the device memory, otherwise what fits (>= 16)
+            per_slot = S * (17 * R + 64)
+            try:
+                free, _total = torch.cuda.mem_get_info(device) if device is not None else torch.cuda.mem_get_info()
+            except Exception:
+                free = 16 << 30
+            Vcap = int(min(Cn, max(16, (free // 4) // max(per_slot, 1))))
         # lognormal columns: log x on the device (math.log, as the reference computes it: lognormal.py:60-63)
         self.lognormal = np.array([c == 'lognormal' for c in cctypes], dtype=bool)
         self.X_raw = X
@@ -145,6 +152,7 @@ class Chains(object):
         self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         self.counter = 1
         self._aux_pre = None          # auxiliary views launched beside a rows sweep (see _prelaunch_aux)
+        self._defer_rows = False
         self._aux_stream = None
         self._ci_dev = None
         self._mirror = None
@@ -187,14 +195,22 @@ class Chains(object):
         if alpha is None:
             alpha = rng.choice(dev.col_alpha_grid_h)
         if Zv is None:
-            if self.Ci or self.Cd:
-                raise ValueError('cgpm_b200: supply Zv when using Cd/Ci constraints.')
-            zv_ids = sim(Cn, alpha, rng)
+            if self.Ci or self.Cd:                                # state.py:96-113
+                if self.outputs != list(range(Cn)):
+                    raise ValueError('Use zero-based outputs with constraints.')
+                if self.Ci:
+                    zv_ids = hm.simulate_crp_constrained(Cn, alpha, self.Cd, self.Ci, rng)
+                else:
+                    zv_ids = hm.simulate_crp_constrained_dependent(Cn, alpha, self.Cd, rng)
+            else:
+                zv_ids = sim(Cn, alpha, rng)
             Zv_od = OrderedDict((c, int(z)) for c, z in zip(self.outputs, zv_ids))
         else:
             Zv_od = OrderedDict((c, int(z)) for c, z in dict(Zv).items())
             if set(Zv_od.keys()) != set(self.outputs):
                 raise ValueError('Zv must assign every output.')
+            if (self.Cd or self.Ci) and not hm.validate_crp_constrained_partition(Zv_od, self.Cd, self.Ci):
+                raise ValueError('Zv violates the dependence / independence constraints.')
         view_alphas = dict(view_alphas) if view_alphas else {}
         Zrv = dict(Zrv) if Zrv else {}
         if Zrv and set(Zrv.keys()) != set(Zv_od.values()):
@@ -300,6 +316,8 @@ class Chains(object):
         iters, start = 0, time.time()
 
         def done():
+            if S is not None:
+                self.dev.sync()         # launches are asynchronous: the time budget is checked against finished work
             p_sec = 0 if S is None else (time.time() - start) / S
             p_it = 0 if N is None else float(iters) / N
             return max(p_it, p_sec)
@@ -489,7 +507,7 @@ class Chains(object):
         if trace is not None:
             tr = torch.zeros(max(len(work) * n * trace['stride'], 1), dtype=torch.float64, device=dev.device)
         dev.transition_rows(work, perm=perm, u=u, trace=tr, trace_stride=trace['stride'] if trace else 0,
-                            seed=self.seed, counter=self._next_counter())
+                            seed=self.seed, counter=self._next_counter(), defer=self._defer_rows and trace is None)
         if trace is not None:
             dev.sync()
             trace['work'] = work
@@ -530,10 +548,17 @@ class Chains(object):
 
     def _rows_then_aux(self, rows_func, chains, cols):
         def run():
+            if self.check_env_debug():
+                return rows_func()
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.dev.device))
-            rows_func()
-            self._prelaunch_aux(chains, cols, ev)
+            self._defer_rows = True            # the capacity check of the sweep (a host read) waits until the
+            try:                               # auxiliary views are enqueued beside it
+                rows_func()
+                self._prelaunch_aux(chains, cols, ev)
+            finally:
+                self._defer_rows = False
+                self.dev.finish_rows()
         return run
 
     def _column_order(self, chains, cidx, counter):
@@ -574,6 +599,10 @@ class Chains(object):
             self._aux_stream = torch.cuda.Stream(device=dev.device)
         side = self._aux_stream
         side.wait_event(ev_before_rows)
+        # allocated on the main stream, used on the side stream: tell the caching allocator
+        dev.arena.record_stream(side)
+        if dev.aux_zr_all is not None:
+            dev.aux_zr_all.record_stream(side)
         with torch.cuda.stream(side):
             self._launch_aux(np.ascontiguousarray(chains, dtype=np.int32), perm, counter, stored, dev.stream_ptr())
             done = torch.cuda.Event()
@@ -608,6 +637,8 @@ class Chains(object):
         tr_d = torch.zeros(max(nch * ncols * ts, 1), dtype=torch.float64, device=dev.device) if trace is not None else None
         self._mirror = None
         if self.stream == 'philox':
+            if pre is not None:
+                pre['done'].synchronize()      # the prelaunched pass may still be using the arena: never re-size under it
             self._ensure_arena(nch * ncols)
             stored = self._ensure_aux_store()
             cols_d = torch.from_numpy(perm).to(dev.device)
@@ -725,8 +756,22 @@ class Chains(object):
 
     # ------------------------------------------------------------------ queries
     def logpdf_score(self):
-        out = self.dev.logpdf_score()
-        return out.cpu().numpy() + self._ln_const
+        """State.logpdf_score (state.py:370-387).  With dependence constraints the column-CRP term is the
+        constrained one (gu.logp_crp_constrained_dependent); with independence constraints the reference refuses."""
+        if self.Ci:
+            raise ValueError('Cannot compute crp score with independences.')
+        out = self.dev.logpdf_score().cpu().numpy() + self._ln_const
+        if self.Cd:
+            m = self.mirror()
+            alphas = self.dev.t['col_alpha'].cpu().numpy()
+            for s in range(self.S):
+                nvs = [int(x) for x in m['nv'][s] if x > 0]
+                if not nvs:
+                    continue
+                Z = {c: int(m['zv'][s][i]) for i, c in enumerate(self.outputs)}
+                out[s] += hm.logp_crp_constrained_dependent(Z, float(alphas[s]), self.Cd) \
+                    - hm.logp_crp(self.C, nvs, float(alphas[s]))
+        return out
 
     def Zv_items(self, s):
         m = self.mirror()

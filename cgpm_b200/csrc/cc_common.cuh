@@ -131,6 +131,14 @@ __device__ __forceinline__ double normal_G(double N, double r, double nu) {
                         ih2 * (-31.0 / 18432.0 + ih2 * (691.0 / 180224.0))))));
     return 0.5 * cc_log_pos(den * __drcp_rn(num)) + poly - 0.5 * CC_LOGPI;
 }
+// G one count up or down by the recurrence lgamma(h + 1) - lgamma(h + 1/2) = log h - (lgamma(h + 1/2) - lgamma(h)):
+//   G(N + 1) = -G(N) + 1/2 log(h^2 rn / (rn + 2)) - log(pi),   h = (nu + N) / 2, rn = r + N
+// (one log instead of the series; read downwards it gives G(N - 1) from G(N)).  Used when a row moves; the
+// rebuilds recompute G from the series, so rounding does not accumulate beyond the moves of one run of sweeps.
+__device__ __forceinline__ double normal_G_step(double G_other, double N_lower, double r, double nu) {
+    const double h = 0.5 * (nu + N_lower), rn = r + N_lower;
+    return 0.5 * cc_log_pos(h * h * rn * __drcp_rn(rn + 2.0)) - CC_LOGPI - G_other;
+}
 struct NormalCache { double mn, a, cst; };
 __device__ __forceinline__ NormalCache normal_cache(double N, double sx, double sxx, double gN, double m,
                                                     double r, double s, double nu) {

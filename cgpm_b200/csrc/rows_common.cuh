@@ -11,12 +11,32 @@ struct RowsParams {
     double* trace;
     int trace_stride;
     uint64_t seed, counter;
-    int B;          // rows per staged batch (power of two, <= 32)
-    int bulk;       // 1: stage whole rows with cp.async.bulk
+    int B, NBUF;    // (unused: every CTA sizes its own staging ring, see rows_stage)
+    int bulk;       // 1: bulk row copies allowed (cp.async.bulk; each CTA decides from its view's width)
     int smem_bytes; // dynamic shared memory given to the CTA
     int wide;       // 1: very wide views -- per-column hypers / types stay in global memory, tables too
-    int prof;       // debug: per-CTA cycles / D / K / moves into st.seq[(chain, view)][0..3]
+    int prof;       // debug: per-CTA cycles / D / K / moves into st.seq[(chain, view)][0..4]
+    int Ksm;        // capacity of the candidate arrays (live, nk, lp, w) in shared memory; the large-K kernel
+                    // keeps them in global memory instead
+    int DL;         // views wider than this are swept one row at a time by the whole CTA
+    int lvl0;       // debug: fixed speculation level (-1: adaptive)
+    double* big_lp; // large-K kernel: [n_work][2][Kcap + 1] candidate scores / weights
 };
+
+// How one view's rows are staged: whole rows by bulk copies when the row is short and the view holds at least a
+// quarter of it, per-cell gathers otherwise; NBUF batches of B rows within about 32 KB (at least two batches of
+// one row).  Host (launch sizing) and device (per CTA) use the same rule.
+struct RowsStage { int bulk, stagebytes, B, NBUF; };
+__host__ __device__ inline RowsStage rows_stage(int Cp, int C, int D, int allow_bulk) {
+    RowsStage r;
+    const int rowbytes = Cp * 8;
+    r.bulk = (allow_bulk && rowbytes <= 4096 && 4 * D >= C) ? 1 : 0;
+    r.stagebytes = r.bulk ? rowbytes : ((D + 1) & ~1) * 8;
+    r.B = 32; r.NBUF = 4;
+    while (r.B > 1 && r.NBUF * r.B * r.stagebytes > 32 * 1024) r.B >>= 1;
+    while (r.NBUF > 2 && r.NBUF * r.B * r.stagebytes > 48 * 1024) r.NBUF >>= 1;
+    return r;
+}
 
 namespace {
 
@@ -59,20 +79,21 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
 // Everything a sweep needs, resolved once per CTA.
 struct Ctx {
     cc_state st;
-    int s, v, n, D, K0, Kc, CTv, B, bulk, xstride, wide, allnorm;
+    int s, v, n, D, K0, Kc, CTv, B, lgB, NBUF, RB, bulk, xstride, wide, allnorm, Ksm, DL, base, lvl0;
     size_t sv;
     // shared memory
-    uint64_t *bar_full, *bar_empty;
-    int *scal;              // [32]: 0 K, 2 free head, 3 nmoved, 5 start in global, 6 CTv, 7 error, 11 all-normal view;
-                            // sequential sweep: 4 own position, 8 choice, 9 destination slot, 10 new-cluster flag;
-                            // two rows in flight: 16 + 8 * (row parity) + {0 own position, 1 drift flag, 2 choice,
+    uint64_t *bar_full, *bar_empty;   // [8] each
+    int *scal;              // [64]: 0 K, 2 free head, 3 nmoved, 5 start in global, 6 CTv, 7 error, 11 all-normal view,
+                            // 40 scratch of the parallel searches, 42 batches released, 43 stop flag for the producer;
+                            // one row at a time: 16 + 8 * (row parity) + {0 own position, 1 drift flag, 2 choice,
                             // 3 destination slot, 4 new-cluster flag}
-    int *live, *nk;
-    double* lp;             // [Kcap+1] candidate scores ([2][Kcap+1] by row parity with two rows in flight)
+    int *pub;               // [2][16][8] by round parity and warp: first flagged row of the warp (speculative rounds)
+    int *live, *nk;         // [Ksm] (shared) or [Kcap] (global, large-K kernel)
+    double* lp;             // [Ksm+1] / [Kcap+1] candidate scores (one row at a time)
     double* w;              // same shape: CRP weight of each candidate (written with lp)
     int *col, *cto, *ctype, *ncat;
     double* hyp;            // [4][D]
-    int *rowidx, *zrow;
+    int *rowidx, *zrow;     // [RB]
     double *u, *x, *tab;
     // global
     int32_t *zr, *moved, *g_cid;

@@ -24,9 +24,11 @@ namespace {
 // each counts its chunk per cluster, the counts are scanned over (cluster, warp) on top of the
 // clusters' start offsets, and each warp scatters its chunk from its own cursors -- so rows of
 // a cluster keep their relative order within and across chunks.  grouped = st.moved (scratch);
-// the start offsets go to `gstart` [n_work][Kcap+1].  Shared memory: NW * Kcap ints.
+// the start offsets go to `gstart` [n_work][Kcap+1].  Shared memory: NW * Kcap ints; when even one
+// warp's counters do not fit (Kcap beyond ~24 000: the reference-faithful initialisation of a large
+// table) the launch has one warp per CTA and the counters live in `gcnt` [n_work][Kcap] instead.
 __global__ void group_kernel(const cc_state st, int n_work, const int32_t* __restrict__ chains,
-                             const int32_t* __restrict__ views, int32_t* __restrict__ gstart) {
+                             const int32_t* __restrict__ views, int32_t* __restrict__ gstart, int32_t* gcnt) {
     const int w = blockIdx.x;
     if (w >= n_work) return;
     const int s = chains[w], v = views[w];
@@ -38,7 +40,8 @@ __global__ void group_kernel(const cc_state st, int n_work, const int32_t* __res
     const int32_t* nk = st.nk + sv * Kcap;
     int32_t* grouped = st.moved + sv * R;
     int32_t* start = gstart + (size_t)w * (Kcap + 1);
-    extern __shared__ int s_cnt[];                     // [NW][Kcap] chunk counts, then cursors
+    extern __shared__ int s_cnt_sh[];                  // [NW][Kcap] chunk counts, then cursors
+    int* s_cnt = gcnt ? gcnt + (size_t)w * Kcap : s_cnt_sh;
     int* mine = s_cnt + warp * Kcap;
     for (int k = lane; k < Kcap; k += 32) mine[k] = 0;
     // start offsets: exclusive scan of nk over slots (warp 0, serial chunks of 32)
@@ -408,10 +411,11 @@ __global__ void refresh_kernel(const cc_state st, int n_work, const int32_t* __r
 // Device form of the reference's debug invariants (View._check_partitions / State._check_partitions,
 // src/mixtures/view.py:528-560, src/crosscat/state.py:1162-1184; enabled there by GPMCCDEBUG).
 // One CTA per chain; out[s] = 0 or the code of the first violated invariant.
-__global__ void __launch_bounds__(256) check_kernel(const cc_state st, int32_t* __restrict__ out) {
+__global__ void __launch_bounds__(256) check_kernel(const cc_state st, int32_t* __restrict__ out, int32_t* gscr) {
     const int s = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     const int R = st.R, C = st.C, Vcap = st.Vcap, Kcap = st.Kcap;
-    extern __shared__ int s_hist[];                 // [Kcap] + [Kcap]
+    extern __shared__ int s_hist_sh[];              // [Kcap] + [Kcap] (in `gscr` [S][2 Kcap] when too large for shared memory)
+    int* s_hist = gscr ? gscr + (size_t)s * 2 * Kcap : s_hist_sh;
     int* s_mark = s_hist + Kcap;
     __shared__ int s_bad, s_sum;
     if (tid == 0) { s_bad = 0; s_sum = 0; }
@@ -519,11 +523,21 @@ int cc_launch_stats(const cc_state* st, int n_work, const int32_t* d_chains, con
     if (n_work == 0) return CC_OK;
     int32_t* gstart = nullptr;
     CC_CUDA(cudaMallocAsync(&gstart, sizeof(int32_t) * (size_t)n_work * (st->Kcap + 1), stream));
-    // as many warps per (chain, view) as 48 KB of per-warp cluster counters allow (8 at Kcap <= 1536)
-    int gw = (48 * 1024) / ((int)sizeof(int) * st->Kcap);
-    gw = gw > 8 ? 8 : (gw < 1 ? 1 : gw);
-    group_kernel<<<n_work, 32 * gw, sizeof(int) * st->Kcap * gw, stream>>>(*st, n_work, d_chains, d_views, gstart);
+    // as many warps per (chain, view) as 96 KB of per-warp cluster counters allow (8 at Kcap <= 3072)
+    const int gmax = 96 * 1024;
+    int gw = gmax / ((int)sizeof(int) * st->Kcap);
+    int32_t* gcnt = nullptr;
+    if (gw < 1) {
+        CC_CUDA(cudaMallocAsync(&gcnt, sizeof(int32_t) * (size_t)n_work * st->Kcap, stream));
+        group_kernel<<<n_work, 32, 0, stream>>>(*st, n_work, d_chains, d_views, gstart, gcnt);
+    } else {
+        gw = gw > 8 ? 8 : gw;
+        const size_t gbytes = sizeof(int) * (size_t)st->Kcap * gw;
+        if (gbytes > 48 * 1024) CC_CUDA(cudaFuncSetAttribute(group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gmax));
+        group_kernel<<<n_work, 32 * gw, gbytes, stream>>>(*st, n_work, d_chains, d_views, gstart, nullptr);
+    }
     CC_CUDA(cudaGetLastError());
+    if (gcnt) CC_CUDA(cudaFreeAsync(gcnt, stream));
     StatsParams p;
     p.st = *st; p.n_work = n_work; p.chains = d_chains; p.views = d_views; p.gstart = gstart;
     p.marginal = marginal; p.cols = d_cols; p.coloff = d_coloff; p.colcnt = d_colcnt; p.mask = d_mask;
@@ -587,8 +601,18 @@ extern "C" int cc_refresh_tables(const cc_state* st, int n_work, const int32_t* 
 extern "C" int cc_check_state(const cc_state* st, int32_t* out_dev, void* stream_) {
     if (!st || !out_dev) { cc_set_error("cc_check_state: null argument"); return CC_ERR_ARG; }
     if (st->S == 0) return CC_OK;
-    check_kernel<<<st->S, 256, sizeof(int) * 2 * st->Kcap, (cudaStream_t)stream_>>>(*st, out_dev);
-    CC_CUDA(cudaGetLastError());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const size_t bytes = sizeof(int) * 2 * (size_t)st->Kcap;
+    if (bytes > 40 * 1024) {
+        int32_t* gscr = nullptr;
+        CC_CUDA(cudaMallocAsync(&gscr, bytes * st->S, stream));
+        check_kernel<<<st->S, 256, 0, stream>>>(*st, out_dev, gscr);
+        CC_CUDA(cudaGetLastError());
+        CC_CUDA(cudaFreeAsync(gscr, stream));
+    } else {
+        check_kernel<<<st->S, 256, bytes, stream>>>(*st, out_dev, nullptr);
+        CC_CUDA(cudaGetLastError());
+    }
     return CC_OK;
 }
 

@@ -99,9 +99,12 @@ class DeviceChains(object):
         self.R, self.C, self.S = R, Cn, int(S)
         self.Cp = (Cn + 1) & ~1
         self.Vcap = int(Vcap) if Vcap else int(min(Cn, 16))
+        # cluster slots per view: one more than the clusters a view can hold (the last slot keeps the empty-cluster
+        # record).  R + 1 always suffices; smaller values grow on demand (grow_kcap), so this is only a first guess.
         self.Kcap = int(Kcap) if Kcap else int(min(max(R + 1, 4), 1024))
-        if not 4 <= self.Kcap <= 4096:
-            raise ValueError('Kcap must be in [4, 4096]')
+        if self.Kcap < 4:
+            raise ValueError('Kcap must be at least 4')
+        self.Kcap = min(self.Kcap, max(R + 1, 4))
         self.ctype_h, self.ncat_h = ctype, ncat
         catoff = np.zeros(Cn, dtype=np.int32)
         catoff[1:] = np.cumsum(ncat)[:-1]
@@ -145,6 +148,7 @@ class DeviceChains(object):
         t['stat'] = z((S_, L.NFIELD, K, Cn), f64)
         t['cnt'] = z((S_, K, self.CT), f64)
         t['err'] = z((S_,), i32)
+        t['rows_prog'] = z((S_, V, 4), i32)
         t['seq'] = z((S_, V, R), i32)
         t['moved'] = z((S_, V, R), i32)
         t['movedflag'] = z((S_, V, R), torch.uint8)
@@ -160,7 +164,7 @@ class DeviceChains(object):
         st.Vcap, st.Kcap, st.CT = V, K, self.CT
         for name in ('Xrm', 'Xcm', 'ctype', 'ncat', 'catoff', 'grids', 'row_alpha_grid',
                      'col_alpha_grid', 'hyp', 'zv', 'nv', 'view_id', 'col_alpha', 'view_alpha', 'view_grid',
-                     'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'seq',
+                     'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'rows_prog', 'seq',
                      'moved', 'movedflag', 'colL', 'aux_zr', 'aux_K', 'aux_alpha', 'aux_K_all'):
             setattr(st, name, t[name].data_ptr())
         st.arena = None
@@ -170,6 +174,8 @@ class DeviceChains(object):
         self.st = st
         self.lib_calls = collections.Counter()
         self.lib = _CountingLib(L.load(), self.lib_calls)
+        self._rows_pending = None
+        self.kcap_grown = 0
 
     # ------------------------------------------------------------------ helpers
     def stream_ptr(self):
@@ -199,6 +205,10 @@ class DeviceChains(object):
         nviews = len(ch['view_slots'])
         if nviews > V:
             raise L.CgpmB200Error('chain needs %d views > Vcap=%d' % (nviews, V))
+        kmax = max([len(c_) for c_ in ch['cid']] or [0])
+        if kmax > K - 1:
+            self.grow_kcap(kmax + 1 + max(16, kmax // 8))
+            K = self.Kcap
         t['hyp'][s].copy_(torch.from_numpy(ch['hyp']))
         t['zv'][s].copy_(torch.from_numpy(ch['zv']))
         nv = np.zeros(V, np.int32); view_id = np.full(V, -1, np.int32)
@@ -275,11 +285,25 @@ class DeviceChains(object):
                 'cc_logpdf_score')
         return out
 
-    def transition_rows(self, work, perm=None, u=None, trace=None, trace_stride=0, seed=0, counter=0):
-        """work: list of dicts(chain, view, n, perm_is_index, perm_off, u_off, trace_off)."""
+    def transition_rows(self, work, perm=None, u=None, trace=None, trace_stride=0, seed=0, counter=0, defer=False):
+        """work: list of dicts(chain, view, n, perm_is_index, perm_off, u_off, trace_off).
+        A sweep that runs out of cluster slots stops in front of the move that needs one (rows_prog status
+        CC_ROWS_GROW); finish_rows() then grows Kcap and resumes it with the same row -- nothing is lost.  With
+        defer=True the caller promises to call finish_rows() itself (after enqueueing work of its own that should
+        run beside the sweep); otherwise it is called here."""
         n = len(work)
         if n == 0:
             return
+        self._rows_pending = dict(work=work, perm=perm, u=u, trace=trace, trace_stride=int(trace_stride), seed=seed,
+                                  counter=counter)
+        self._launch_rows(resume=0)
+        if not defer:
+            self.finish_rows()
+
+    def _launch_rows(self, resume):
+        pd = self._rows_pending
+        work = pd['work']
+        n = len(work)
         arr = (L.cc_row_work * n)()
         for i, w in enumerate(work):
             arr[i].chain = w['chain']; arr[i].view = w['view']; arr[i].n = w['n']
@@ -289,10 +313,58 @@ class DeviceChains(object):
             arr[i].trace_off = w.get('trace_off', -1)
             arr[i].n_cols = w.get('n_cols', 0)
             arr[i].n_normal = w.get('n_normal', 0)
+            arr[i].resume = resume
+        perm, u, trace = pd['perm'], pd['u'], pd['trace']
         rc = self.lib.cc_transition_rows(
             C.byref(self.st), n, arr,
             C.c_void_p(perm.data_ptr()) if perm is not None else None,
             C.c_void_p(u.data_ptr()) if u is not None else None,
             C.c_void_p(trace.data_ptr()) if trace is not None else None,
-            int(trace_stride), C.c_uint64(seed), C.c_uint64(counter), self.stream_ptr())
+            pd['trace_stride'], C.c_uint64(pd['seed']), C.c_uint64(pd['counter']), self.stream_ptr())
         L.check(rc, 'cc_transition_rows')
+
+    def finish_rows(self):
+        """Complete the rows sweep launched last: while some view stopped for lack of cluster slots, grow Kcap and
+        resume.  Needs one small device-to-host read per sweep whenever Kcap < R + 1."""
+        if self._rows_pending is None:
+            return
+        try:
+            while self.Kcap < self.R + 1:
+                prog = self.t['rows_prog'].cpu().numpy()                      # synchronises the stream
+                worst = max(int(prog[w['chain'], w['view'], 2]) for w in self._rows_pending['work'])
+                if worst != L.ROWS_GROW:
+                    if worst != L.ROWS_DONE:
+                        raise L.CgpmB200Error('rows sweep left in state %d' % worst)
+                    break
+                self.grow_kcap(2 * self.Kcap)
+                self._launch_rows(resume=1)
+        finally:
+            self._rows_pending = None
+
+    # ------------------------------------------------------------------ capacity
+    def grow_kcap(self, want):
+        """Re-allocate the per-cluster arrays with at least `want` cluster slots per view (at most R + 1, which
+        always suffices).  Slots keep their numbers; the empty-cluster record moves to the new last slot."""
+        new = int(min(max(want, self.Kcap + 1), self.R + 1))
+        old = self.Kcap
+        if new <= old:
+            return
+        t, dev = self.t, self.device
+        S_, V, Cn = self.S, self.Vcap, self.C
+        for name, fill in (('live', -1), ('cid', 0), ('nk', 0)):
+            a = torch.full((S_, V, new), fill, dtype=torch.int32, device=dev)
+            a[:, :, :old - 1] = t[name][:, :, :old - 1]
+            t[name] = a
+        stat = torch.zeros((S_, L.NFIELD, new, Cn), dtype=torch.float64, device=dev)
+        stat[:, :, :old - 1] = t['stat'][:, :, :old - 1]
+        stat[:, :, new - 1] = t['stat'][:, :, old - 1]
+        t['stat'] = stat
+        cnt = torch.zeros((S_, new, self.CT), dtype=torch.float64, device=dev)
+        cnt[:, :old - 1] = t['cnt'][:, :old - 1]
+        cnt[:, new - 1] = t['cnt'][:, old - 1]
+        t['cnt'] = cnt
+        self.Kcap = new
+        self.st.Kcap = new
+        for name in ('live', 'cid', 'nk', 'stat', 'cnt'):
+            setattr(self.st, name, t[name].data_ptr())
+        self.kcap_grown += 1

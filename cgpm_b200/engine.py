@@ -482,8 +482,14 @@ class Engine(_Api):
 
     def _make_chains(self, S, seed):
         kw = self._state_kwargs
+        old = getattr(self, '_ch', None)
         self._ch = Chains(self.X, outputs=kw.get('outputs'), cctypes=kw.get('cctypes'), distargs=kw.get('distargs'),
                           Cd=kw.get('Cd'), Ci=kw.get('Ci'), S=S, seed=int(seed), **self._opts)
+        if old is not None:
+            # re-created chains (drop_state / add_state) continue the call counter of the device generator: its keys are
+            # (seed, counter, purpose, chain, ...), so no key a chain -- or the chain that inherits its index -- has
+            # consumed is ever drawn again
+            self._ch.counter = old.counter
 
     def _init_from_kwargs(self, s, rng, kw):
         self._ch.init_chain(s, rng, Zv=kw.get('Zv'), Zrv=kw.get('Zrv'), alpha=kw.get('alpha'),

@@ -89,3 +89,144 @@ def crp_simulate_fast(n, alpha, rng):
     # roots are first members, so sorted roots are already in order of appearance
     _, inv = np.unique(parent, return_inverse=True)
     return inv.astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------
+# Column-CRP dependence / independence constraints (State(Cd=..., Ci=...), src/crosscat/state.py:96-113,370-379).
+def pflip(p, rng):
+    """src/utils/general.py:127-139 with array = range(len(p)): no draw for a single candidate."""
+    if len(p) == 1:
+        return 0
+    p = np.asarray(p, dtype=float) / sum(p)
+    return int(rng.choice(list(range(len(p))), p=p))
+
+
+def validate_dependency_constraints(N, Cd, Ci):
+    """src/utils/validation.py:34-66."""
+    counts = {}
+    for block in Cd:
+        if len(block) == 1:
+            raise ValueError('Single customer in dependency constraint.')
+        for col in block:
+            if N is not None and N <= col:
+                raise ValueError('Dependence customer out of range.')
+            counts[col] = counts.get(col, 0) + 1
+            if counts[col] > 1:
+                raise ValueError('Multiple customer dependencies.')
+        for pair in Ci:
+            if pair[0] in block and pair[1] in block:
+                raise ValueError('Contradictory customer independence.')
+    for pair in Ci:
+        if len(pair) != 2:
+            raise ValueError('Independencies require two customers.')
+        if N is not None and (N <= pair[0] or N <= pair[1]):
+            raise ValueError('Independence customer of out range.')
+        if pair[0] == pair[1]:
+            raise ValueError('Independency specified for same customer.')
+    return True
+
+
+def _compatible(Ci, a, b):
+    """src/utils/validation.py:80-89 without row constraints (Rd / Ri are refused by State)."""
+    return not ((a, b) in Ci or (b, a) in Ci)
+
+
+def validate_crp_constrained_partition(Zv, Cd, Ci):
+    """src/utils/validation.py:22-32: Zv maps customer -> table."""
+    import itertools
+    Ci = [tuple(p) for p in Ci]
+    valid = True
+    for block in Cd:
+        valid = valid and all(Zv[block[0]] == Zv[b] for b in block)
+        for a, b in itertools.combinations(block, 2):
+            valid = valid and _compatible(Ci, a, b)
+    for a, b in Ci:
+        valid = valid and not Zv[a] == Zv[b]
+    return valid
+
+
+def simulate_crp(N, alpha, rng):
+    """src/utils/general.py:207-246 (note its normaliser i - 1 + alpha; pflip renormalises)."""
+    alpha = float(alpha)
+    partition = [0] * N
+    Nk = [1]
+    for i in range(1, N):
+        K = len(Nk)
+        ps = np.zeros(K + 1)
+        for k in range(K):
+            ps[k] = float(Nk[k])
+        ps[K] = alpha
+        ps /= (float(i) - 1 + alpha)
+        a = pflip(ps, rng)
+        if a == K:
+            Nk.append(1)
+        else:
+            Nk[a] += 1
+        partition[i] = a
+    return partition
+
+
+def simulate_crp_constrained(N, alpha, Cd, Ci, rng):
+    """src/utils/general.py:248-291: friends are seated together, enemies never share a table."""
+    validate_dependency_constraints(N, Cd, Ci)
+    Ci = [tuple(p) for p in Ci]
+    Z = [-1] * N
+    friends = {col: block for block in Cd for col in block}
+    for cust in range(N):
+        if Z[cust] > -1:
+            continue
+        prob_table = [0] * (max(Z) + 1)
+        for t in range(max(Z) + 1):
+            t_custs = [i for i, z in enumerate(Z) if z == t]
+            prob_table[t] = len(t_custs)
+            for tc in t_custs:
+                for f in friends.get(cust, [cust]):
+                    if not _compatible(Ci, f, tc):
+                        prob_table[t] = 0
+                        break
+        prob_table.append(alpha)
+        a = pflip(prob_table, rng)
+        for f in friends.get(cust, [cust]):
+            Z[f] = a
+    assert validate_crp_constrained_partition(Z, Cd, Ci)
+    return Z
+
+
+def crp_constrained_num_effective(N, Cd):
+    """src/utils/general.py:358-370."""
+    return (N - sum(len(block) for block in Cd)) + len(Cd)
+
+
+def simulate_crp_constrained_dependent(N, alpha, Cd, rng):
+    """src/utils/general.py:293-332: every clique of friends is one customer of a plain CRP."""
+    validate_dependency_constraints(N, Cd, [])
+    crp_block = simulate_crp(crp_constrained_num_effective(N, Cd), alpha, rng)
+    partition = [-1] * N
+    for i, block in enumerate(Cd):
+        for customer in block:
+            partition[customer] = crp_block[i]
+    unused = iter(crp_block[len(Cd):])
+    for customer, a in enumerate(partition):
+        if a == -1:
+            partition[customer] = next(unused)
+    return partition
+
+
+def logp_crp(N, Nk, alpha):
+    """src/utils/general.py:88-94."""
+    return len(Nk) * math.log(alpha) + sum(math.lgamma(c) for c in Nk) + math.lgamma(alpha) - math.lgamma(N + alpha)
+
+
+def logp_crp_constrained_dependent(Z, alpha, Cd):
+    """src/utils/general.py:335-355: Z maps customer -> table."""
+    if not validate_crp_constrained_partition(Z, Cd, []):
+        return -float('inf')
+    counts = {}
+    seen = set()
+    for block in Cd:
+        seen.update(block)
+        counts[Z[block[0]]] = counts.get(Z[block[0]], 0) + 1
+    for customer in Z:
+        if customer not in seen:
+            counts[Z[customer]] = counts.get(Z[customer], 0) + 1
+    return logp_crp(crp_constrained_num_effective(len(Z), Cd), list(counts.values()), alpha)

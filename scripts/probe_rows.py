@@ -45,11 +45,15 @@ import os
 if os.environ.get('CGPM_B200_ROWS_PROF'):
     seq = dev.t['seq'].cpu().numpy()
     rec = sorted([(int(seq[w['chain'], w['view'], 0]), int(seq[w['chain'], w['view'], 1]), int(seq[w['chain'], w['view'], 2]), int(seq[w['chain'], w['view'], 3])) for w in work])
+    print('final levels', collections.Counter(int(seq[w['chain'], w['view'], 5]) for w in work) if False else sorted(set(int(seq[w['chain'], w['view'], 5]) for w in work)))
     print('per-CTA (kcycles, D, K, moves): slowest', rec[-8:])
     print('median', rec[len(rec)//2], 'fastest', rec[:3])
     import collections
     byD = collections.defaultdict(list)
-    for kc, D, K, mv in rec: byD[D // 8 * 8].append(kc)
+    for kc, D, K, mv in rec: byD[D if D < 4 else D // 8 * 8 + 4].append(kc)
+    mvD = collections.defaultdict(list)
+    for kc, D, K, mv in rec: mvD[D if D < 4 else D // 8 * 8 + 4].append(mv / R)
+    print('move rate by width', {d: round(float(np.mean(v)), 4) for d, v in sorted(mvD.items())})
     print({d: (len(v), int(np.mean(v))) for d, v in sorted(byD.items())})
 dev.check_errors()
 print('score', dev.logpdf_score().cpu().numpy()[:3])

@@ -169,3 +169,11 @@ def snapshot_engine(eng, s):
 def assert_snapshot_equal(got, ref, tag=''):
     for key in ('Zv', 'Zrv', 'row_order', 'alpha', 'view_alphas', 'hypers', 'suffstats'):
         assert got[key] == ref[key], (tag, key, got[key], ref[key])
+
+
+def rel_tol(ref):
+    """north_star: conditional log-probabilities within 1e-5 RELATIVE of the reference's.  Purely relative down to
+    |ref| = 1e-5; below that the bound stays at 1e-10 absolute -- a conditional is a sum of O(1) fp64 terms, so
+    asking for better than 1e-10 absolute near a zero crossing would be asking for more than the reference's own
+    arithmetic carries."""
+    return 1e-5 * np.maximum(1e-5, np.abs(np.asarray(ref, dtype=float)))

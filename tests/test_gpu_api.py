@@ -93,3 +93,26 @@ def test_result_shapes_like_the_reference(table):
     st = eng.get_state(2)
     assert st.n_rows() == 50 and st.n_cols() == 6 and set(st.Zv().keys()) == set(range(6))
     assert abs(st.logpdf_score() - eng.logpdf_score()[2]) <= 1e-12 * abs(st.logpdf_score())
+
+
+def test_device_stream_keys_are_not_reused_after_add_and_drop_state():
+    """The Philox stream is keyed by (seed, call counter, purpose, chain, ...): chains re-created by drop_state /
+    add_state keep the engine's seed, so the counter must carry over (and keeps growing) or later sweeps would
+    replay uniforms already consumed."""
+    from cgpm_b200.engine import Engine, gen_rng
+    from helpers import small_table
+    X, cct, da = small_table(40, 3)
+    eng = Engine(X, num_states=3, rng=gen_rng(2), cctypes=cct, distargs=da, stream='philox')
+    eng.transition(N=2, progress=False)
+    c0, seed = eng._ch.counter, eng._ch.seed
+    assert c0 > 1
+    eng.drop_state(0)
+    assert eng._ch.seed == seed and eng._ch.counter == c0
+    eng.transition(N=1, progress=False)
+    c1 = eng._ch.counter
+    assert c1 > c0
+    eng.add_state(count=2)
+    assert eng._ch.seed == seed and eng._ch.counter == c1 and eng.num_states() == 4
+    eng.transition(N=1, progress=False)
+    assert eng._ch.counter > c1
+    assert all(np.isfinite(eng.logpdf_score()))

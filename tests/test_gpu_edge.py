@@ -23,10 +23,9 @@ def pair(X, cct, da, seed, S=2, **kw):
 def test_global_table_mode_and_mid_sweep_migration(monkeypatch):
     """The per-(cluster, column) tables live in shared memory when they fit.  With the
     shared tables capped (env override used only here), (1) a 60-column view with 30
-    clusters starts in global-table mode (two-rows-in-flight kernel, mode 5), (2) a 4-column
-    view that grows from 2 to many clusters migrates from shared to global memory mid-sweep
-    (sequential kernel, mode 2), (3) so does a 20-column view (two-rows-in-flight kernel,
-    mode 6).  All must follow the oracle exactly (partitions, bit-identical statistics)."""
+    clusters starts in global-table mode (mode 1), (2) a 4-column view that grows from 2 to
+    many clusters migrates from shared to global memory mid-sweep (mode 2), (3) so does a
+    20-column view.  All must follow the oracle exactly (partitions, bit-identical statistics)."""
     from cgpm_b200 import synth
     monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
     modes = set()
@@ -46,7 +45,54 @@ def test_global_table_mode_and_mid_sweep_migration(monkeypatch):
             compare(eng, oracles, (name, it))
             seq = eng._ch.dev.t['seq'].cpu().numpy()
             modes |= set(int(seq[s, 0, 4]) for s in range(2))
-    assert {5, 2, 6} <= modes, modes       # the global start and both mid-sweep migrations ran
+    assert {1, 2} <= modes, modes       # the global start and the mid-sweep migrations ran
+
+
+@pytest.mark.parametrize('case', ['handover_mid_sweep', 'handover_at_start', 'grow_kcap', 'grow_in_large_k_kernel'])
+def test_large_k_kernel_and_capacity_growth(case, monkeypatch):
+    """Sweeps that outgrow the shared-memory candidate arrays continue in the large-K kernel (everything per
+    cluster in global memory), and sweeps that run out of cluster slots altogether stop in front of the move,
+    the host grows Kcap and they resume with the same row: both hand-overs go through rows_prog and must leave
+    the trajectory of the strictly sequential scan untouched (oracle: partitions, member order, bit-identical
+    statistics, stream position)."""
+    from cgpm_b200 import synth
+    monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
+    C, R = 3, 120
+    cct = ['normal'] * C
+    X, _, _ = synth.gen_table(R, cct, [None] * C, n_views=1, clusters_per_view=3, seed=6)
+    Zv = {c: 0 for c in range(C)}
+    kw = {}
+    if case == 'handover_mid_sweep':           # 2 clusters -> dozens (alpha = 150), candidate arrays of 8 slots
+        monkeypatch.setenv('CGPM_B200_ROWS_KSM', '8')
+        Zr, alpha = np.arange(R) % 2, 150.0
+        kw['Kcap'] = 128
+    elif case == 'handover_at_start':          # 40 clusters from the start
+        monkeypatch.setenv('CGPM_B200_ROWS_KSM', '8')
+        Zr, alpha = np.arange(R) % 40, 3.0
+        kw['Kcap'] = 128
+    elif case == 'grow_kcap':                  # 4 slots per view to begin with
+        Zr, alpha = np.arange(R) % 2, 150.0
+        kw['Kcap'] = 4
+    else:                                      # growth requested by the large-K kernel
+        monkeypatch.setenv('CGPM_B200_ROWS_KSM', '6')
+        Zr, alpha = np.arange(R) % 3, 150.0
+        kw['Kcap'] = 12
+    eng, oracles = pair(X, cct, None, 3, S=2, Zv=Zv, Zrv={0: [int(z) for z in Zr]}, view_alphas={0: alpha}, alpha=1.0, **kw)
+    compare(eng, oracles, (case, 'init'))
+    modes = set()
+    for it in range(3):
+        eng.transition(N=1, kernels=['rows'], progress=False)
+        for o in oracles:
+            o.transition(N=1, kernels=['rows'])
+        compare(eng, oracles, (case, it))
+        seq = eng._ch.dev.t['seq'].cpu().numpy()
+        modes |= set(int(seq[s, 0, 4]) for s in range(2))
+    dev = eng._ch.dev
+    if case.startswith('handover') or case == 'grow_in_large_k_kernel':
+        assert 9 in modes, modes               # the large-K kernel finished at least one sweep
+    if case.startswith('grow'):
+        assert dev.kcap_grown > 0 and dev.Kcap > kw['Kcap']
+    eng._ch.check_partitions()
 
 
 def test_row_and_column_subsets_and_views_argument():
@@ -113,15 +159,18 @@ def test_nan_heavy_categorical_only_and_tiny_tables():
     compare(eng, oracles, 'nan column')
 
 
-def test_capacity_error_is_loud():
+def test_cluster_capacity_grows_on_the_device_stream():
+    """Kcap = 4 and a CRP that wants dozens of clusters: the engine grows the cluster slots instead of failing
+    (round 1 raised a capacity error here) and the partitions stay consistent."""
     from cgpm_b200 import synth
-    from cgpm_b200._lib import CgpmB200Error
     from cgpm_b200.engine import Engine, gen_rng
     X, _, _ = synth.gen_table(64, ['normal'] * 3, [None] * 3, n_views=1, clusters_per_view=2, seed=1)
-    eng = Engine(X, num_states=1, rng=gen_rng(1), cctypes=['normal'] * 3, stream='philox', Kcap=4,
+    eng = Engine(X, num_states=2, rng=gen_rng(1), cctypes=['normal'] * 3, stream='philox', Kcap=4,
                  Zv={0: 0, 1: 0, 2: 0}, Zrv={0: [0] * 64}, view_alphas={0: 50.0}, alpha=1.0)
-    with pytest.raises(CgpmB200Error):
-        eng.transition(N=3, kernels=['rows'], progress=False)
+    eng.transition(N=3, kernels=['rows'], progress=False)
+    dev = eng._ch.dev
+    assert dev.kcap_grown > 0 and dev.Kcap > 4
+    eng._ch.check_partitions()
 
 
 def test_very_wide_views_use_the_wide_mode():

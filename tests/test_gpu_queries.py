@@ -120,12 +120,13 @@ def test_metadata_round_trip_and_reference_schema():
     om = oracles[0].to_metadata()
     m0 = md['states'][0]
     assert sorted(m0['Zv']) == sorted(om['Zv']) and m0['Zrv'] == om['Zrv']
-    assert [sorted((k, repr(v)) for k, v in col) for col in []] == []
-    for a, b in zip(m0['suffstats'], om['suffstats']):
+    for a, b in zip(m0['suffstats'], om['suffstats']):            # full sufficient statistics, bit for bit
         da_, db_ = dict(a), dict(b)
         assert set(da_) == set(db_)
         for k in da_:
-            assert float(da_[k]['N']) == float(db_[k]['N'])
+            assert set(da_[k]) == set(db_[k]), (k, da_[k], db_[k])
+            for f in da_[k]:
+                assert np.array_equal(np.asarray(da_[k][f], dtype=float), np.asarray(db_[k][f], dtype=float)), (k, f)
     eng2 = Engine.from_metadata(md, rng=gen_rng(3), stream='numpy')
     assert np.allclose(eng2.logpdf_score(), eng.logpdf_score(), rtol=1e-12)
     import io, pickle, json

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import crosscat_oracle as co
-from helpers import (small_table, ctype_arrays, oracle_spec, oracle_suffstats,
+from helpers import (small_table, ctype_arrays, oracle_spec, oracle_suffstats, rel_tol,
                      device_suffstats, assert_suffstats_equal)
 
 pytestmark = pytest.mark.gpu
@@ -104,7 +104,7 @@ def test_rows_trajectory_matches_oracle(n_rows, seed, kw):
                     ref = np.asarray(logp)
                     fin = np.isfinite(ref)
                     assert np.array_equal(np.isfinite(got), fin)
-                    assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-5 * np.maximum(1.0, np.abs(ref[fin])))
+                    assert np.all(np.abs(got[fin] - ref[fin]) <= rel_tol(ref[fin]))
                 wi += 1
     scores = dev.logpdf_score().cpu().numpy()
     for s, o in enumerate(oracles):
@@ -130,22 +130,23 @@ def check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, tag):
                 assert int(rec[0]) == rowid and int(rec[1]) == len(K) and int(rec[2]) == zb, (tag, s, vid, i)
                 got = rec[3:3 + len(K)]
                 ref = np.asarray(logp)
-                assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))), (tag, s, vid, i)
+                assert np.all(np.abs(got - ref) <= rel_tol(ref)), (tag, s, vid, i)
             wi += 1
 
 
-@pytest.mark.parametrize('n_rows,seed,n_init,narrow', [(60, 5, 3, True), (300, 6, 3, True), (200, 7, 45, True),
-                                                      (300, 6, 3, False), (200, 7, 45, False)])
-def test_rows_trajectory_narrow_views(n_rows, seed, n_init, narrow, monkeypatch):
-    """All-normal table whose views hold one or two columns: with the width / type hints these
-    views go to the single-warp kernel (narrow=True) -- with CGPM_B200_ROWS_NO_NARROW to the
-    general one; both must follow the oracle step by step (n_init = 45 starts from more than
-    32 clusters per view, the multi-pass path of the draw)."""
+@pytest.mark.parametrize('n_rows,seed,n_init,lvl', [(60, 5, 3, None), (300, 6, 3, None), (200, 7, 45, None),
+                                                   (300, 6, 3, 0), (300, 6, 3, 2), (300, 6, 3, 9), (200, 7, 45, 0)])
+def test_rows_trajectory_narrow_views(n_rows, seed, n_init, lvl, monkeypatch):
+    """All-normal table whose views hold one or two columns (rows move at every other step): the
+    speculative rounds -- adaptive window (lvl=None) or pinned with CGPM_B200_ROWS_LVL to the most rows in
+    flight (0), a middle setting and a single row group (9) -- must follow the oracle step by step
+    (n_init = 45 starts from more than 32 clusters per view: one row at a time with the multi-pass
+    draw, then speculative rounds once the view has shrunk below 32 clusters)."""
     from cgpm_b200.device import DeviceChains
     from cgpm_b200 import codec
     from cgpm_b200.synth import gen_table
-    if not narrow:
-        monkeypatch.setenv('CGPM_B200_ROWS_NO_NARROW', '1')
+    if lvl is not None:
+        monkeypatch.setenv('CGPM_B200_ROWS_LVL', str(lvl))
     monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
     cct = ['normal'] * 5
     da = [None] * 5
@@ -180,22 +181,26 @@ def test_rows_trajectory_narrow_views(n_rows, seed, n_init, narrow, monkeypatch)
             o.transition_view_rows(trace=otr[s])
         work, tr = rows_sweep_numpy_stream(dev, oracles, views_order, rngs, trace=True, hints=True)
         modes = dev.t['seq'].cpu().numpy()[:, :3, 4]
-        assert np.all(modes == (3 if narrow else 0)), modes        # which kernel swept the views
-        check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, (sweep, narrow))
+        assert np.all(modes == 0), modes        # shared-memory tables, first kernel
+        check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, (sweep, lvl))
 
 
-@pytest.mark.parametrize('n_rows,seed,mixed,pipe', [(150, 11, False, True), (120, 12, True, True), (150, 11, False, False)])
-def test_rows_trajectory_wide_view(n_rows, seed, mixed, pipe, monkeypatch):
-    """A view of 20 columns (with the width hint) is swept by the two-rows-in-flight kernel of
-    rows_sweep_pipe.cuh (pipe=True; CGPM_B200_ROWS_NO_PIPE selects the sequential sweep): both must
-    follow the oracle step by step -- partitions, member order, bit-identical statistics and
-    per-step conditionals -- including rows that move and make the next row's speculative
-    scores stale."""
+@pytest.mark.parametrize('n_rows,seed,mixed,env', [(150, 11, False, {}), (120, 12, True, {}),
+                                                  (150, 11, False, {'CGPM_B200_ROWS_LVL': '0'}),
+                                                  (120, 12, True, {'CGPM_B200_ROWS_LVL': '0'}),
+                                                  (150, 11, False, {'CGPM_B200_ROWS_DL': '8'}),
+                                                  (120, 12, True, {'CGPM_B200_ROWS_NO_BULK': '1'})])
+def test_rows_trajectory_wide_view(n_rows, seed, mixed, env, monkeypatch):
+    """A view of 20 columns next to one of 3 (all-normal and mixed with categorical columns), swept by
+    speculative rounds (adaptive, or pinned to the most rows in flight where every mover invalidates a long
+    window), one row at a time (CGPM_B200_ROWS_DL=8 puts the 20-column view beyond the width limit) and with
+    per-cell gathers instead of bulk row copies: all must follow the oracle step by step -- partitions,
+    member order, bit-identical statistics and per-step conditionals."""
     from cgpm_b200.device import DeviceChains
     from cgpm_b200 import codec
     from cgpm_b200.synth import gen_table
-    if not pipe:
-        monkeypatch.setenv('CGPM_B200_ROWS_NO_PIPE', '1')
+    for k_, v_ in env.items():
+        monkeypatch.setenv(k_, v_)
     monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
     widths = (20, 3)
     ncol = sum(widths)
@@ -254,5 +259,5 @@ def test_rows_trajectory_wide_view(n_rows, seed, mixed, pipe, monkeypatch):
         dev.sync()
         dev.check_errors()
         trh = tr.cpu().numpy().reshape(len(work), R, TS)
-        assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == (4 if pipe else 0))      # which kernel swept the wide view
-        check_against_oracle(dev, oracles, ctype, n_rows, otr, trh, rngs, (sweep, mixed, pipe))
+        assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == 0)      # shared-memory tables, first kernel
+        check_against_oracle(dev, oracles, ctype, n_rows, otr, trh, rngs, (sweep, mixed, env))

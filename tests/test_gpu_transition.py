@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import crosscat_oracle as co
-from helpers import small_table, oracle_suffstats, device_suffstats, assert_suffstats_equal
+from helpers import small_table, oracle_suffstats, device_suffstats, assert_suffstats_equal, rel_tol
 
 pytestmark = pytest.mark.gpu
 
@@ -13,7 +13,8 @@ KERNELS = ['alpha', 'view_alphas', 'column_hypers', 'rows', 'columns']
 
 def compare(eng, oracles, tag):
     ch = eng._ch
-    scores = ch.logpdf_score()
+    # (with Ci the reference refuses to score the column CRP, state.py:370-372; the oracle returns the plain score)
+    scores = ch.logpdf_score() if not ch.Ci else ch.dev.logpdf_score().cpu().numpy() + ch._ln_const
     for s, o in enumerate(oracles):
         md = eng._ch and __import__('cgpm_b200.engine', fromlist=['x'])._chain_metadata(ch, s)
         om = o.to_metadata()
@@ -66,7 +67,7 @@ def test_columns_trace_logps(n_rows=60, seed=21):
                 rec = tr['data'][s, j]
                 assert int(rec[0]) == col and int(rec[1]) == len(tables) and int(rec[2]) == vs
                 got, ref = rec[3:3 + len(tables)], np.asarray(logp)
-                assert np.all(np.abs(got - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))), (got, ref)
+                assert np.all(np.abs(got - ref) <= rel_tol(ref)), (got, ref)
         eng.transition(N=1, kernels=['rows', 'column_hypers'], progress=False)
         for o in oracles:
             o.transition(N=1, kernels=['rows', 'column_hypers'])

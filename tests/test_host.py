@@ -119,3 +119,33 @@ def test_gather_over_two_gloo_ranks():
         assert full == [i * 1.5 for i in range(7)]
         assert full2 == [float(i) for i in range(7)]
         assert acc == 3.0
+
+
+def test_constrained_crp_helpers_match_the_reference():
+    """cgpm_b200.hostmath restates gu.simulate_crp_constrained[_dependent] / logp_crp_constrained_dependent
+    (src/utils/general.py:248-355): same partitions from the same stream, same log-probability."""
+    import os
+    import sys
+    import pytest
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
+    if not os.path.exists(os.path.join(ref, 'cgpm', '.built')):
+        pytest.skip('oracle/_ref not built')
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    from cgpm.utils import general as gu
+    from cgpm_b200 import hostmath as hm
+    Cd = [[0, 2], [3, 4, 5]]
+    Ci = [(0, 1), (2, 3), (6, 7)]
+    for seed in range(5):
+        a = gu.simulate_crp_constrained(9, 1.7, Cd, Ci, {}, {}, rng=np.random.RandomState(seed))
+        r = np.random.RandomState(seed)
+        b = hm.simulate_crp_constrained(9, 1.7, Cd, Ci, r)
+        assert list(a) == list(b)
+        a = gu.simulate_crp_constrained_dependent(9, 0.8, Cd, rng=np.random.RandomState(seed))
+        b = hm.simulate_crp_constrained_dependent(9, 0.8, Cd, np.random.RandomState(seed))
+        assert list(a) == list(b)
+        Z = {i: z for i, z in enumerate(b)}
+        assert hm.logp_crp_constrained_dependent(Z, 0.8, Cd) == gu.logp_crp_constrained_dependent(Z, 0.8, Cd)
+    assert hm.logp_crp_constrained_dependent({0: 0, 1: 0, 2: 1}, 1.0, [[0, 2]]) == -float('inf')
+    with pytest.raises(ValueError):
+        hm.validate_dependency_constraints(4, [[0, 1]], [(0, 1)])
