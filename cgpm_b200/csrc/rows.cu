@@ -344,6 +344,54 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 const bool dn = own && !singleton;
                 int drift = 0;
                 double acc = 0.0, acc2 = 0.0;
+                if (!GT && allnorm && !wide) {
+                    // All-normal view, shared-memory tables.  Pass A: every (row, candidate) lane evaluates the plain
+                    // Student-t term of its columns -- straight-line code, two independent chains per trip.  Pass B:
+                    // the term of the row's own cluster WITHOUT the row (view.py:416-419) is a different formula; instead
+                    // of letting one lane per group run it while the others wait at every column, all g lanes of the
+                    // row group share the own cluster's columns and the sum replaces the own lane's result.
+                    const int fsI = c.Kc * D;
+                    const double* hnu = c.hyp + 3 * D;
+                    const double* hr = c.hyp + D;
+                    int nodrift = 0;
+                    if (cand) {
+                        const double* pe = c.tab + ke * D;
+                        auto termA = [&](int jj) -> double {
+                            return normal_core(pe + jj, pe + jj, fsI, xrow[c.bulk ? c.col[jj] : jj], hnu[jj], hr[jj], false, false, nodrift,
+                                               [](double&, double&) {});
+                        };
+                        int j = cc;
+                        double acc3 = 0.0, acc4 = 0.0;
+                        for (; j + 3 * gc < D; j += 4 * gc) {          // four independent chains per trip
+                            acc += termA(j); acc2 += termA(j + gc); acc3 += termA(j + 2 * gc); acc4 += termA(j + 3 * gc);
+                        }
+                        for (; j < D; j += gc) acc += termA(j);
+                        acc += acc2 + (acc3 + acc4);
+                    }
+                    for (int o = gc >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    double accB = 0.0;
+                    if (arow) {
+                        const double* po = c.tab + z * D;
+                        for (int j = lane & (g - 1); j < D; j += g) {
+                            const double x = xrow[c.bulk ? c.col[j] : j];
+                            if (!singleton) {
+                                accB += normal_core(po + j, po + j, fsI, x, hnu[j], hr[j], true, true, drift,
+                                                    [&](double& m, double& ss) { m = c.hyp[j]; ss = c.hyp[2 * D + j]; });
+                            } else {
+                                // a lone member is scored against the empty cluster (pass A); its sums still go through -= x, += x
+                                const double sx0 = po[CC_F_SX * fsI + j], sxx0 = po[CC_F_SXX * fsI + j];
+                                const double xx = __dmul_rn(x, x);
+                                if (!isnan(x) && (__dadd_rn(__dsub_rn(sx0, x), x) != sx0 || __dadd_rn(__dsub_rn(sxx0, xx), xx) != sxx0)) drift = 1;
+                            }
+                        }
+                    }
+                    for (int o = g >> 1; o > 0; o >>= 1) {
+                        accB += __shfl_xor_sync(0xffffffffu, accB, o);
+                        drift |= __shfl_xor_sync(0xffffffffu, drift, o);
+                    }
+                    if (dn) acc = accB;
+                    if (!own) drift = 0;
+                } else {
                 if (cand) {
                     // two columns per trip: independent chains, so the two logs overlap
                     int j = cc;
@@ -357,6 +405,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 for (int o = gc >> 1; o > 0; o >>= 1) {
                     acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     drift |= __shfl_xor_sync(0xffffffffu, drift, o);
+                }
                 }
                 if (cand) {
                     lpv = acc;
@@ -848,18 +897,18 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
                 const uint32_t parity = ((b / c.NBUF) - 1) & 1;
                 uint32_t done = 0;
                 while (true) {
+                    // suspended by the hardware until the phase completes or ~50 us pass (no polling instructions)
                     asm volatile(
                         "{\n"
                         ".reg .pred p;\n"
-                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
                         "selp.u32 %0, 1, 0, p;\n"
                         "}\n"
                         : "=r"(done)
-                        : "r"(smem_u32(&c.bar_empty[buf])), "r"(parity)
+                        : "r"(smem_u32(&c.bar_empty[buf])), "r"(parity), "r"(50000u)
                         : "memory");
                     if (done) break;
                     if (*stopflag) { stopped = true; break; }
-                    __nanosleep(2000);
                 }
                 if (stopped) break;
             }

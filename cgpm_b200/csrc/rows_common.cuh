@@ -24,17 +24,19 @@ struct RowsParams {
 };
 
 // How one view's rows are staged: whole rows by bulk copies when the row is short and the view holds at least a
-// quarter of it, per-cell gathers otherwise; NBUF batches of B rows within about 32 KB (at least two batches of
-// one row).  Host (launch sizing) and device (per CTA) use the same rule.
+// quarter of it, per-cell gathers otherwise; NBUF (<= 8) batches of B (<= 32) rows within about 64 KB (at least two
+// batches of one row).  The ring bounds the number of rows a speculative round can have in flight.  Host (launch
+// sizing) and device (per CTA) use the same rule.
 struct RowsStage { int bulk, stagebytes, B, NBUF; };
 __host__ __device__ inline RowsStage rows_stage(int Cp, int C, int D, int allow_bulk) {
     RowsStage r;
     const int rowbytes = Cp * 8;
     r.bulk = (allow_bulk && rowbytes <= 4096 && 4 * D >= C) ? 1 : 0;
     r.stagebytes = r.bulk ? rowbytes : ((D + 1) & ~1) * 8;
-    r.B = 32; r.NBUF = 4;
-    while (r.B > 1 && r.NBUF * r.B * r.stagebytes > 32 * 1024) r.B >>= 1;
-    while (r.NBUF > 2 && r.NBUF * r.B * r.stagebytes > 48 * 1024) r.NBUF >>= 1;
+    r.B = 32; r.NBUF = 8;
+    while (r.NBUF > 4 && r.NBUF * r.B * r.stagebytes > 64 * 1024) r.NBUF >>= 1;
+    while (r.B > 1 && r.NBUF * r.B * r.stagebytes > 64 * 1024) r.B >>= 1;
+    while (r.NBUF > 2 && r.NBUF * r.B * r.stagebytes > 64 * 1024) r.NBUF >>= 1;
     return r;
 }
 

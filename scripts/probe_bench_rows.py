@@ -22,7 +22,10 @@ for it in range(warm + 2):
     e0.record()
     eng.transition(N=1, kernels=['rows'], progress=False)
     e1.record(); torch.cuda.synchronize()
-    print('rows sweep %d: %.1f ms' % (it, e0.elapsed_time(e1)))
+    seq = ch.dev.t['seq'].cpu().numpy(); nv = ch.dev.t['nv'].cpu().numpy()
+    top = sorted((int(seq[s, v, 0]) * 1024 // R, int(seq[s, v, 1]), int(seq[s, v, 2]), round(int(seq[s, v, 3]) / R, 3), int(seq[s, v, 4]), int(seq[s, v, 5]))
+                 for s in range(S) for v in range(ch.dev.Vcap) if nv[s, v] > 0)[-4:]
+    print('rows sweep %d: %.1f ms; slowest (cycles/row, D, K after, move rate, mode, level): %s' % (it, e0.elapsed_time(e1), top))
     eng.transition(N=1, kernels=['columns'], progress=False)
 eng.transition(N=1, kernels=['rows'], progress=False)
 torch.cuda.synchronize()

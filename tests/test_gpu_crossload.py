@@ -20,6 +20,12 @@ pytestmark = [pytest.mark.gpu,
 QUERIES = [(-1, {0: 1.2}, {}), (-1, {0: 1.2, 1: 2}, {2: 0.3}), (-1, {3: 1, 5: -0.5}, {0: 2., 4: 1., 1: 0}), (3, {0: 0.5}, {})]
 
 
+def table(n, seed):
+    X, cct, da = small_table(n, seed)
+    X[3, 0] = np.nan                 # the observed-row query above asks for this cell
+    return X, cct, da
+
+
 def ref_modules():
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -51,7 +57,7 @@ def assert_stats_close(a, b, rtol=1e-12):
 def test_gpu_metadata_loads_into_the_reference():
     from cgpm_b200.engine import Engine, gen_rng
     REngine, RState, gu = ref_modules()
-    X, cct, da = small_table(60, 31)
+    X, cct, da = table(60, 31)
     eng = Engine(X, num_states=3, rng=gen_rng(4), cctypes=cct, distargs=da, stream='numpy')
     eng.transition(N=3, progress=False)
     md = eng.to_metadata()
@@ -85,7 +91,7 @@ def test_gpu_metadata_loads_into_the_reference():
 def test_reference_pickle_loads_onto_the_gpu(tmp_path):
     from cgpm_b200.engine import Engine, State, gen_rng
     REngine, RState, gu = ref_modules()
-    X, cct, da = small_table(60, 32)
+    X, cct, da = table(60, 32)
     ref = REngine(X, num_states=3, rng=gu.gen_rng(7), cctypes=cct, distargs=da, multiprocess=0)
     ref.transition(N=3, progress=False, multiprocess=0)
     buf = io.BytesIO()
