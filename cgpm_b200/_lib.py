@@ -44,7 +44,7 @@ class cc_row_work(C.Structure):
         ('chain', C.c_int32), ('view', C.c_int32), ('n', C.c_int32),
         ('perm_is_index', C.c_int32), ('perm_off', C.c_int64), ('u_off', C.c_int64),
         ('trace_off', C.c_int64), ('n_cols', C.c_int32), ('n_normal', C.c_int32),
-        ('resume', C.c_int32), ('_pad', C.c_int32),
+        ('resume', C.c_int32), ('cost_hint', C.c_int32),
     ]
 
 

@@ -368,7 +368,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                         for (; j < D; j += gc) acc += termA(j);
                         acc += acc2 + (acc3 + acc4);
                     }
-                    for (int o = gc >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    // (pass B is issued before pass A's reduction: the two chains are independent and overlap)
                     double accB = 0.0;
                     if (arow) {
                         const double* po = c.tab + z * D;
@@ -385,12 +385,12 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                             }
                         }
                     }
-                    for (int o = g >> 1; o > 0; o >>= 1) {
-                        accB += __shfl_xor_sync(0xffffffffu, accB, o);
-                        drift |= __shfl_xor_sync(0xffffffffu, drift, o);
-                    }
+                    for (int o = gc >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    // only the first min(g, D) lanes of a group hold a part of pass B; the sum goes to every lane from lane 0
+                    for (int o = (1 << ceil_log2(min(g, D))) >> 1; o > 0; o >>= 1) accB += __shfl_xor_sync(0xffffffffu, accB, o);
+                    accB = __shfl_sync(0xffffffffu, accB, lane & ~(g - 1));
                     if (dn) acc = accB;
-                    if (!own) drift = 0;
+                    // (drift stays per lane: the group's flag is collected by a ballot below)
                 } else {
                 if (cand) {
                     // two columns per trip: independent chains, so the two logs overlap
@@ -406,6 +406,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                     acc += __shfl_xor_sync(0xffffffffu, acc, o);
                     drift |= __shfl_xor_sync(0xffffffffu, drift, o);
                 }
+                if (!own) drift = 0;
                 }
                 if (cand) {
                     lpv = acc;
@@ -429,7 +430,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 const unsigned segmask = (g == 32) ? 0xffffffffu : ((1u << g) - 1u);
                 const unsigned hit = (__ballot_sync(0xffffffffu, cand && inc > uu * tot) >> seg0) & segmask;
                 const unsigned ownb = (__ballot_sync(0xffffffffu, own) >> seg0) & segmask;
-                const unsigned drb = (__ballot_sync(0xffffffffu, own && drift) >> seg0) & segmask;
+                const unsigned drb = (__ballot_sync(0xffffffffu, drift != 0) >> seg0) & segmask;
                 const int ownpos = ownb ? ((__ffs(ownb) - 1) >> lgc) : 0;
                 choice = hit ? ((__ffs(hit) - 1) >> lgc) : -1;
                 bool fail = false;
@@ -441,7 +442,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 }
                 const bool flagged = arow && (dst != z || drb != 0);
                 const bool leader = (lane & (g - 1)) == 0;
-                if (fail && leader) c.scal[7] = CC_ERR_ARG;
+                if (fail && leader) { c.scal[7] = CC_ERR_ARG; c.scal[12] = 1; c.scal[13] = i; c.scal[14] = K; }
                 const unsigned fb = __ballot_sync(0xffffffffu, flagged && leader);
                 if (fb) {
                     if (lane == __ffs(fb) - 1) {
@@ -597,7 +598,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 }
                 if (choice < 0) {                       // NaN / all -inf: keep the row, flag the chain
                     choice = pubL[0];
-                    if (lane == 0) c.scal[7] = CC_ERR_ARG;
+                    if (lane == 0) { c.scal[7] = CC_ERR_ARG; c.scal[12] = 2; c.scal[13] = i; c.scal[14] = K; }
                 }
                 if (c.trace && lane == 0) {
                     double* tr = c.trace + c.trace_off + (size_t)i * c.trace_stride;
@@ -651,7 +652,18 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
             consumer_sync<NT>();
             if (tid == 0) {
                 int choice = c.scal[40];
-                if (choice == 0x7fffffff || !(s_tot == s_tot)) { choice = pubL[0]; c.scal[7] = CC_ERR_ARG; }
+                if (choice == 0x7fffffff || !(s_tot == s_tot)) {
+                    if (c.scal[7] == 0) {          // remember the first failure (debug probes read it from st.seq)
+                        c.scal[12] = (choice == 0x7fffffff) ? 3 : 4; c.scal[13] = i; c.scal[14] = K;
+                        int bad = -1;
+                        for (int pc = 0; pc < ncand; ++pc) if (!(c.lp[pc] == c.lp[pc]) || !(c.w[pc] == c.w[pc])) { bad = pc; break; }
+                        c.scal[15] = bad;
+                        c.scal[32] = (bad >= 0 && bad < K) ? c.live[bad] : -1;
+                        c.scal[33] = (int)(uu * 1e9);
+                        c.scal[34] = (s_tot == s_tot) ? 1 : 0;
+                    }
+                    choice = pubL[0]; c.scal[7] = CC_ERR_ARG;
+                }
                 if (c.trace) {
                     double* tr = c.trace + c.trace_off + (size_t)i * c.trace_stride;
                     tr[0] = (double)r;
@@ -790,6 +802,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     }
     const int K0 = st.nclu[sv];
     c.K0 = K0;
+    __syncthreads();                 // c.col[] (thread 0) is read by everybody below
     if (!BIG) {
         // the candidate arrays must hold every live slot and leave the empty-cluster position free
         __shared__ int s_fit;
@@ -1013,11 +1026,13 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         st.nclu[sv] = K;
         if (c.scal[7]) st.err[s] = c.scal[7];
         prog[0] = pos; prog[1] = nmoved; prog[2] = status;
+        prog[3] = (int)min((clock64() - t_start) >> 10, (long long)0x7fffffff) + ((BIG || wk.resume) ? prog[3] : 0);
         if (p.prof) {
             int32_t* q = st.seq + sv * R;
             q[0] = (int)((clock64() - t_start) >> 10); q[1] = D; q[2] = K; q[3] = nmoved;
             q[4] = (BIG ? 8 : 0) + (start_global ? 1 : (in_global ? 2 : 0));      // kernel; table mode: shared / global / migrated mid-sweep
             q[5] = lvl;
+            if (c.scal[7]) { q[6] = c.scal[12]; q[7] = c.scal[13]; q[8] = c.scal[14]; q[9] = D; q[10] = c.scal[15]; q[11] = c.scal[32]; q[12] = c.scal[33]; q[13] = c.scal[34]; }      // where a draw failed
         }
     }
     if (status != ST_OK) return;
@@ -1088,7 +1103,10 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     const int allow_bulk = getenv("CGPM_B200_ROWS_NO_BULK") ? 0 : 1;
     auto width = [&](const cc_row_work& w) -> int { return (w.n_cols > 0 && w.n_cols <= st->C) ? w.n_cols : st->C; };
     std::vector<cc_row_work> sorted(work, work + n_work);
-    std::stable_sort(sorted.begin(), sorted.end(), [&](const cc_row_work& a, const cc_row_work& b) { return width(a) > width(b); });
+    std::stable_sort(sorted.begin(), sorted.end(), [&](const cc_row_work& a, const cc_row_work& b) {
+        if (a.cost_hint != b.cost_hint) return a.cost_hint > b.cost_hint;
+        return width(a) > width(b);
+    });
     cc_row_work* dwork = nullptr;
     double* big_lp = nullptr;
     CC_CUDA(cudaMallocAsync(&dwork, sizeof(cc_row_work) * n_work, stream));

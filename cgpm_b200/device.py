@@ -176,6 +176,7 @@ class DeviceChains(object):
         self.lib = _CountingLib(L.load(), self.lib_calls)
         self._rows_pending = None
         self.kcap_grown = 0
+        self._view_cost = {}          # (chain, view slot) -> kilocycles of the view's last rows sweep (launch order)
 
     # ------------------------------------------------------------------ helpers
     def stream_ptr(self):
@@ -314,6 +315,7 @@ class DeviceChains(object):
             arr[i].n_cols = w.get('n_cols', 0)
             arr[i].n_normal = w.get('n_normal', 0)
             arr[i].resume = resume
+            arr[i].cost_hint = self._view_cost.get((w['chain'], w['view']), 0)
         perm, u, trace = pd['perm'], pd['u'], pd['trace']
         rc = self.lib.cc_transition_rows(
             C.byref(self.st), n, arr,
@@ -332,6 +334,8 @@ class DeviceChains(object):
             while self.Kcap < self.R + 1:
                 prog = self.t['rows_prog'].cpu().numpy()                      # synchronises the stream
                 worst = max(int(prog[w['chain'], w['view'], 2]) for w in self._rows_pending['work'])
+                for w in self._rows_pending['work']:
+                    self._view_cost[(w['chain'], w['view'])] = int(prog[w['chain'], w['view'], 3])
                 if worst != L.ROWS_GROW:
                     if worst != L.ROWS_DONE:
                         raise L.CgpmB200Error('rows sweep left in state %d' % worst)

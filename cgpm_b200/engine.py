@@ -533,6 +533,53 @@ class Engine(_Api):
         statenos = list(statenos or range(self.num_states()))
         return self._ch.simulate_bulk(statenos, rowids, targets_list, constraints_list, Ns)
 
+    # ---- array form of the bulk queries (not in the reference: its dict-per-query form costs a Python loop per
+    #      query; a batch of hypothetical rows over fixed target / constraint columns is encoded with numpy) ----
+    def logpdf_bulk_arrays(self, target_cols, target_vals, constraint_cols=None, constraint_vals=None, statenos=None):
+        """[n_states, Q] array: logpdf(-1, {target_cols[j]: target_vals[q, j]}, {constraint_cols[j]: constraint_vals[q, j]})."""
+        from . import query
+        statenos = list(statenos or range(self.num_states()))
+        return query.logpdf_bulk_arrays(self._ch, statenos, target_cols, target_vals, constraint_cols, constraint_vals)
+
+    def simulate_bulk_arrays(self, Q, target_cols, constraint_cols=None, constraint_vals=None, N=1, statenos=None):
+        """[n_states, Q, N, len(target_cols)] array of predictive samples for Q hypothetical rows."""
+        from . import query
+        self._seed_states()
+        statenos = list(statenos or range(self.num_states()))
+        return query.simulate_bulk_arrays(self._ch, statenos, Q, target_cols, constraint_cols, constraint_vals, N)
+
+    # ---- dense state bridge and instrumentation (the lovecat-style export / write-back of INTEGRATION.md) ----
+    def to_dense(self, pinned=None):
+        """Device -> pinned host copy of every chain's state in dense slot form (the write-back half of
+        lovecat._update_state, src/crosscat/lovecat.py:226-290): dict of CPU tensors, reusable as `pinned`."""
+        return self._ch.export_dense(pinned=pinned)
+
+    def load_dense(self, dense, X=None):
+        """Host -> device copy of a dense state (and optionally the table, a pinned [R, C] float64 tensor), followed
+        by the ordered rebuild of all sufficient statistics (the export half of the bridge, lovecat.py:73-223)."""
+        self._ch.import_dense(dense, X=X)
+
+    def start_kernel_timing(self):
+        """Record a CUDA event pair around every CrossCat kernel call of transition()."""
+        self._ch.events = []
+
+    def stop_kernel_timing(self):
+        """{kernel name: [milliseconds per call]} since start_kernel_timing()."""
+        import torch
+        torch.cuda.synchronize(self._ch.dev.device)
+        events, self._ch.events = self._ch.events or [], None
+        out = {}
+        for name, a, b in events:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        return out
+
+    def native_launches(self, reset=False):
+        """Kernels of libcgpm_b200.so launched so far (a lower bound: counted per C-ABI call)."""
+        n = sum(self._ch.dev.lib_calls.values())
+        if reset:
+            self._ch.dev.lib_calls.clear()
+        return n
+
     def dependence_probability(self, col0, col1, statenos=None, multiprocess=1):
         statenos = statenos or range(self.num_states())
         return [self._dependence_probability(s, col0, col1) for s in statenos]

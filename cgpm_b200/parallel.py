@@ -50,6 +50,24 @@ def all_reduce_sum(t, group=None):
     return t
 
 
+def all_gather_objects(local_list, group=None):
+    """Python objects (one list per rank, in shard order) -> the concatenated list on every rank."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return list(local_list)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, list(local_list), group=group)
+    return [x for part in parts for x in part]
+
+
+def weighted_integrate(logpdfs, weights=None):
+    """Engine._likelihood_weighted_integrate (src/crosscat/engine.py:361-371) over the chains of all ranks:
+    logmeanexp of the chains' log-densities, weighted by the log-density of the constraints when given."""
+    logpdfs = [float(x) for x in logpdfs]
+    if weights is None:
+        return hm.logmeanexp(logpdfs)
+    return hm.logmeanexp_weighted(logpdfs, [float(w) for w in weights])
+
+
 class ShardedEngine(object):
     """Engine whose chains are spread over the ranks of the default process group.
     Every rank constructs it with the same arguments; rank r holds chains
@@ -105,3 +123,47 @@ class ShardedEngine(object):
             acc += torch.as_tensor(D, dtype=torch.float64, device=self._device())
         all_reduce_sum(acc)
         return (acc / self.num_states_total).cpu().numpy()
+
+    # ---- the rest of the Engine surface (src/crosscat/engine.py:192-281,361-435) over all ranks ----------------
+    def num_states(self):
+        return self.num_states_total
+
+    def logpdf(self, rowid, targets, constraints=None):
+        loc = torch.as_tensor(self.local.logpdf(rowid, targets, constraints), dtype=torch.float64, device=self._device())
+        return all_gather_chains(loc, self.num_states_total).cpu().numpy().tolist()
+
+    def logpdf_likelihood_weighted(self, rowid, targets, constraints=None):
+        """The ensemble estimate of engine.py:361-371: chains weighted by the density they give the constraints."""
+        lp = self.logpdf(rowid, targets, constraints)
+        if constraints:
+            return weighted_integrate(lp, self.logpdf(rowid, constraints))
+        return weighted_integrate(lp)
+
+    def simulate(self, rowid, targets, constraints=None, N=None):
+        return all_gather_objects(self.local.simulate(rowid, targets, constraints, N=N))
+
+    def simulate_bulk(self, rowids, targets_list, constraints_list=None, Ns=None):
+        """[num_states][Q] lists of sample dicts, chains in global order (engine.py:241-251)."""
+        return all_gather_objects(self.local.simulate_bulk(rowids, targets_list, constraints_list, Ns=Ns))
+
+    def dependence_probability(self, col0, col1):
+        loc = torch.as_tensor(self.local.dependence_probability(col0, col1), dtype=torch.float64, device=self._device())
+        return all_gather_chains(loc, self.num_states_total).cpu().numpy().tolist()
+
+    def to_metadata(self):
+        """engine.py:394-401 with the states of every rank, in global order (the same dict on every rank)."""
+        md = self.local.to_metadata()
+        md['states'] = all_gather_objects(md['states'])
+        return md
+
+    def get_state(self, index):
+        """The State object of chain `index`, rebuilt on every rank from its owner's metadata."""
+        from .engine import State, gen_rng, _chain_metadata
+        box = [None]
+        owner = [r for r in range(self.world) if shard_range(self.num_states_total, self.world, r)[0] <= index
+                 < shard_range(self.num_states_total, self.world, r)[1]][0]
+        if self.rank == owner:
+            box[0] = _chain_metadata(self.local._ch, index - self.lo, X_list=self.local.X.tolist())
+        if dist.is_available() and dist.is_initialized():
+            dist.broadcast_object_list(box, src=owner)
+        return State.from_metadata(box[0], rng=gen_rng(index), **self.local._opts_for_state())

@@ -168,3 +168,113 @@ def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=No
             per_chain.append(samples)
         res.append(per_chain)
     return res
+
+
+# ---------------------------------------------------------------------------------------------
+# Array form of the bulk queries: Q hypothetical rows (rowid = -1) that all ask for the same target columns
+# given the same constraint columns -- the shape of a scoring / imputation batch (BASELINE.json configs[4]).
+# The dict form above costs a Python loop per query; here the CSR arrays are built with numpy in one piece.
+def _encode_arrays(ch, target_cols, target_vals, constraint_cols, constraint_vals, simulate):
+    target_cols = list(target_cols)
+    constraint_cols = list(constraint_cols or [])
+    for c in target_cols + constraint_cols:
+        if c not in ch.col_index:
+            raise ValueError('Unknown column: %s' % (c,))
+    if len(set(target_cols)) != len(target_cols):
+        raise ValueError('Columns in targets must be unique.')
+    if set(target_cols) & set(constraint_cols):
+        raise ValueError('Targets and constraints must be disjoint.')
+    nt, nc = len(target_cols), len(constraint_cols)
+    cv = np.asarray(constraint_vals, dtype=np.float64).reshape(-1, nc) if nc else None
+    if simulate:
+        Q = int(target_vals)                 # number of queries
+        tv = np.zeros((Q, nt))
+    else:
+        tv = np.asarray(target_vals, dtype=np.float64).reshape(-1, nt)
+        Q = tv.shape[0]
+    if cv is not None and cv.shape[0] != Q:
+        raise ValueError('constraint values must have one row per query')
+    jac = np.zeros(Q)
+    dead = np.zeros(Q, dtype=bool)
+    tv = tv.copy()
+    for j, c in enumerate(target_cols):
+        if ch.lognormal[ch.col_index[c]] and not simulate:
+            bad = tv[:, j] <= 0
+            dead |= bad
+            tv[bad, j] = 1.0
+            tv[:, j] = np.log(tv[:, j])
+            jac -= np.where(bad, 0.0, tv[:, j])
+    if cv is not None:
+        cv = cv.copy()
+        for j, c in enumerate(constraint_cols):
+            if ch.lognormal[ch.col_index[c]]:
+                if np.any(cv[:, j] <= 0):
+                    raise ValueError('Zero density constraints: %s' % ({c: float(cv[cv[:, j] <= 0, j][0])},))
+                cv[:, j] = np.log(cv[:, j])
+    per = nt + nc
+    col_row = np.asarray([ch.col_index[c] for c in target_cols + constraint_cols], np.int32)
+    role_row = np.asarray([0] * nt + [1] * nc, np.uint8)
+    vals = tv if cv is None else np.concatenate([tv, cv], axis=1)
+    dev = ch.dev.device
+    return {
+        'Q': Q, 'rowid': torch.full((Q,), -1, dtype=torch.int32, device=dev),
+        'off': torch.arange(0, (Q + 1) * per, per, dtype=torch.int32, device=dev),
+        'col': torch.from_numpy(np.tile(col_row, Q)).to(dev),
+        'val': torch.from_numpy(np.ascontiguousarray(vals.reshape(-1))).to(dev),
+        'role': torch.from_numpy(np.tile(role_row, Q)).to(dev),
+        'constraints': None, 'jac': jac, 'dead': dead, 'constraint_cols': constraint_cols, 'cv': cv,
+    }
+
+
+def logpdf_bulk_arrays(ch, chains, target_cols, target_vals, constraint_cols=None, constraint_vals=None):
+    """[len(chains), Q] array of State.logpdf(-1, {target_cols[j]: target_vals[q, j]}, {constraint ...})."""
+    enc = _encode_arrays(ch, target_cols, target_vals, constraint_cols, constraint_vals, simulate=False)
+    if enc['constraints'] is None:
+        enc['constraints'] = _LazyConstraints(enc)
+    return logpdf_bulk_encoded(ch, chains, enc)
+
+
+class _LazyConstraints(object):
+    """constraints_list[q] for error messages, built on demand."""
+
+    def __init__(self, enc):
+        self.enc = enc
+
+    def __getitem__(self, q):
+        cv = self.enc['cv']
+        return {} if cv is None else {c: float(cv[q, j]) for j, c in enumerate(self.enc['constraint_cols'])}
+
+
+def simulate_bulk_arrays(ch, chains, Q, target_cols, constraint_cols=None, constraint_vals=None, N=1):
+    """[len(chains), Q, N, len(target_cols)] array of predictive samples of hypothetical rows (categorical
+    columns as integer-valued floats, lognormal columns on their original scale)."""
+    enc = _encode_arrays(ch, target_cols, Q, constraint_cols, constraint_vals, simulate=True)
+    enc['constraints'] = _LazyConstraints(enc)
+    N = int(N)
+    soff = np.arange(0, (Q + 1) * N, N, dtype=np.int32)
+    total = int(Q * N)
+    maxt = max(1, len(target_cols))
+    dev = ch.dev
+    n = len(chains)
+    out = torch.zeros((2, n, total, maxt), dtype=torch.float64, device=dev.device)
+    flag = torch.zeros((n, Q), dtype=torch.int32, device=dev.device)
+    chs = np.ascontiguousarray(chains, dtype=np.int32)
+    soff_d = torch.from_numpy(soff).to(dev.device)
+    salt = 0
+    for s in chains:
+        if ch.rngs[s] is not None:
+            salt = (salt * 1000003 + int(ch.rngs[s].randint(0, 2 ** 31 - 1))) & 0xFFFFFFFFFFFFFFFF
+    L.check(dev.lib.cc_simulate_bulk(C.byref(dev.st), n, chs.ctypes.data_as(C.c_void_p), Q, _dp(enc['rowid']),
+                                     _dp(enc['off']), _dp(enc['col']), _dp(enc['val']), _dp(enc['role']),
+                                     _dp(soff_d), total, maxt, _dp(out), _dp(flag),
+                                     C.c_uint64(ch.seed ^ salt), C.c_uint64(ch._next_counter()), dev.stream_ptr()),
+            'cc_simulate_bulk')
+    vals = out[0].cpu().numpy().reshape(n, Q, N, maxt)
+    bad = flag.cpu().numpy()
+    if bad.any():
+        q = int(np.nonzero(bad.any(axis=0))[0][0])
+        raise ValueError('Zero density constraints: %s' % (enc['constraints'][q],))
+    for j, c in enumerate(target_cols):
+        if ch.lognormal[ch.col_index[c]]:
+            vals[..., j] = np.exp(vals[..., j])
+    return vals[..., :len(target_cols)]

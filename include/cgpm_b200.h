@@ -86,7 +86,7 @@ typedef struct cc_state {
     double*  cnt;        /* [S][Kcap][CT]   categorical counts                    */
     int32_t* err;        /* [S]  sticky per-chain error code (CC_ERR_CAPACITY)    */
     int32_t* rows_prog;  /* [S][Vcap][4]  progress of the view's rows sweep: {next row position, rows re-seated so
-                            far, status, -}.  status CC_ROWS_DONE after a complete sweep; CC_ROWS_HANDOVER while a
+                            far, status, kilocycles the sweep took}.  status CC_ROWS_DONE after a complete sweep; CC_ROWS_HANDOVER while a
                             sweep is passed from the shared-memory kernel to the large-K kernel inside one
                             cc_transition_rows call; CC_ROWS_GROW when the sweep stopped in front of a move that
                             needs a cluster slot beyond Kcap: the caller re-allocates the per-cluster arrays with a
@@ -120,7 +120,9 @@ typedef struct cc_row_work {
     int32_t n_normal;     /* how many of them are normal columns, if the caller knows it, else 0 */
     int32_t resume;       /* 0: a fresh sweep; 1: continue the sweep recorded in rows_prog (items whose status is
                              CC_ROWS_DONE are skipped) */
-    int32_t _pad;
+    int32_t cost_hint;    /* expected cost of the sweep in any unit (e.g. rows_prog[..][3] of the view's last sweep), or
+                             0: work items are started in descending order of (cost_hint, n_cols) so that the longest
+                             sweeps never start last when there are more items than resident CTAs */
 } cc_row_work;
 
 const char* cc_last_error(void);

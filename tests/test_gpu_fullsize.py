@@ -63,3 +63,75 @@ def test_full_size_invariants_exact_statistics_and_reproducibility():
     for s in range(ch.S):
         for v in np.nonzero(live[s])[0]:
             assert torch.equal(eng2._ch.dev.t['zr'][s, v], zr[s, v])
+
+
+def test_full_size_mixed_table_under_debug_invariants(monkeypatch):
+    """BASELINE.json configs[2]'s column mix at full row count on one GPU: 100 000 x 40, every other column
+    categorical with k in {2, 4, 8, 16}, 5 % missing cells, normal values on a 2^-12 grid.  GPMCCDEBUG
+    (src/utils/config.py:112-114) checks the partition invariants after every kernel, including
+    N(cluster, column) == number of non-missing members; afterwards the incrementally maintained statistics --
+    normal sums AND categorical counts -- equal a fresh ordered rebuild bit for bit and logpdf_score does not move."""
+    from cgpm_b200 import synth
+    from cgpm_b200.engine import Engine, gen_rng
+    import bench
+    monkeypatch.setenv('GPMCCDEBUG', '1')
+    R, C, S = 100000, 40, 4
+    cct, da = bench.column_types(C, True)
+    X, _, _ = synth.gen_table(R, cct, da, n_views=4, clusters_per_view=4, seed=1, quantize_bits=12, nan_frac=0.05)
+    Zv, Zrv = bench.initial_partitions(R, C, 5)
+    eng = Engine(X, num_states=S, rng=gen_rng(2), cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, alpha=1.0,
+                 view_alphas={v: 1.0 for v in Zrv}, stream='philox', Kcap=128)
+    eng.transition(N=2, kernels=['rows', 'columns', 'view_alphas', 'alpha', 'column_hypers'], progress=False)
+    ch = eng._ch
+    ch.check_partitions()
+    score_inc = ch.logpdf_score()
+    stat_inc = ch.dev.t['stat'].clone(); cnt_inc = ch.dev.t['cnt'].clone()
+    ch.dev.rebuild()
+    ch.dev.sync()
+    live = ch.dev.t['nv'].cpu().numpy() > 0
+    nclu = ch.dev.t['nclu'].cpu().numpy(); livel = ch.dev.t['live'].cpu().numpy(); zvh = ch.dev.t['zv'].cpu().numpy()
+    for s in range(S):
+        for v in np.nonzero(live[s])[0]:
+            slots = torch.as_tensor(livel[s, v, :nclu[s, v]].astype(np.int64), device=ch.dev.device)
+            cols = np.nonzero(zvh[s] == v)[0]
+            colt = torch.as_tensor(cols.astype(np.int64), device=ch.dev.device)
+            for f in (0, 1, 2):
+                assert torch.equal(stat_inc[s, f][slots][:, colt], ch.dev.t['stat'][s, f][slots][:, colt]), (s, int(v), f)
+            for c in cols:
+                if ch.ctype[c] == 1:
+                    o0, k = int(ch.dev.catoff_h[c]), int(ch.ncat[c])
+                    assert torch.equal(cnt_inc[s][slots][:, o0:o0 + k], ch.dev.t['cnt'][s][slots][:, o0:o0 + k]), (s, int(v), int(c))
+    assert np.allclose(score_inc, ch.logpdf_score(), rtol=1e-12, atol=0)
+
+
+def test_reference_faithful_default_initialisation_at_scale():
+    """Engine(X, num_states=...) with NO supplied partitions, as a user of the reference would call it: every view
+    draws its CRP concentration from a grid up to R and seats the rows from the prior (view.py:99-103,
+    crp.py:148-152), so views start with anything from one to thousands of clusters.  The cluster capacity follows
+    the drawn partitions and grows on demand; views beyond the shared-memory candidate arrays are swept by the
+    large-K kernel.  Three sweeps of rows + columns must leave consistent partitions and statistics equal to a
+    rebuild (values on a 2^-12 grid)."""
+    from cgpm_b200 import synth
+    from cgpm_b200.engine import Engine, gen_rng
+    R, C, S = 20000, 12, 4
+    cct = ['normal'] * C
+    X, _, _ = synth.gen_table(R, cct, [None] * C, n_views=3, clusters_per_view=4, seed=2, quantize_bits=12)
+    eng = Engine(X, num_states=S, rng=gen_rng(11), cctypes=cct, stream='philox')
+    ch = eng._ch
+    k0 = int(ch.dev.t['nclu'].max().item())
+    assert k0 > 1024, k0                       # the draw below must exercise the large-K path (seed-dependent)
+    eng.transition(N=3, kernels=['rows', 'columns'], progress=False)
+    ch.check_partitions()
+    score_inc = ch.logpdf_score()
+    stat_inc = ch.dev.t['stat'].clone()
+    ch.dev.rebuild()
+    ch.dev.sync()
+    live = ch.dev.t['nv'].cpu().numpy() > 0
+    nclu = ch.dev.t['nclu'].cpu().numpy(); livel = ch.dev.t['live'].cpu().numpy(); zvh = ch.dev.t['zv'].cpu().numpy()
+    for s in range(S):
+        for v in np.nonzero(live[s])[0]:
+            slots = torch.as_tensor(livel[s, v, :nclu[s, v]].astype(np.int64), device=ch.dev.device)
+            colt = torch.as_tensor(np.nonzero(zvh[s] == v)[0].astype(np.int64), device=ch.dev.device)
+            for f in (0, 1, 2):
+                assert torch.equal(stat_inc[s, f][slots][:, colt], ch.dev.t['stat'][s, f][slots][:, colt]), (s, int(v), f)
+    assert np.allclose(score_inc, ch.logpdf_score(), rtol=1e-12, atol=0)

@@ -99,7 +99,10 @@ def _gloo_worker(rank, world, port, q):
     mat = torch.stack([torch.full((3,), float(i)) for i in range(lo, hi)])
     full2 = all_gather_chains(mat, n)
     acc = all_reduce_sum(torch.ones(2, 2, dtype=torch.float64) * (rank + 1))
-    q.put((rank, full.tolist(), full2[:, 0].tolist(), acc[0, 0].item()))
+    from cgpm_b200.parallel import all_gather_objects, weighted_integrate
+    objs = all_gather_objects([{'chain': i} for i in range(lo, hi)])
+    lw = weighted_integrate(full.tolist(), [0.5 * x for x in full.tolist()])
+    q.put((rank, full.tolist(), full2[:, 0].tolist(), acc[0, 0].item(), [o['chain'] for o in objs], lw))
     dist.destroy_process_group()
 
 
@@ -115,10 +118,14 @@ def test_gather_over_two_gloo_ranks():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, full, full2, acc in res:
+    from cgpm_b200 import hostmath as hm
+    for rank, full, full2, acc, objs, lw in res:
         assert full == [i * 1.5 for i in range(7)]
         assert full2 == [float(i) for i in range(7)]
         assert acc == 3.0
+        assert objs == list(range(7))                       # python objects gathered in global chain order
+        # engine.py:361-371: chains weighted by the density they give the constraints
+        assert lw == hm.logmeanexp_weighted([i * 1.5 for i in range(7)], [i * 0.75 for i in range(7)])
 
 
 def test_constrained_crp_helpers_match_the_reference():
