@@ -48,6 +48,12 @@ class cc_row_work(C.Structure):
     ]
 
 
+GROW_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int32, C.c_int32)
+K_ALPHA, K_VIEW_ALPHAS, K_COLUMN_HYPERS, K_ROWS, K_COLUMNS = range(5)
+KERNEL_CODES = {'alpha': K_ALPHA, 'view_alphas': K_VIEW_ALPHAS, 'column_hypers': K_COLUMN_HYPERS, 'rows': K_ROWS,
+                'columns': K_COLUMNS}
+
+
 class CgpmB200Error(RuntimeError):
     pass
 
@@ -84,6 +90,8 @@ def _declare(lib):
     lib.cc_transition_col_hypers.argtypes = [C.POINTER(cc_state), I, P, P, P, P, U64, U64, P]
     lib.cc_transition_alphas.restype = I
     lib.cc_transition_alphas.argtypes = [C.POINTER(cc_state), I, P, P, P, I, U64, U64, P]
+    lib.cc_transition.restype = I
+    lib.cc_transition.argtypes = [C.POINTER(cc_state), I, P, I, I, P, P, P, U64, C.POINTER(C.c_uint64), GROW_FN, P, P]
     lib.cc_logpdf_bulk.restype = I
     lib.cc_logpdf_bulk.argtypes = [C.POINTER(cc_state), I, P, I, P, P, P, P, P, P, P, P]
     lib.cc_simulate_bulk.restype = I
@@ -101,7 +109,7 @@ OPTIONAL = {}
 # every symbol include/cgpm_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = ['cc_last_error', 'cc_abi_version', 'cc_rebuild', 'cc_refresh_tables', 'cc_check_state', 'cc_logpdf_score',
            'cc_transition_rows', 'cc_col_aux', 'cc_col_marginals', 'cc_col_scan', 'cc_col_install',
-           'cc_transition_col_hypers', 'cc_transition_alphas', 'cc_logpdf_bulk', 'cc_simulate_bulk']
+           'cc_transition_col_hypers', 'cc_transition_alphas', 'cc_transition', 'cc_logpdf_bulk', 'cc_simulate_bulk']
 
 
 def load():

@@ -303,6 +303,9 @@ class Chains(object):
             'rows': lambda: self.transition_view_rows(chains, views=views, cols=cols, rows=rowids),
             'columns': lambda: self.transition_dims(chains, cols=cols),
         }
+        if (self.stream == 'philox' and rowids is None and cols is None and views is None and S is None and N
+                and self.events is None and not self.check_env_debug() and not os.environ.get('CGPM_B200_PYTHON_SCHEDULE')):
+            return self._transition_native(chains, int(N), kernels, progress, checkpoint)
         funcs = [self._timed(k, table[k]) for k in kernels]
         if self.stream == 'philox' and not os.environ.get('CGPM_B200_NO_AUX_OVERLAP'):
             # rows immediately followed by columns: generate the column sweep's auxiliary views beside the rows sweep
@@ -342,6 +345,48 @@ class Chains(object):
         if progress:
             print('\rCompleted: %d iterations in %f seconds.' % (iters, time.time() - start))
         return iters
+
+    # kernels the C schedule launches per kernel code and iteration (a lower bound, for the launch counter)
+    NATIVE_LAUNCHES = {'alpha': 1, 'view_alphas': 1, 'column_hypers': 1, 'rows': 1, 'columns': 7, 'column_params': 0}
+
+    def _transition_native(self, chains, N, kernels, progress, checkpoint):
+        """The whole schedule through cc_transition (csrc/transition.cu): N iterations of the kernel list in one C call
+        per checkpoint interval -- no Python between kernels.  Same kernels, same conditional distributions as the
+        Python schedule below (which stays for the injected numpy stream, row / column / view subsets, time budgets,
+        per-kernel timing and the debug invariants)."""
+        dev = self.dev
+        start = time.time()
+        codes = np.ascontiguousarray([L.KERNEL_CODES[k] for k in kernels if k != 'column_params'], dtype=np.int32)
+        ch = np.ascontiguousarray(chains, dtype=np.int32)
+        if 'columns' in kernels:
+            self._ensure_arena(len(chains) * self.C)
+            self._ensure_aux_store()
+        ci_off, ci_adj = (self._ci_dev if self._ci_dev else (None, None))
+        self._aux_pre = None
+        done = 0
+        while done < N:
+            n = min(N - done, checkpoint) if checkpoint else N - done
+            ctr = C.c_uint64(self.counter)
+            rc = dev.lib.cc_transition(C.byref(dev.st), len(ch), _p(ch), n, len(codes), _p(codes), _dp(ci_off), _dp(ci_adj),
+                                       C.c_uint64(self.seed), C.byref(ctr), dev.grow_callback(), None, dev.stream_ptr())
+            self.counter = int(ctr.value)
+            self._mirror = None
+            L.check(rc, 'cc_transition')
+            dev.lib_calls['cc_transition'] += n * sum(self.NATIVE_LAUNCHES[k] for k in kernels)
+            for k in kernels:
+                for s in chains:
+                    it = self.diagnostics[s]['iterations']
+                    it[k] = it.get(k, 0) + n
+            done += n
+            if checkpoint and done % checkpoint == 0:
+                self._refresh_views_order(chains)
+                self._increment_diagnostics(chains)
+        dev.sync()
+        self._refresh_views_order(chains)
+        dev.check_errors()
+        if progress:
+            print('\rCompleted: %d iterations in %f seconds.' % (N, time.time() - start))
+        return N
 
     CHECK_CODES = {1: 'nv is not the histogram of zv', 2: 'live view without id', 3: 'column in no view',
                    4: 'non-positive CRP alpha', 5: 'cluster count out of range', 6: 'invalid or repeated live slot',
@@ -675,7 +720,8 @@ class Chains(object):
                 if not stored:
                     # regenerate the same auxiliary partitions (same key) and keep them
                     L.check(lib.cc_col_aux(st, len(b_ch), _p(b_ch), _p(b_co), None, None, 1, seed, C.c_uint64(counter), sp()), 'cc_col_aux')
-                nv_before = dev.t['nv'].cpu().numpy()
+                nv_before = self._make_room_for_births(b_ch, b_co, stored)
+                st = C.byref(dev.st)
                 L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), 2 if stored else 1, sp()), 'cc_col_install')
                 new_slots = np.array([int(np.nonzero(nv_before[s] == 0)[0][0]) if np.any(nv_before[s] == 0) else 0
                                       for s in b_ch], dtype=np.int32)
@@ -735,6 +781,8 @@ class Chains(object):
                 if len(idx):
                     b_ch = np.ascontiguousarray(ch_h[idx], dtype=np.int32)
                     b_co = np.ascontiguousarray(perm[idx, j], dtype=np.int32)
+                    self._make_room_for_births(b_ch, b_co, False)
+                    st = C.byref(dev.st)
                     L.check(lib.cc_col_install(st, len(b_ch), _p(b_ch), _p(b_co), 1, sp()), 'cc_col_install')
                 self._mirror = None
                 self._refresh_views_order(chains)
@@ -753,6 +801,25 @@ class Chains(object):
             trace['perm'] = perm
             trace['data'] = tr_d.cpu().numpy()[:nch * ncols * ts].reshape(nch, ncols, ts)
         self._count(chains, 'columns')
+
+    def _make_room_for_births(self, b_ch, b_co, stored):
+        """Before auxiliary views are installed as new views: grow the cluster slots to the largest partition about
+        to be installed and the view slots of chains that have none free (a chain can hold up to C views).  Returns
+        nv as it is before the install."""
+        dev = self.dev
+        if stored:
+            ak = dev.t['aux_K_all'][torch.from_numpy(b_ch.astype(np.int64)).to(dev.device),
+                                    torch.from_numpy(b_co.astype(np.int64)).to(dev.device)]
+        else:
+            ak = dev.t['aux_K'][torch.from_numpy(b_ch.astype(np.int64)).to(dev.device)]
+        kmax = int(ak.max().item())
+        if kmax > dev.Kcap - 1:
+            dev.grow_kcap(kmax + 1 + max(16, kmax // 8))
+        nv_before = dev.t['nv'].cpu().numpy()
+        if any(np.all(nv_before[s] > 0) for s in b_ch):
+            dev.grow_vcap(max(dev.Vcap + 8, (3 * dev.Vcap) // 2))
+            nv_before = dev.t['nv'].cpu().numpy()
+        return nv_before
 
     # ------------------------------------------------------------------ queries
     def logpdf_score(self):

@@ -204,8 +204,9 @@ class DeviceChains(object):
         t, dev = self.t, self.device
         V, K, R = self.Vcap, self.Kcap, self.R
         nviews = len(ch['view_slots'])
-        if nviews > V:
-            raise L.CgpmB200Error('chain needs %d views > Vcap=%d' % (nviews, V))
+        if nviews > V or any(v >= V for v in ch['view_slots']):
+            self.grow_vcap(max(nviews, max(ch['view_slots']) + 1))
+            V = self.Vcap
         kmax = max([len(c_) for c_ in ch['cid']] or [0])
         if kmax > K - 1:
             self.grow_kcap(kmax + 1 + max(16, kmax // 8))
@@ -346,6 +347,22 @@ class DeviceChains(object):
             self._rows_pending = None
 
     # ------------------------------------------------------------------ capacity
+    def grow_callback(self):
+        """The cc_grow_fn handed to cc_transition: re-allocates through grow_kcap / grow_vcap, which update the
+        cc_state struct in place."""
+        if getattr(self, '_grow_ref', None) is None:
+            def cb(_user, min_kcap, min_vcap):
+                try:
+                    if min_kcap > self.Kcap:
+                        self.grow_kcap(min_kcap)
+                    if min_vcap > self.Vcap:
+                        self.grow_vcap(min_vcap)
+                    return 0
+                except Exception:            # out of memory: cc_transition reports the capacity error
+                    return 1
+            self._grow_ref = L.GROW_FN(cb)
+        return self._grow_ref
+
     def grow_kcap(self, want):
         """Re-allocate the per-cluster arrays with at least `want` cluster slots per view (at most R + 1, which
         always suffices).  Slots keep their numbers; the empty-cluster record moves to the new last slot."""
@@ -372,3 +389,43 @@ class DeviceChains(object):
         for name in ('live', 'cid', 'nk', 'stat', 'cnt'):
             setattr(self.st, name, t[name].data_ptr())
         self.kcap_grown += 1
+
+    def grow_vcap(self, want):
+        """Re-allocate the per-view arrays with at least `want` view slots per chain (at most C, which always
+        suffices).  Slots keep their numbers; the auxiliary-view column of colL moves to the new last position."""
+        new = int(min(max(want, self.Vcap + 1), max(self.C, self.Vcap)))
+        old = self.Vcap
+        if new <= old:
+            return
+        t, dev = self.t, self.device
+        S_, R, K, Cn = self.S, self.R, self.Kcap, self.C
+
+        def widen(name, shape_tail, dtype, fill):
+            a = torch.full((S_, new) + shape_tail, fill, dtype=dtype, device=dev)
+            a[:, :old] = t[name]
+            t[name] = a
+        i32, f64 = torch.int32, torch.float64
+        widen('nv', (), i32, 0)
+        widen('view_id', (), i32, -1)
+        widen('view_alpha', (), f64, 1.0)
+        widen('nclu', (), i32, 0)
+        widen('rows_prog', (4,), i32, 0)
+        widen('live', (K,), i32, -1)
+        widen('cid', (K,), i32, 0)
+        widen('nk', (K,), i32, 0)
+        vg = torch.from_numpy(np.tile(self.row_alpha_grid_h, (S_, new, 1))).to(dev)
+        vg[:, :old] = t['view_grid']
+        t['view_grid'] = vg
+        for name, dt in (('zr', i32), ('order', i32), ('seq', i32), ('moved', i32), ('movedflag', torch.uint8)):
+            widen(name, (R,), dt, 0)
+        colL = torch.zeros((S_, Cn, new + 1), dtype=f64, device=dev)
+        colL[:, :, :old] = t['colL'][:, :, :old]
+        colL[:, :, new] = t['colL'][:, :, old]
+        t['colL'] = colL
+        self.Vcap = new
+        self.st.Vcap = new
+        for name in ('nv', 'view_id', 'view_alpha', 'nclu', 'rows_prog', 'live', 'cid', 'nk', 'view_grid', 'zr', 'order',
+                     'seq', 'moved', 'movedflag', 'colL'):
+            setattr(self.st, name, t[name].data_ptr())
+        self._view_cost = {}
+        self.vcap_grown = getattr(self, 'vcap_grown', 0) + 1

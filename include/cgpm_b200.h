@@ -222,6 +222,34 @@ int cc_transition_col_hypers(const cc_state* st, int n, const int32_t* chains, c
 int cc_transition_alphas(const cc_state* st, int n, const int32_t* chains, const int32_t* views,
                          const double* u, int ndraw, uint64_t seed, uint64_t counter, void* stream);
 
+/* ---- the whole kernel schedule behind one call ---------------------------------
+ * The reference's native precedent takes the kernel list and the number of steps in ONE call:
+ * LocalEngine.analyze(M_c, T, X_L, X_D, seed, kernel_list, n_steps, ...) (src/crosscat/lovecat.py:377-391,
+ * reached from State.transition_lovecat, src/crosscat/state.py:812-831).  cc_transition is that call for the
+ * device-resident state: n_iters iterations of the kernels listed (in the caller's order, State.transition /
+ * _transition_generic, state.py:727-761,866-905) over the listed chains, all rows and all columns, on the device
+ * random stream keyed by (seed, *counter); *counter is advanced once per kernel call.  A C or C++ host needs
+ * nothing else to run inference: cc_rebuild once after loading a state, then cc_transition, then the queries. */
+#define CC_K_ALPHA          0   /* 'alpha'          state.py:763-765 */
+#define CC_K_VIEW_ALPHAS    1   /* 'view_alphas'    state.py:767-772 */
+#define CC_K_COLUMN_HYPERS  2   /* 'column_hypers'  state.py:781-786 */
+#define CC_K_ROWS           3   /* 'rows'           state.py:795-802 */
+#define CC_K_COLUMNS        4   /* 'columns'        state.py:804-810; needs cc_state.arena (cc_col_aux) */
+
+/* Capacity is the caller's memory.  When a rows sweep needs more cluster slots, or a view birth needs more cluster
+ * or view slots, cc_transition synchronises the stream and calls `grow`: it must re-allocate the per-cluster /
+ * per-view arrays with at least the requested capacities (contents carried over: slots keep their numbers, the
+ * empty-cluster record of `stat` / `cnt` moves to the new last slot, the auxiliary column of colL to the new
+ * last position) and update the cc_state passed to cc_transition in place; return 0 on success.  The schedule
+ * then continues exactly where it stopped.  With grow == NULL running out of capacity returns CC_ERR_CAPACITY
+ * (never needed with Kcap = R + 1 and Vcap = C). */
+typedef int (*cc_grow_fn)(void* user, int32_t min_kcap, int32_t min_vcap);
+
+int cc_transition(cc_state* st, int n_chains, const int32_t* chains /*host*/, int n_iters, int n_kernels,
+                  const int32_t* kernels /*host, CC_K_* */, const int32_t* ci_off_dev, const int32_t* ci_adj_dev
+                  /* CSR of the independence constraints or NULL, as in cc_col_scan */, uint64_t seed,
+                  uint64_t* counter, cc_grow_fn grow, void* user, void* stream);
+
 /* ---- batched queries (src/crosscat/sampling.py:37-116) ------------------------
  * Queries are CSR: cells qoff[q]..qoff[q+1] of query q have column qcol, value
  * qval and role qrole (0 target, 1 constraint); rowid[q] is an observed rowid

@@ -173,6 +173,25 @@ def test_cluster_capacity_grows_on_the_device_stream():
     eng._ch.check_partitions()
 
 
+def test_view_capacity_grows_during_a_column_sweep():
+    """Two view slots per chain to begin with and a column CRP that wants many views (alpha = 50): the column
+    kernel's births re-allocate the per-view arrays (DeviceChains.grow_vcap) mid-sweep and the trajectory still
+    follows the oracle exactly."""
+    from helpers import small_table
+    X, cct, da = small_table(60, 13)
+    Zv = {c: c % 2 for c in range(6)}
+    eng, oracles = pair(X, cct, da, 13, S=2, Zv=Zv, alpha=50.0, Vcap=2)
+    compare(eng, oracles, 'vcap init')
+    for it in range(3):
+        eng.transition(N=1, kernels=['columns', 'rows'], progress=False)
+        for o in oracles:
+            o.transition(N=1, kernels=['columns', 'rows'])
+        compare(eng, oracles, ('vcap', it))
+    dev = eng._ch.dev
+    assert getattr(dev, 'vcap_grown', 0) > 0 and dev.Vcap > 2
+    eng._ch.check_partitions()
+
+
 def test_very_wide_views_use_the_wide_mode():
     """More than 1024 columns in a view: per-column hypers / types and the tables stay in
     global memory (rows kernel 'wide' mode); results still follow the oracle exactly."""
