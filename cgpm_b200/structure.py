@@ -90,6 +90,7 @@ def build(old, X, outputs, cctypes, distargs, grids, states, rebuild_cols=()):
                 Kcap=max(old.dev.Kcap, min(X.shape[0] + 1, 1024)), seed=old.seed, grids=grids,
                 row_alpha_grid=crp_grid(X.shape[0]), col_alpha_grid=old.dev.col_alpha_grid_h)
     ch.counter = old.counter
+    ch.device_edits = getattr(old, 'device_edits', 0)
     dev = ch.dev
     for s, fs in enumerate(states):
         spec = {'Zv': fs['Zv'], 'alpha': fs['alpha'], 'hyp': fs['hyp'],
@@ -150,8 +151,23 @@ def _dev_value(ch, i, x):
     return x
 
 
+def _on_device(ch, name, *args):
+    """Row edits run on the device (structure_dev.py) unless CGPM_B200_HOST_EDITS is set or the edit changes a
+    view's cluster list (then the general path below takes the chains through the host)."""
+    import os
+    from . import structure_dev
+    if os.environ.get('CGPM_B200_HOST_EDITS'):
+        return False
+    if getattr(structure_dev, name)(ch, *args):
+        ch.device_edits = getattr(ch, 'device_edits', 0) + 1
+        return True
+    return False
+
+
 def incorporate(ch, rowid, observation, chains=None):
     """State.incorporate (state.py:255-283) for every chain; returns the new Chains."""
+    if _on_device(ch, 'incorporate', rowid, observation):
+        return ch
     X, outputs, cctypes, distargs, grids = _schema(ch)
     R = X.shape[0]
     if rowid != R:
@@ -203,6 +219,8 @@ def incorporate(ch, rowid, observation, chains=None):
 
 def unincorporate(ch, rowid):
     """State.unincorporate (state.py:285-299)."""
+    if _on_device(ch, 'unincorporate', rowid):
+        return ch
     X, outputs, cctypes, distargs, grids = _schema(ch)
     R = X.shape[0]
     if rowid != R - 1:
@@ -228,6 +246,8 @@ def unincorporate(ch, rowid):
 
 def force_cell(ch, rowid, observation):
     """State.force_cell (state.py:302-315)."""
+    if _on_device(ch, 'force_cell', rowid, observation):
+        return ch
     X, outputs, cctypes, distargs, grids = _schema(ch)
     if not 0 <= rowid < X.shape[0]:
         raise ValueError('Force observation requires existing rowid.')

@@ -11,8 +11,13 @@ from test_gpu_transition import compare
 pytestmark = pytest.mark.gpu
 
 
-def test_incorporate_unincorporate_force_cell_dims_follow_oracle():
+@pytest.mark.parametrize('host_edits', [False, True])
+def test_incorporate_unincorporate_force_cell_dims_follow_oracle(host_edits, monkeypatch):
+    """host_edits=False: row edits run on the device (structure_dev.py: device-to-device re-sizing, statistics updated
+    in place); True: the general path through the host (CGPM_B200_HOST_EDITS).  Both must follow the oracle bit for bit."""
     from cgpm_b200.engine import Engine, gen_rng
+    if host_edits:
+        monkeypatch.setenv('CGPM_B200_HOST_EDITS', '1')
     X, cct, da = small_table(40, 3)
     S = 2
     # view 0 must exist when incorporate_dim(v=None) runs: the reference pairs its per-view
@@ -51,6 +56,7 @@ def test_incorporate_unincorporate_force_cell_dims_follow_oracle():
     for s, o in enumerate(oracles):
         assert eng._ch.rngs[s].random_sample() == o.rng.random_sample()
     assert eng.X.shape == (41, 7)
+    assert (getattr(eng._ch, 'device_edits', 0) >= 4) == (not host_edits)      # inc1, inc2, force, uninc ran on the device
     with pytest.raises(ValueError):
         eng.incorporate(50, {0: 1.0})
     with pytest.raises(ValueError):
