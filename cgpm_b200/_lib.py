@@ -13,11 +13,11 @@ LIB_PATH = os.path.join(HERE, 'libcgpm_b200.so')
 
 NGRID = 30
 NFIELD = 8
-NORMAL, CATEGORICAL = 0, 1
+NORMAL, CATEGORICAL, BERNOULLI, POISSON, EXPONENTIAL, GEOMETRIC = range(6)
 F_N, F_SX, F_SXX, F_MN, F_A, F_CST, F_GN, F_GM1 = range(8)
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY = 0, 1, 2, 3
 ROWS_DONE, ROWS_HANDOVER, ROWS_GROW = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class cc_state(C.Structure):
@@ -25,7 +25,7 @@ class cc_state(C.Structure):
         ('R', C.c_int32), ('C', C.c_int32), ('Cp', C.c_int32), ('S', C.c_int32),
         ('Vcap', C.c_int32), ('Kcap', C.c_int32), ('CT', C.c_int32), ('_pad', C.c_int32),
         ('Xrm', C.c_void_p), ('Xcm', C.c_void_p), ('ctype', C.c_void_p),
-        ('ncat', C.c_void_p), ('catoff', C.c_void_p), ('grids', C.c_void_p),
+        ('ncat', C.c_void_p), ('catoff', C.c_void_p), ('grids', C.c_void_p), ('Xaux', C.c_void_p), ('auxcol', C.c_void_p),
         ('row_alpha_grid', C.c_void_p), ('col_alpha_grid', C.c_void_p),
         ('hyp', C.c_void_p), ('zv', C.c_void_p), ('nv', C.c_void_p),
         ('view_id', C.c_void_p), ('col_alpha', C.c_void_p), ('view_alpha', C.c_void_p), ('view_grid', C.c_void_p),

@@ -12,7 +12,10 @@ from collections import OrderedDict
 
 import numpy as np
 
-HYPER_NAMES = {0: ['m', 'r', 's', 'nu'], 1: ['alpha']}
+HYPER_NAMES = {0: ['m', 'r', 's', 'nu'], 1: ['alpha'],                          # normal, categorical
+               2: ['alpha', 'beta'], 3: ['a', 'b'], 4: ['a', 'b'], 5: ['a', 'b']}       # bernoulli, poisson, exponential, geometric
+# suffstat names of State.to_metadata (get_suffstats of each primitive): (N, first sum, second sum or None)
+SUFFSTAT_NAMES = {0: ('sum_x', 'sum_x_sq'), 2: ('x_sum', None), 3: ('sum_x', 'sum_log_fact_x'), 4: ('sum_x', None), 5: ('sum_x', None)}
 
 
 def pack_chain(spec, R, C):

@@ -38,7 +38,8 @@ from .device import DeviceChains
 # lognormal (src/primitives/lognormal.py) is a normal column on log x: the device sees the transformed column, the
 # host keeps the original values, the column's own hyper grids, the -log x Jacobian of densities and scores,
 # and the reference's order of the hyperparameter dict (m, r, nu, s: lognormal.py:151-157).
-CCTYPES = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL, 'lognormal': L.NORMAL}
+CCTYPES = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL, 'lognormal': L.NORMAL, 'bernoulli': L.BERNOULLI,
+           'poisson': L.POISSON, 'exponential': L.EXPONENTIAL, 'geometric': L.GEOMETRIC}
 LOGNORMAL_HYPERS = ['m', 'r', 'nu', 's']
 
 
@@ -102,7 +103,8 @@ class Chains(object):
         distargs = [dict(d) if d else {} for d in (distargs or [None] * Cn)]
         bad = [c for c in cctypes if c not in CCTYPES]
         if bad:                                           # same rule as state.py:817-820
-            raise ValueError('Only normal, lognormal and categorical cgpms supported by cgpm_b200: %s' % (cctypes,))
+            raise ValueError('Only normal, lognormal, categorical, bernoulli, poisson, exponential and geometric cgpms '
+                             'supported by cgpm_b200: %s' % (cctypes,))
         for ct, d in zip(cctypes, distargs):
             if ct == 'categorical' and 'k' not in d:
                 raise ValueError('Categorical requires distarg `k`.')
@@ -238,7 +240,8 @@ class Chains(object):
                 else:
                     names_all[i] = self._default_hyper_order(i)
                     for n in names_all[i]:                      # dim.py:180-183
-                        hyp[i, names.index(n)] = rng.choice(dev.grids_h[i][names.index(n)])
+                        g = dev.grids_h[i][names.index(n)]
+                        hyp[i, names.index(n)] = rng.choice(g[~np.isnan(g)])     # (a grid shorter than 30 is NaN-padded)
         spec = {'Zv': [Zv_od[c] for c in self.outputs], 'views': views, 'alpha': float(alpha), 'hyp': hyp}
         dev.upload_chain(s, codec.pack_chain(spec, R, Cn))
         self.views_order[s] = list(range(len(views)))

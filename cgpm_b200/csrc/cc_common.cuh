@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <math_constants.h>
 #include "../../include/cgpm_b200.h"
 
 #define CC_LOGPI   1.1447298858494001741434273513531
@@ -163,6 +164,80 @@ __device__ __forceinline__ double categorical_marginal(double N, const double* c
     for (int j = 0; j < k; ++j) lg += lgamma(counts[j] + alpha);
     return lgamma(A) - lgamma(A + N) + lg - k * lgamma(alpha);
 }
+
+// ---------------------------------------------------------------------------
+// The other collapsed primitives ("sum types": bernoulli, poisson, exponential, geometric).  Statistics: N,
+// sum_x (CC_F_SX) and for poisson sum_log_fact_x (CC_F_SXX); two hyperparameters h0, h1 = (alpha, beta) or (a, b).
+__device__ __forceinline__ bool cc_is_sum_type(int ct) { return ct != CC_CATEGORICAL; }       // ordered-sum statistics
+__device__ __forceinline__ bool cc_is_count_type(int ct) { return ct >= CC_BERNOULLI; }
+// the values a primitive's incorporate accepts / its logpdf gives mass to (bernoulli.py:49, poisson.py:52,
+// exponential.py:50, geometric.py:50)
+__device__ __forceinline__ bool count_valid(int ct, double x) {
+    if (ct == CC_BERNOULLI) return x == 0.0 || x == 1.0;
+    if (ct == CC_EXPONENTIAL) return x >= 0.0;
+    return x >= 0.0 && x == floor(x);
+}
+__device__ __forceinline__ double cc_betaln(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+// logpdf_score of one cluster: bernoulli.py:153-155, poisson.py:155-160, exponential.py:148-153, geometric.py:148-153
+__device__ __forceinline__ double count_marginal(int ct, double N, double sx, double sxx, double h0, double h1) {
+    if (ct == CC_BERNOULLI) return cc_betaln(sx + h0, N - sx + h1) - cc_betaln(h0, h1);
+    if (ct == CC_GEOMETRIC) return cc_betaln(h0 + N, h1 + sx) - cc_betaln(h0, h1);
+    const double an = (ct == CC_POISSON) ? h0 + sx : h0 + N, bn = (ct == CC_POISSON) ? h1 + N : h1 + sx;
+    const double z = (lgamma(an) - an * log(bn)) - (lgamma(h0) - h0 * log(h1));
+    return (ct == CC_POISSON) ? z - sxx : z;
+}
+// Out-of-line copies: the lgamma calls of these primitives need a stack frame and many registers, which must not leak
+// into the kernels' normal / categorical hot paths (they run only for bernoulli / poisson / exponential / geometric cells).
+static __device__ __noinline__ double count_marginal_ni(int ct, double N, double sx, double sxx, double h0, double h1) {
+    return count_marginal(ct, N, sx, sxx, h0, h1);
+}
+// marginal of any sum type (the normal included)
+__device__ __forceinline__ double sum_marginal(int ct, double N, double sx, double sxx, double h0, double h1, double h2, double h3) {
+    return (ct == CC_NORMAL) ? normal_marginal(N, sx, sxx, h0, h1, h2, h3) : count_marginal_ni(ct, N, sx, sxx, h0, h1);
+}
+// the second accumulated term of a sum type: x*x (normal.py:69), gammaln(x+1) (poisson.py:56), nothing otherwise.
+// lf: the host's gammaln(x + 1) of the cell when it is known (Xaux), else NaN -> the device lgamma
+__device__ __forceinline__ double sum_second_term(int ct, double x, double lf) {
+    if (ct == CC_NORMAL) return __dmul_rn(x, x);
+    if (ct == CC_POISSON) return (lf == lf) ? lf : lgamma(x + 1.0);
+    return 0.0;
+}
+__device__ __forceinline__ double cell_aux(const cc_state& st, int c, int r) {
+    if (!st.Xaux || r < 0) return CUDART_NAN;
+    const int a = st.auxcol[c];
+    return (a < 0) ? CUDART_NAN : st.Xaux[(size_t)a * st.R + r];
+}
+// cached predictive constants (CC_F_MN, CC_F_A, CC_F_CST) of a sum-type cluster, so that the predictive of x is
+//   bernoulli    (x == 1 ? MN : A) - CST             MN = log(sx + alpha), A = log(N - sx + beta), CST = log(N + alpha + beta)
+//   poisson      lgamma(A + x) - (A + x) MN + CST - lgamma(x + 1)      A = a + sx, MN = log(b + N + 1), CST = A log(b + N) - lgamma(A)
+//   exponential  CST - A log(MN + x)                 A = a + N + 1, MN = b + sx, CST = log(a + N) + (a + N) log(MN)
+//   geometric    CST + lgamma(MN + x) - lgamma(A + x + 1)     MN = b + sx, A = a + N + MN, CST = log(a + N) - lgamma(MN) + lgamma(A)
+// (bernoulli.py:141-151, poisson.py:147-153, exponential.py:140-146, geometric.py:140-146 with Z(M) - Z(N) written out)
+__device__ __forceinline__ NormalCache count_cache(int ct, double N, double sx, double h0, double h1) {
+    NormalCache c;
+    if (ct == CC_BERNOULLI) { c.mn = log(sx + h0); c.a = log(N - sx + h1); c.cst = log(N + h0 + h1); }
+    else if (ct == CC_POISSON) { c.a = h0 + sx; c.mn = log(h1 + N + 1.0); c.cst = c.a * log(h1 + N) - lgamma(c.a); }
+    else if (ct == CC_EXPONENTIAL) { const double an = h0 + N; c.mn = h1 + sx; c.a = an + 1.0; c.cst = log(an) + an * log(c.mn); }
+    else { const double an = h0 + N; c.mn = h1 + sx; c.a = an + c.mn; c.cst = log(an) - lgamma(c.mn) + lgamma(c.a); }
+    return c;
+}
+__device__ __forceinline__ double count_pred_cached(int ct, double x, double mn, double a, double cst) {
+    if (!count_valid(ct, x)) return -INFINITY;
+    if (ct == CC_BERNOULLI) return ((x == 1.0) ? mn : a) - cst;
+    if (ct == CC_POISSON) return lgamma(a + x) - (a + x) * mn + cst - lgamma(x + 1.0);
+    if (ct == CC_EXPONENTIAL) return cst - a * log(mn + x);
+    return cst + lgamma(mn + x) - lgamma(a + x + 1.0);
+}
+// the same predictive straight from the statistics (a row scored against its own cluster without itself)
+__device__ __forceinline__ double count_pred_raw(int ct, double x, double N, double sx, double h0, double h1) {
+    const NormalCache c = count_cache(ct, N, sx, h0, h1);
+    return count_pred_cached(ct, x, c.mn, c.a, c.cst);
+}
+
+static __device__ __noinline__ double count_pred_cached_ni(int ct, double x, double mn, double a, double cst) { return count_pred_cached(ct, x, mn, a, cst); }
+static __device__ __noinline__ double count_pred_raw_ni(int ct, double x, double N, double sx, double h0, double h1) { return count_pred_raw(ct, x, N, sx, h0, h1); }
+static __device__ __noinline__ NormalCache count_cache_ni(int ct, double N, double sx, double h0, double h1) { return count_cache(ct, N, sx, h0, h1); }
+static __device__ __noinline__ double sum_second_term_ni(int ct, double x, double lf) { return sum_second_term(ct, x, lf); }
 
 // ---------------------------------------------------------------------------
 // warp helpers

@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                 __syncwarp();
             }
             // table sizes (only the grouped statistics pass of categorical columns needs them)
-            if (st.ctype[c] != CC_NORMAL) for (int j = lane; j < K; j += 32) Lv[0][j] = 0;
+            if (st.ctype[c] == CC_CATEGORICAL) for (int j = lane; j < K; j += 32) Lv[0][j] = 0;
             __syncwarp();
-            for (int b0 = 0; st.ctype[c] != CC_NORMAL && b0 < R; b0 += 32) {
+            for (int b0 = 0; st.ctype[c] == CC_CATEGORICAL && b0 < R; b0 += 32) {
                 const int i = b0 + lane;
                 const int k = (i < R) ? z[i] : -1;
                 const unsigned peers = __match_any_sync(0xffffffffu, k);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         }
         __syncwarp();
         const long long t1 = clock64();
-        if (member_draw && st.ctype[c] == CC_NORMAL) {
+        if (member_draw && st.ctype[c] != CC_CATEGORICAL) {      // the sum types (normal, bernoulli, poisson, exponential, geometric)
             // ---- pass 2, normal column on the device stream: rows in their natural order, one 32-byte record
             //      (sum_x, sum_x_sq, count of present cells) per table.  The lowest lane of each group of rows
             //      that share a table loads the record, adds the group's cells in row order and stores it, so
@@ -263,6 +263,9 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             if (p.write_zr == 2 && lane == 0) st.aux_K_all[(size_t)s * st.C + c] = K;
             __syncwarp();
             const double* xc = st.Xcm + (size_t)c * R;
+            const int ctq = st.ctype[c];
+            // second accumulated term: x*x for a normal column; gammaln(x+1) for poisson (a proposal weight: the device lgamma will do)
+            auto sq = [&](double v) -> double { return (ctq == CC_NORMAL) ? __dmul_rn(v, v) : sum_second_term_ni(ctq, v, CUDART_NAN); };
             for (int b0 = 0; b0 < R; b0 += 32) {
                 const int i = b0 + lane;
                 const bool act = i < R;
@@ -275,12 +278,12 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                 double sx = 0.0, sxx = 0.0, cn = 0.0;
                 if (leader) { sx = rec[4 * k]; sxx = rec[4 * k + 1]; cn = rec[4 * k + 2]; }
                 if (__all_sync(0xffffffffu, !act || peers == (1u << lane))) {
-                    if (leader && !isnan(x)) { cn += 1.0; sx = __dadd_rn(sx, x); sxx = __dadd_rn(sxx, __dmul_rn(x, x)); }
+                    if (leader && !isnan(x)) { cn += 1.0; sx = __dadd_rn(sx, x); sxx = __dadd_rn(sxx, sq(x)); }
                 } else {
                     for (int l = 0; l < 32; ++l) {
                         const int kl = __shfl_sync(0xffffffffu, k, l);
                         const double xl = __shfl_sync(0xffffffffu, x, l);
-                        if (leader && kl == k && !isnan(xl)) { cn += 1.0; sx = __dadd_rn(sx, xl); sxx = __dadd_rn(sxx, __dmul_rn(xl, xl)); }
+                        if (leader && kl == k && !isnan(xl)) { cn += 1.0; sx = __dadd_rn(sx, xl); sxx = __dadd_rn(sxx, sq(xl)); }
                     }
                 }
                 if (leader) { rec[4 * k] = sx; rec[4 * k + 1] = sxx; rec[4 * k + 2] = cn; }
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             const double* hyp = st.hyp + ((size_t)s * st.C + c) * 4;
             const double h0 = hyp[0], h1 = hyp[1], h2 = hyp[2], h3 = hyp[3];
             double lsum = 0.0;
-            for (int j = lane; j < K; j += 32) lsum += normal_marginal(rec[4 * j + 2], rec[4 * j], rec[4 * j + 1], h0, h1, h2, h3);
+            for (int j = lane; j < K; j += 32) lsum += sum_marginal(ctq, rec[4 * j + 2], rec[4 * j], rec[4 * j + 1], h0, h1, h2, h3);
             lsum = warp_sum(lsum);
             if (lane == 0) {
                 st.colL[((size_t)s * st.C + c) * (st.Vcap + 1) + st.Vcap] = lsum;
@@ -340,6 +343,7 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
         const double h0 = hyp[0], h1 = hyp[1], h2 = hyp[2], h3 = hyp[3];
         const int ctype = st.ctype[c], kc = st.ncat[c];
         const double* xc = st.Xcm + (size_t)c * R;
+        auto sq2 = [&](double v) -> double { return (ctype == CC_NORMAL) ? __dmul_rn(v, v) : sum_second_term_ni(ctype, v, CUDART_NAN); };
         double lsum = 0.0;
         const int BIG = 96;       // tables at least this large are summed by the whole warp
         for (int b0 = 0; b0 < K; b0 += 32) {
@@ -353,17 +357,17 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
                 big &= big - 1;
                 const int bb = __shfl_sync(0xffffffffu, beg, l0), ee = __shfl_sync(0xffffffffu, end, l0);
                 double N = 0.0, sx = 0.0, sxx = 0.0;
-                if (ctype == CC_NORMAL) {
+                if (ctype != CC_CATEGORICAL) {
                     for (int i0 = bb; i0 < ee; i0 += 32) {
                         const int i = i0 + lane;
                         const double xv = (i < ee) ? xc[grouped[i]] : CUDART_NAN;
                         const int cntm = min(32, ee - i0);
                         for (int l = 0; l < cntm; ++l) {
                             const double v = __shfl_sync(0xffffffffu, xv, l);
-                            if (!isnan(v)) { N += 1.0; sx = __dadd_rn(sx, v); sxx = __dadd_rn(sxx, __dmul_rn(v, v)); }
+                            if (!isnan(v)) { N += 1.0; sx = __dadd_rn(sx, v); sxx = __dadd_rn(sxx, sq2(v)); }
                         }
                     }
-                    if (lane == 0) lsum += normal_marginal(N, sx, sxx, h0, h1, h2, h3);
+                    if (lane == 0) lsum += sum_marginal(ctype, N, sx, sxx, h0, h1, h2, h3);
                 } else {
                     uint32_t lc[CC_MAXCAT];
                     for (int q = 0; q < kc; ++q) lc[q] = 0;
@@ -384,20 +388,20 @@ __global__ void __launch_bounds__(128) aux_kernel(const AuxParams p) {
             }
             if (j >= K || end - beg >= BIG) continue;
             double N = 0.0, sx = 0.0, sxx = 0.0;
-            if (ctype == CC_NORMAL) {
+            if (ctype != CC_CATEGORICAL) {
                 int i = beg;
                 for (; i + 4 <= end; i += 4) {
                     const double x0 = xc[grouped[i]], x1 = xc[grouped[i + 1]], x2 = xc[grouped[i + 2]], x3 = xc[grouped[i + 3]];
-                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
-                    if (!isnan(x1)) { N += 1.0; sx = __dadd_rn(sx, x1); sxx = __dadd_rn(sxx, __dmul_rn(x1, x1)); }
-                    if (!isnan(x2)) { N += 1.0; sx = __dadd_rn(sx, x2); sxx = __dadd_rn(sxx, __dmul_rn(x2, x2)); }
-                    if (!isnan(x3)) { N += 1.0; sx = __dadd_rn(sx, x3); sxx = __dadd_rn(sxx, __dmul_rn(x3, x3)); }
+                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, sq2(x0)); }
+                    if (!isnan(x1)) { N += 1.0; sx = __dadd_rn(sx, x1); sxx = __dadd_rn(sxx, sq2(x1)); }
+                    if (!isnan(x2)) { N += 1.0; sx = __dadd_rn(sx, x2); sxx = __dadd_rn(sxx, sq2(x2)); }
+                    if (!isnan(x3)) { N += 1.0; sx = __dadd_rn(sx, x3); sxx = __dadd_rn(sxx, sq2(x3)); }
                 }
                 for (; i < end; ++i) {
                     const double x0 = xc[grouped[i]];
-                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                    if (!isnan(x0)) { N += 1.0; sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, sq2(x0)); }
                 }
-                lsum += normal_marginal(N, sx, sxx, h0, h1, h2, h3);
+                lsum += sum_marginal(ctype, N, sx, sxx, h0, h1, h2, h3);
             } else {
                 uint32_t lc[CC_MAXCAT];
                 for (int q = 0; q < kc; ++q) lc[q] = 0;

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(NW * 32) col_hyper_kernel(const HyperParams p)
     __shared__ double s_lp[32];
     __shared__ double s_h[4];
     __shared__ int s_ord[4];
-    const int nh = (ctype == CC_NORMAL) ? 4 : 1;
+    const int nh = (ctype == CC_NORMAL) ? 4 : (ctype == CC_CATEGORICAL) ? 1 : 2;      // m r s nu | alpha | (alpha beta) or (a b)
     const Philox rng(p.seed);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) s_h[i] = hyp[i];
@@ -82,11 +82,12 @@ __global__ void __launch_bounds__(NW * 32) col_hyper_kernel(const HyperParams p)
             for (int pos = lane; pos < K; pos += 32) {
                 const int k = live[pos];
                 const size_t e = (size_t)k * C + c;
-                if (ctype == CC_NORMAL) acc += normal_marginal(fN[e], fSX[e], fSXX[e], hh[0], hh[1], hh[2], hh[3]);
+                if (ctype != CC_CATEGORICAL) acc += sum_marginal(ctype, fN[e], fSX[e], fSXX[e], hh[0], hh[1], hh[2], hh[3]);
                 else acc += categorical_marginal(fN[e], st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[c], kc, hh[0]);
             }
             acc = warp_sum(acc);
-            if (lane == 0) s_lp[g] = acc;
+            // a grid shorter than CC_NGRID is padded with NaN (poisson.py:122-124): no mass there
+            if (lane == 0) s_lp[g] = (hh[h] == hh[h]) ? acc : -INFINITY;
         }
         __syncthreads();
         if (warp == 0) {
@@ -118,6 +119,13 @@ __global__ void __launch_bounds__(NW * 32) col_hyper_kernel(const HyperParams p)
             stat_field(st, s, CC_F_CST)[e] = cc.cst;
             stat_field(st, s, CC_F_GN)[e] = gN;
             stat_field(st, s, CC_F_GM1)[e] = gM1;
+            if (pos >= K) { stat_field(st, s, CC_F_N)[e] = 0.0; stat_field(st, s, CC_F_SX)[e] = 0.0; stat_field(st, s, CC_F_SXX)[e] = 0.0; }
+        } else if (ctype != CC_CATEGORICAL) {
+            const double sx = (pos < K) ? fSX[e] : 0.0;
+            const NormalCache cc = count_cache_ni(ctype, N, sx, h0, h1);
+            stat_field(st, s, CC_F_MN)[e] = cc.mn;
+            stat_field(st, s, CC_F_A)[e] = cc.a;
+            stat_field(st, s, CC_F_CST)[e] = cc.cst;
             if (pos >= K) { stat_field(st, s, CC_F_N)[e] = 0.0; stat_field(st, s, CC_F_SX)[e] = 0.0; stat_field(st, s, CC_F_SXX)[e] = 0.0; }
         } else {
             stat_field(st, s, CC_F_CST)[e] = log(N + h0 * kc);

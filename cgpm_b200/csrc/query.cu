@@ -20,6 +20,8 @@ __device__ double cell_logpdf(const cc_state& st, int s, int c, int k, double x)
     if (st.ctype[c] == CC_NORMAL)
         return normal_predictive_cached(x, stat_field(st, s, CC_F_MN)[e], stat_field(st, s, CC_F_A)[e],
                                         stat_field(st, s, CC_F_CST)[e], (k < 0) ? 0.0 : stat_field(st, s, CC_F_N)[e], hyp[3]);
+    if (st.ctype[c] != CC_CATEGORICAL)       // bernoulli.py:62-68, poisson.py:68-74, exponential.py:60-66, geometric.py:60-66
+        return count_pred_cached_ni(st.ctype[c], x, stat_field(st, s, CC_F_MN)[e], stat_field(st, s, CC_F_A)[e], stat_field(st, s, CC_F_CST)[e]);
     const int kc = st.ncat[c];
     if (!(x == floor(x) && x >= 0 && x < kc)) return -INFINITY;            // categorical.py:71-72
     const double a = hyp[0];
@@ -148,6 +150,17 @@ struct Rng {                      // per-thread Philox stream
         if (u1 < 1e-300) u1 = 1e-300;
         return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
     }
+    __device__ double poisson(double lam) {   // Knuth's product of uniforms in chunks of rate <= 30 (sums of Poissons are Poisson)
+        double x = 0.0;
+        while (lam > 0.0) {
+            const double l = fmin(lam, 30.0);
+            lam -= l;
+            const double lim = exp(-l);
+            double prod = uniform();
+            while (prod > lim) { x += 1.0; prod *= uniform(); }
+        }
+        return x;
+    }
     __device__ double gamma(double a) {   // Marsaglia-Tsang (2000), shape a, scale 1
         if (a < 1.0) {
             const double u = uniform();
@@ -267,6 +280,25 @@ __global__ void __launch_bounds__(128) simulate_kernel(const SimParams p) {
             const double rho = rng.gamma(nun * 0.5) * (2.0 / sn);          // normal.py:202-206
             const double mu = mn + rng.normal() / sqrt(rho * rn);
             x = mu + rng.normal() / sqrt(rho);                             // normal.py:93
+        } else if (st.ctype[c] != CC_CATEGORICAL) {
+            const int ct = st.ctype[c];
+            const double N = (k < 0) ? 0.0 : stat_field(st, s, CC_F_N)[e];
+            const double sx = (k < 0) ? 0.0 : stat_field(st, s, CC_F_SX)[e];
+            if (ct == CC_BERNOULLI) {                                      // bernoulli.py:70-80
+                x = (rng.uniform() * (N + hyp[0] + hyp[1]) < sx + hyp[0]) ? 1.0 : 0.0;
+            } else if (ct == CC_POISSON) {                                 // poisson.py:76-84: negative_binomial(an, bn / (bn + 1))
+                const double an = hyp[0] + sx, bn = hyp[1] + N;
+                x = rng.poisson(rng.gamma(an) / bn);                       //   = Poisson(Gamma(an, scale (1 - p) / p)), p = bn / (bn + 1)
+            } else if (ct == CC_EXPONENTIAL) {                             // exponential.py:68-77
+                const double mu = rng.gamma(hyp[0] + N) / (hyp[1] + sx);
+                double u = rng.uniform();
+                x = -log(u > 0 ? u : 1e-300) / mu;
+            } else {                                                       // geometric.py:68-75: geometric(pn) - 1, pn ~ Beta(an, bn)
+                const double ga = rng.gamma(hyp[0] + N), gb = rng.gamma(hyp[1] + sx);
+                const double pn = ga / (ga + gb);
+                double u = rng.uniform();
+                x = (pn >= 1.0) ? 0.0 : floor(log(u > 0 ? u : 1e-300) / log1p(-pn));
+            }
         } else {
             const int kc = st.ncat[c];
             const double a = hyp[0];

@@ -51,7 +51,24 @@
 #include "cc_common.cuh"
 #include "rows_common.cuh"
 
+// This file is compiled twice: as rows.cu (CC_ROWS_COUNT 0: normal and categorical columns only -- the hot
+// configuration, kept free of the other primitives' lgamma calls, which cost registers and a stack frame) and through
+// rows_counts.cu (CC_ROWS_COUNT 1: tables that also hold bernoulli / poisson / exponential / geometric columns).
+#ifndef CC_ROWS_COUNT
+#define CC_ROWS_COUNT 0
+#endif
+#if CC_ROWS_COUNT
+#define CC_ROWS_ENTRY cc_transition_rows_counts
+#else
+#define CC_ROWS_ENTRY cc_transition_rows
+extern "C" int cc_transition_rows_counts(const cc_state* st, int n_work, const cc_row_work* work, const int32_t* perm,
+                                         const double* u, double* trace, int trace_stride, uint64_t seed, uint64_t counter,
+                                         void* stream_);
+#endif
+
 namespace {
+
+constexpr bool CTS = CC_ROWS_COUNT != 0;
 
 enum { ST_OK = 0, ST_HANDOVER = CC_ROWS_HANDOVER, ST_GROW = CC_ROWS_GROW, ST_MIGRATE = 3 };
 
@@ -114,6 +131,26 @@ __device__ __forceinline__ void apply_move(const Ctx& c, const Tab<GT>& T, int r
             T.at(CC_F_N, k, j) = N; T.at(CC_F_SX, k, j) = sx; T.at(CC_F_SXX, k, j) = sxx;
             T.at(CC_F_MN, k, j) = cc.mn; T.at(CC_F_A, k, j) = cc.a; T.at(CC_F_CST, k, j) = cc.cst;
             T.at(CC_F_GN, k, j) = gN; T.at(CC_F_GM1, k, j) = gM1;
+        } else if (CTS && ct != CC_CATEGORICAL) {
+            if constexpr (CTS) {
+                // sum types: N, sum_x and (poisson) sum_log_fact_x by the reference's -= / += (bernoulli.py:46-58,
+                // poisson.py:49-63, exponential.py:47-58, geometric.py:47-58), then the cached constants
+                const double h0 = hyper(c, wide, ghyp, 0, j), h1 = hyper(c, wide, ghyp, 1, j);
+                const bool fresh = !is_old && newc;
+                if (isnan_x && !fresh) continue;
+                double N = fresh ? 0.0 : T.at(CC_F_N, k, j), sx = fresh ? 0.0 : T.at(CC_F_SX, k, j), sxx = fresh ? 0.0 : T.at(CC_F_SXX, k, j);
+                if (!isnan_x) {
+                    const double t2 = sum_second_term_ni(ct, x, cell_aux(c.st, c.col[j], r));
+                    if (is_old) {       // scored against its own cluster first (-= x, += x), then removed
+                        N -= 1.0;
+                        sx = __dsub_rn(__dadd_rn(__dsub_rn(sx, x), x), x);
+                        sxx = __dsub_rn(__dadd_rn(__dsub_rn(sxx, t2), t2), t2);
+                    } else { N += 1.0; sx = __dadd_rn(sx, x); sxx = __dadd_rn(sxx, t2); }
+                }
+                const NormalCache cc = count_cache_ni(ct, N, sx, h0, h1);
+                T.at(CC_F_N, k, j) = N; T.at(CC_F_SX, k, j) = sx; T.at(CC_F_SXX, k, j) = sxx;
+                T.at(CC_F_MN, k, j) = cc.mn; T.at(CC_F_A, k, j) = cc.a; T.at(CC_F_CST, k, j) = cc.cst;
+            }
         } else {
             const double a = hyper(c, wide, ghyp, 0, j);
             const int kc = wide ? c.st.ncat[c.col[j]] : c.ncat[j];
@@ -221,14 +258,28 @@ __device__ __forceinline__ void apply_move(const Ctx& c, const Tab<GT>& T, int r
 // The row stays, but `-= x; += x` changed its cluster's sums in the last bit (view.py:416-419):
 // store them and refresh the cached constants.  All NT consumer threads.
 template <int NT, bool GT>
-__device__ __forceinline__ void apply_drift(const Ctx& c, const Tab<GT>& T, int z, const double* xrow) {
+__device__ __forceinline__ void apply_drift(const Ctx& c, const Tab<GT>& T, int z, int r, const double* xrow) {
     const bool wide = c.wide != 0;
     const double* ghyp = c.st.hyp + (size_t)c.s * c.st.C * 4;
     for (int j = threadIdx.x; j < c.D; j += NT) {
         const int ct = wide ? c.st.ctype[c.col[j]] : c.ctype[j];
-        if (ct != CC_NORMAL) continue;
+        if (ct == CC_CATEGORICAL) continue;
         const double x = xrow[c.bulk ? c.col[j] : j];
         if (isnan(x)) continue;
+        if (ct != CC_NORMAL) {
+            if constexpr (CTS) {
+                const double sx0 = T.at(CC_F_SX, z, j), sxx0 = T.at(CC_F_SXX, z, j);
+                const double t2 = sum_second_term_ni(ct, x, cell_aux(c.st, c.col[j], r));
+                const double sx2 = __dadd_rn(__dsub_rn(sx0, x), x), sxx2 = __dadd_rn(__dsub_rn(sxx0, t2), t2);
+                if (sx2 != sx0 || sxx2 != sxx0) {
+                    T.at(CC_F_SX, z, j) = sx2;
+                    T.at(CC_F_SXX, z, j) = sxx2;
+                    const NormalCache c2 = count_cache_ni(ct, T.at(CC_F_N, z, j), sx2, hyper(c, wide, ghyp, 0, j), hyper(c, wide, ghyp, 1, j));
+                    T.at(CC_F_MN, z, j) = c2.mn; T.at(CC_F_A, z, j) = c2.a; T.at(CC_F_CST, z, j) = c2.cst;
+                }
+            }
+            continue;
+        }
         const double sx0 = T.at(CC_F_SX, z, j), sxx0 = T.at(CC_F_SXX, z, j);
         const double xx = __dmul_rn(x, x);
         const double sx2 = __dadd_rn(__dsub_rn(sx0, x), x), sxx2 = __dadd_rn(__dsub_rn(sxx0, xx), xx);
@@ -243,11 +294,35 @@ __device__ __forceinline__ void apply_drift(const Ctx& c, const Tab<GT>& T, int 
 }
 
 // One cell of a row against one candidate cluster (normal or categorical column j of the view).
+// Sum-type cell (bernoulli, poisson, exponential, geometric): the cached form against any other cluster (a lone member's
+// own cluster without the row is the empty cluster: ke), the statistics with the row removed against its own
+// (view.py:416-419), reporting in `drift` whether -= x, += x returns different sums.
+template <bool GT>
+__device__ __forceinline__ double count_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp, const double* xrow,
+                                             int ct, int j, int k, int ke, bool own, bool dn, int r, int& drift) {
+    const double x = xrow[c.bulk ? c.col[j] : j];
+    if (isnan(x)) return 0.0;
+    if (own) {
+        const double sx0 = T.at(CC_F_SX, k, j), sxx0 = T.at(CC_F_SXX, k, j);
+        const double t2 = sum_second_term_ni(ct, x, cell_aux(c.st, c.col[j], r));
+        const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, t2);
+        if (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, t2) != sxx0) drift = 1;
+        if (dn) return count_pred_raw_ni(ct, x, T.at(CC_F_N, k, j) - 1.0, sx1, hyper(c, wide, ghyp, 0, j), hyper(c, wide, ghyp, 1, j));
+    }
+    return count_pred_cached_ni(ct, x, T.at(CC_F_MN, ke, j), T.at(CC_F_A, ke, j), T.at(CC_F_CST, ke, j));
+}
+
+// CTS: the table has sum-type columns other than normal (compiled out otherwise: their lgamma calls cost the
+// all-normal / categorical paths registers and a stack frame)
 template <bool GT>
 __device__ __forceinline__ double cell_term(const Ctx& c, const Tab<GT>& T, bool wide, bool allnorm, const double* ghyp,
-                                            const double* xrow, int j, int k, int ke, bool own, bool dn, bool empty, int& drift) {
-    if (allnorm || (wide ? c.st.ctype[c.col[j]] : c.ctype[j]) == CC_NORMAL)
-        return normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
+                                            const double* xrow, int j, int k, int ke, bool own, bool dn, bool empty, int r, int& drift) {
+    if (allnorm) return normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
+    const int ct = wide ? c.st.ctype[c.col[j]] : c.ctype[j];
+    if (ct == CC_NORMAL) return normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
+    if constexpr (CTS) {
+        if (ct != CC_CATEGORICAL) return count_term<GT>(c, T, wide, ghyp, xrow, ct, j, k, ke, own, dn, r, drift);
+    }
     return categorical_term<GT>(c, T, wide, ghyp, xrow, j, k, own, empty);
 }
 
@@ -396,10 +471,10 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                     // two columns per trip: independent chains, so the two logs overlap
                     int j = cc;
                     for (; j + gc < D; j += 2 * gc) {
-                        acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, drift);
-                        acc2 += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j + gc, k, ke, own, dn, pc >= K, drift);
+                        acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
+                        acc2 += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j + gc, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
                     }
-                    if (j < D) acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, drift);
+                    if (j < D) acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
                     acc += acc2;
                 }
                 for (int o = gc >> 1; o > 0; o >>= 1) {
@@ -511,7 +586,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
             }
             const double* xs = c.x + (size_t)((istar - c.base) & RBm) * c.xstride;
             if (kind == 1) apply_move<NT, GT, false>(c, T, c.rowidx[(istar - c.base) & RBm], zs, zb, newc, nkz == 1, ownpos, K, nkz, xs);
-            else apply_drift<NT, GT>(c, T, zs, xs);
+            else apply_drift<NT, GT>(c, T, zs, CTS ? c.rowidx[(istar - c.base) & RBm] : -1, xs);
             start = istar + 1;
             consumer_sync<NT>();
             if (tid == 0) release_upto(start);       // after the barrier: the mover's cells were read from the ring
@@ -542,10 +617,10 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
             if (active) {
                 int j = glL;
                 for (; j + G < D; j += 2 * G) {
-                    acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, drift);
-                    acc2 += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j + G, k, ke, own, dn, pc >= K, drift);
+                    acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
+                    acc2 += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j + G, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
                 }
-                if (j < D) acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, drift);
+                if (j < D) acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
                 acc += acc2;
             }
             for (int o = G >> 1; o > 0; o >>= 1) {
@@ -688,7 +763,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
             }
             apply_move<NT, GT, BIG>(c, T, r, z, zb, newc, singleton, ownpos, K, nkz, xrow);
         } else if (drifted) {
-            apply_drift<NT, GT>(c, T, z, xrow);
+            apply_drift<NT, GT>(c, T, z, r, xrow);
         }
         start = i + 1;
         if (zb != z || drifted) consumer_sync<NT>();
@@ -1072,7 +1147,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
 
 }  // namespace
 
-extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_work* work,
+extern "C" int CC_ROWS_ENTRY(const cc_state* st, int n_work, const cc_row_work* work,
                                   const int32_t* perm, const double* u, double* trace, int trace_stride,
                                   uint64_t seed, uint64_t counter, void* stream_) {
     if (!st || n_work < 0 || (n_work > 0 && !work)) { cc_set_error("cc_transition_rows: bad arguments"); return CC_ERR_ARG; }
@@ -1111,7 +1186,16 @@ extern "C" int cc_transition_rows(const cc_state* st, int n_work, const cc_row_w
     double* big_lp = nullptr;
     CC_CUDA(cudaMallocAsync(&dwork, sizeof(cc_row_work) * n_work, stream));
     CC_CUDA(cudaMemcpyAsync(dwork, sorted.data(), sizeof(cc_row_work) * n_work, cudaMemcpyHostToDevice, stream));
+    std::vector<int32_t> ctype_h(st->C);
+    CC_CUDA(cudaMemcpyAsync(ctype_h.data(), st->ctype, sizeof(int32_t) * st->C, cudaMemcpyDeviceToHost, stream));
     CC_CUDA(cudaStreamSynchronize(stream));            // `sorted` is a local; n_work is small
+#if !CC_ROWS_COUNT
+    for (int c = 0; c < st->C; ++c)                    // bernoulli / poisson / exponential / geometric columns: the other build
+        if (ctype_h[c] >= CC_BERNOULLI) {
+            CC_CUDA(cudaFreeAsync(dwork, stream));
+            return cc_transition_rows_counts(st, n_work, work, perm, u, trace, trace_stride, seed, counter, stream_);
+        }
+#endif
 
     const int Ksm_env = getenv("CGPM_B200_ROWS_KSM") ? atoi(getenv("CGPM_B200_ROWS_KSM")) : 0;
     const int Ksm = std::max(4, std::min(st->Kcap, Ksm_env > 0 ? Ksm_env : 1024));

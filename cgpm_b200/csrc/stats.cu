@@ -200,6 +200,11 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
         if (warp == 0 && act) st.colL[((size_t)s * C + c) * (st.Vcap + 1) + v] = tot;
         return;
     }
+    const bool sumt = ctype != CC_CATEGORICAL;       // ordered sums N, sum_x and a second term (x*x | gammaln(x+1) | none)
+    const double* aux = (act && ctype == CC_POISSON && st.Xaux && st.auxcol[c] >= 0) ? st.Xaux + (size_t)st.auxcol[c] * R : nullptr;
+    auto second = [&](double x, int r) -> double {
+        return (ctype == CC_NORMAL) ? __dmul_rn(x, x) : sum_second_term_ni(ctype, x, aux ? aux[r] : CUDART_NAN);
+    };
     double lacc = 0.0;     // MARGINAL: this warp's partial over its clusters
     for (int pos = warp; pos < K + (p.marginal ? 0 : 1); pos += NW) {
         // pos == K (TABLE mode): the prior (empty-cluster) record at slot Kcap-1
@@ -238,6 +243,10 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
                         if (!isnan(xv[q])) { N += 1.0; sx = __dadd_rn(sx, xv[q]); sxx = __dadd_rn(sxx, __dmul_rn(xv[q], xv[q])); }
+                } else if (sumt) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (!isnan(xv[q])) { N += 1.0; sx = __dadd_rn(sx, xv[q]); sxx = __dadd_rn(sxx, second(xv[q], rr[q])); }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
                 const double x0 = X[(size_t)r0 * Cp];
                 if (!isnan(x0)) {
                     N += 1.0;
-                    if (ctype == CC_NORMAL) { sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, __dmul_rn(x0, x0)); }
+                    if (sumt) { sx = __dadd_rn(sx, x0); sxx = __dadd_rn(sxx, second(x0, r0)); }
                     else lc[(int)x0]++;
                 }
             }
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
         if (!act) continue;
         if (p.marginal) {
             double mg;
-            if (ctype == CC_NORMAL) mg = normal_marginal(N, sx, sxx, h0, h1, h2, h3);
+            if (sumt) mg = sum_marginal(ctype, N, sx, sxx, h0, h1, h2, h3);
             else {
                 const double A = kc * h0;
                 double lg = 0.0;
@@ -281,6 +290,15 @@ __global__ void __launch_bounds__(NW * 32) stats_kernel(const StatsParams p) {
                 stat_field(st, s, CC_F_CST)[e] = cc.cst;
                 stat_field(st, s, CC_F_GN)[e] = gN;
                 stat_field(st, s, CC_F_GM1)[e] = gM1;
+            } else if (sumt) {
+                const NormalCache cc = count_cache_ni(ctype, N, sx, h0, h1);
+                stat_field(st, s, CC_F_SX)[e] = sx;
+                stat_field(st, s, CC_F_SXX)[e] = sxx;
+                stat_field(st, s, CC_F_MN)[e] = cc.mn;
+                stat_field(st, s, CC_F_A)[e] = cc.a;
+                stat_field(st, s, CC_F_CST)[e] = cc.cst;
+                stat_field(st, s, CC_F_GN)[e] = 0.0;
+                stat_field(st, s, CC_F_GM1)[e] = 0.0;
             } else {
                 stat_field(st, s, CC_F_SX)[e] = 0.0;
                 stat_field(st, s, CC_F_SXX)[e] = 0.0;
@@ -358,9 +376,9 @@ __global__ void __launch_bounds__(NT) score_kernel(const cc_state st, double* __
             const double* hyp = st.hyp + ((size_t)s * C + c) * 4;
             const size_t idx = (size_t)k * C + c;
             const double N = stat_field(st, s, CC_F_N)[idx];
-            if (st.ctype[c] == CC_NORMAL)
-                acc += normal_marginal(N, stat_field(st, s, CC_F_SX)[idx], stat_field(st, s, CC_F_SXX)[idx],
-                                       hyp[0], hyp[1], hyp[2], hyp[3]);
+            if (st.ctype[c] != CC_CATEGORICAL)
+                acc += sum_marginal(st.ctype[c], N, stat_field(st, s, CC_F_SX)[idx], stat_field(st, s, CC_F_SXX)[idx],
+                                    hyp[0], hyp[1], hyp[2], hyp[3]);
             else
                 acc += categorical_marginal(N, st.cnt + ((size_t)s * Kcap + k) * CT + st.catoff[c], st.ncat[c], hyp[0]);
         }
@@ -402,6 +420,11 @@ __global__ void refresh_kernel(const cc_state st, int n_work, const int32_t* __r
             stat_field(st, s, CC_F_CST)[idx] = cc.cst;
             stat_field(st, s, CC_F_GN)[idx] = gN;
             stat_field(st, s, CC_F_GM1)[idx] = gM1;
+        } else if (st.ctype[c] != CC_CATEGORICAL) {
+            const NormalCache cc = count_cache_ni(st.ctype[c], N, stat_field(st, s, CC_F_SX)[idx], hyp[0], hyp[1]);
+            stat_field(st, s, CC_F_MN)[idx] = cc.mn;
+            stat_field(st, s, CC_F_A)[idx] = cc.a;
+            stat_field(st, s, CC_F_CST)[idx] = cc.cst;
         } else {
             stat_field(st, s, CC_F_CST)[idx] = log(N + hyp[0] * st.ncat[c]);
         }

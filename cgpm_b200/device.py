@@ -36,9 +36,50 @@ def hyper_grids(xcol, ctype, n_grid=L.NGRID):
         g[1] = log_linspace(1. / N, N, n_grid)
         g[2] = log_linspace(ssqdev / 100., ssqdev, n_grid)
         g[3] = log_linspace(1., N, n_grid)
-    else:
+    elif ctype == L.CATEGORICAL:
         g[0] = log_linspace(1., float(len(X)), n_grid)
+    elif ctype == L.BERNOULLI:                                   # bernoulli.py:107-112
+        g[0] = log_linspace(1., float(len(X)), n_grid)
+        g[1] = log_linspace(1., float(len(X)), n_grid)
+    elif ctype == L.POISSON:                                     # poisson.py:119-126: integers only, possibly fewer than n_grid
+        a = np.unique(np.round(np.linspace(1, len(X), n_grid)))
+        g[0] = np.nan
+        g[0, :len(a)] = a
+        g[1] = log_linspace(.1, float(len(X)), n_grid)
+    elif ctype == L.EXPONENTIAL:                                 # exponential.py:109-114
+        g[0] = log_linspace(.5, float(len(X)), n_grid)
+        g[1] = log_linspace(.5, float(len(X)), n_grid)
+    elif ctype == L.GEOMETRIC:                                   # geometric.py:105-110
+        g[0] = log_linspace(1, float(len(X)) / 2., n_grid)
+        g[1] = log_linspace(.1, float(len(X)) / 2., n_grid)
+    else:
+        raise ValueError('unknown column type %s' % (ctype,))
     return g
+
+
+COUNT_NAMES = {L.BERNOULLI: 'Bernoulli', L.POISSON: 'Poisson', L.EXPONENTIAL: 'Exponential', L.GEOMETRIC: 'Geometric'}
+
+
+def count_valid(ctype, col):
+    """Values the primitive's incorporate accepts (bernoulli.py:49, poisson.py:52, exponential.py:50, geometric.py:50);
+    NaN cells are never incorporated."""
+    col = np.asarray(col, dtype=np.float64)
+    nan = np.isnan(col)
+    if ctype == L.BERNOULLI:
+        return nan | (col == 0) | (col == 1)
+    if ctype == L.EXPONENTIAL:
+        return nan | (col >= 0)
+    return nan | ((col % 1 == 0) & (col >= 0))
+
+
+def log_fact(col):
+    """gammaln(x + 1) of every cell as the reference adds it to sum_log_fact_x (poisson.py:56; scipy.special.gammaln)."""
+    from scipy.special import gammaln
+    col = np.asarray(col, dtype=np.float64)
+    out = np.full(col.shape, np.nan)
+    ok = ~np.isnan(col)
+    out[ok] = gammaln(col[ok] + 1)
+    return out
 
 
 def crp_grid(n, n_grid=L.NGRID):
@@ -94,6 +135,10 @@ class DeviceChains(object):
                 if not np.all(ok):      # categorical.py:56-57
                     bad = col[~ok][0]
                     raise ValueError('Invalid Categorical(%d): %s' % (ncat[c], bad))
+            elif ctype[c] in COUNT_NAMES:
+                ok = count_valid(ctype[c], X[:, c])
+                if not np.all(ok):
+                    raise ValueError('Invalid %s: %s' % (COUNT_NAMES[ctype[c]], X[:, c][~ok][0]))
         self.device = torch.device('cuda', torch.cuda.current_device()) \
             if device is None else torch.device(device)
         self.R, self.C, self.S = R, Cn, int(S)
@@ -128,6 +173,14 @@ class DeviceChains(object):
         t['ncat'] = torch.from_numpy(ncat).to(dev)
         t['catoff'] = torch.from_numpy(catoff).to(dev)
         t['grids'] = torch.from_numpy(self.grids_h).to(dev)
+        # per-cell constants of the poisson columns: gammaln(x + 1) exactly as the host computes it
+        self.aux_cols = [c for c in range(Cn) if ctype[c] == L.POISSON]
+        auxcol = np.full(Cn, -1, np.int32)
+        auxcol[self.aux_cols] = np.arange(len(self.aux_cols))
+        self.auxcol_h = auxcol
+        if self.aux_cols:
+            t['Xaux'] = torch.from_numpy(np.ascontiguousarray(np.stack([log_fact(X[:, c]) for c in self.aux_cols]))).to(dev)
+            t['auxcol'] = torch.from_numpy(auxcol).to(dev)
         t['row_alpha_grid'] = torch.from_numpy(self.row_alpha_grid_h).to(dev)
         t['col_alpha_grid'] = torch.from_numpy(self.col_alpha_grid_h).to(dev)
         S_, V, K = self.S, self.Vcap, self.Kcap
@@ -167,6 +220,8 @@ class DeviceChains(object):
                      'nclu', 'live', 'cid', 'nk', 'zr', 'order', 'stat', 'cnt', 'err', 'rows_prog', 'seq',
                      'moved', 'movedflag', 'colL', 'aux_zr', 'aux_K', 'aux_alpha', 'aux_K_all'):
             setattr(st, name, t[name].data_ptr())
+        st.Xaux = t['Xaux'].data_ptr() if self.aux_cols else None
+        st.auxcol = t['auxcol'].data_ptr() if self.aux_cols else None
         st.arena = None
         st.arena_bytes = 0
         st.aux_zr_all = None

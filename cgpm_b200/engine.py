@@ -5,8 +5,9 @@ cgpm.crosscat.state.State (src/crosscat/state.py:44-1284) for the inference hot
 path: construction ("initialize"), transition(N, S, kernels, rowids, cols,
 views, progress, checkpoint, statenos), logpdf_score, dependence probability,
 logpdf / simulate (bulk), and the metadata / pickle round trip ("serialize").
-Same names, argument meaning and error behaviour; only `normal` and
-`categorical` columns are accepted (the rule lovecat applies, state.py:817-822).
+Same names, argument meaning and error behaviour; the collapsed primitives are accepted as
+column types (normal, lognormal, categorical, bernoulli, poisson, exponential, geometric); conditional and foreign
+cgpms are not (the rule lovecat applies more narrowly, state.py:817-822).
 The reference's process fan-out (utils/parallel_map.py) is replaced by one CUDA
 launch over all chains; `multiprocess` is accepted and ignored.
 
@@ -76,17 +77,22 @@ def _chain_metadata(ch, s, X_list=None):
         for pos, k in enumerate(vw['live']):
             cid = int(vw['cid'][pos])
             N = float(dl['stat'][L.F_N, k, i])
-            if ch.ctype[i] == L.NORMAL:
-                sx, sxx = (('sum_log_x', 'sum_log_x_sq') if ch.lognormal[i] else ('sum_x', 'sum_x_sq'))
-                items.append((cid, {'N': N, sx: float(dl['stat'][L.F_SX, k, i]),
-                                    sxx: float(dl['stat'][L.F_SXX, k, i])}))
+            if ch.ctype[i] != L.CATEGORICAL:
+                sx, sxx = (('sum_log_x', 'sum_log_x_sq') if ch.lognormal[i] else codec.SUFFSTAT_NAMES[int(ch.ctype[i])])
+                d = {'N': N, sx: float(dl['stat'][L.F_SX, k, i])}
+                if sxx is not None:
+                    d[sxx] = float(dl['stat'][L.F_SXX, k, i])
+                items.append((cid, d))
             else:
                 o0 = ch.dev.catoff_h[i]
                 items.append((cid, {'N': int(N), 'counts': [float(x) for x in dl['cnt'][k, o0:o0 + ch.ncat[i]]]}))
         top = max(int(c) for c in vw['cid']) + 1
-        if ch.ctype[i] == L.NORMAL:
-            sx, sxx = (('sum_log_x', 'sum_log_x_sq') if ch.lognormal[i] else ('sum_x', 'sum_x_sq'))
-            items.append((top, {'N': 0, sx: 0, sxx: 0}))
+        if ch.ctype[i] != L.CATEGORICAL:
+            sx, sxx = (('sum_log_x', 'sum_log_x_sq') if ch.lognormal[i] else codec.SUFFSTAT_NAMES[int(ch.ctype[i])])
+            d = {'N': 0, sx: 0}
+            if sxx is not None:
+                d[sxx] = 0
+            items.append((top, d))
         else:
             items.append((top, {'N': 0, 'counts': [0.0] * int(ch.ncat[i])}))
         md['suffstats'].append(items)

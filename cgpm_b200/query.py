@@ -158,7 +158,7 @@ def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=No
         per_chain = []
         for q in range(Q):
             tcols = list(targets_list[q])
-            is_cat = [ch.ctype[ch.col_index[c]] == L.CATEGORICAL for c in tcols]
+            is_cat = [ch.ctype[ch.col_index[c]] in (L.CATEGORICAL, L.BERNOULLI, L.POISSON, L.GEOMETRIC) for c in tcols]     # integer-valued
             is_ln = [bool(ch.lognormal[ch.col_index[c]]) for c in tcols]
             samples = []
             for r in range(soff[q], soff[q + 1]):

@@ -42,7 +42,7 @@ def full_state(ch, s):
             cid = int(vw['cid'][pos])
             for i in cols:
                 N = float(dl['stat'][L.F_N, k, i])
-                if ch.ctype[i] == L.NORMAL:
+                if ch.ctype[i] != L.CATEGORICAL:
                     stats[(i, cid)] = [N, float(dl['stat'][L.F_SX, k, i]), float(dl['stat'][L.F_SXX, k, i])]
                 else:
                     o0 = ch.dev.catoff_h[i]
@@ -56,29 +56,51 @@ def full_state(ch, s):
 
 
 def _empty(ch_ctype, ncat):
-    return [0.0, 0.0, 0.0] if ch_ctype == L.NORMAL else [0.0, np.zeros(ncat)]
+    return [0.0, 0.0, 0.0] if ch_ctype != L.CATEGORICAL else [0.0, np.zeros(ncat)]
 
 
-def _add(st, x, is_normal):
-    """normal.py:64-70 / categorical.py:53-61."""
-    if is_normal:
+def _second(x, ctype):
+    """What the column type adds to its second statistic: x*x (normal.py:69), gammaln(x+1) (poisson.py:56), nothing."""
+    if ctype == L.NORMAL:
+        return x * x
+    if ctype == L.POISSON:
+        from scipy.special import gammaln
+        return gammaln(x + 1)
+    return 0.0
+
+
+def _add(st, x, ctype):
+    """normal.py:64-70 / categorical.py:53-61 / bernoulli.py:46-53 / poisson.py:49-57 / exponential.py:47-53 /
+    geometric.py:47-53."""
+    if ctype != L.CATEGORICAL:
         st[0] += 1.
         st[1] += x
-        st[2] += x * x
+        st[2] += _second(x, ctype)
     else:
         st[0] += 1
         st[1][int(x)] += 1
 
 
-def _sub(st, x, is_normal):
-    """normal.py:72-76 / categorical.py:63-66."""
-    if is_normal:
+def _sub(st, x, ctype):
+    """normal.py:72-76 / categorical.py:63-66 and the unincorporate of the other primitives."""
+    if ctype != L.CATEGORICAL:
         st[0] -= 1
         st[1] -= x
-        st[2] -= x * x
+        st[2] -= _second(x, ctype)
     else:
         st[0] -= 1
         st[1][int(x)] -= 1
+
+
+def check_cell(ch, i, x):
+    """The ValueError the column's primitive raises for a value it cannot incorporate."""
+    from .device import COUNT_NAMES, count_valid
+    if math.isnan(x):
+        return
+    if ch.ctype[i] == L.CATEGORICAL and not (x % 1 == 0 and 0 <= x < ch.ncat[i]):
+        raise ValueError('Invalid Categorical(%d): %s' % (ch.ncat[i], x))
+    if ch.ctype[i] in COUNT_NAMES and not bool(count_valid(ch.ctype[i], [x])[0]):
+        raise ValueError('Invalid %s: %s' % (COUNT_NAMES[ch.ctype[i]], x))
 
 
 def build(old, X, outputs, cctypes, distargs, grids, states, rebuild_cols=()):
@@ -111,7 +133,7 @@ def build(old, X, outputs, cctypes, distargs, grids, states, rebuild_cols=()):
                     if st is None:
                         continue
                     stat[L.F_N, p, i] = st[0]
-                    if ch.ctype[i] == L.NORMAL:
+                    if ch.ctype[i] != L.CATEGORICAL:
                         stat[L.F_SX, p, i] = st[1]
                         stat[L.F_SXX, p, i] = st[2]
                     else:
@@ -181,9 +203,7 @@ def incorporate(ch, rowid, observation, chains=None):
         raise ValueError('Cannot incorporate nan: %s.' % observation)
     row = np.array([float(observation.get(c, float('nan'))) for c in outputs])
     for i in range(ch.C):
-        if ch.ctype[i] == L.CATEGORICAL and not math.isnan(row[i]) and \
-                not (row[i] % 1 == 0 and 0 <= row[i] < ch.ncat[i]):
-            raise ValueError('Invalid Categorical(%d): %s' % (ch.ncat[i], row[i]))
+        check_cell(ch, i, row[i])
     X = np.vstack([X, row[None, :]])
     todo = []           # (chain, view id) pairs whose new row gets a Gibbs step
     for s, fs in enumerate(states):
@@ -199,7 +219,7 @@ def incorporate(ch, rowid, observation, chains=None):
                 if fresh:
                     fs['stats'][(i, k)] = _empty(ch.ctype[i], ch.ncat[i])       # dim.py:99-101
                 if not math.isnan(row[i]):
-                    _add(fs['stats'][(i, k)], _dev_value(ch, i, row[i]), ch.ctype[i] == L.NORMAL)
+                    _add(fs['stats'][(i, k)], _dev_value(ch, i, row[i]), ch.ctype[i])
             if given is None:
                 todo.append((s, vid))
     new = build(ch, X, outputs, cctypes, distargs, grids, states)
@@ -235,7 +255,7 @@ def unincorporate(ch, rowid):
             cols = [i for i, v in enumerate(fs['Zv']) if v == vid]
             for i in cols:
                 if not math.isnan(row[i]):
-                    _sub(fs['stats'][(i, k)], _dev_value(ch, i, row[i]), ch.ctype[i] == L.NORMAL)
+                    _sub(fs['stats'][(i, k)], _dev_value(ch, i, row[i]), ch.ctype[i])
             vw['Zr'].pop()
             vw['order'].remove(rowid)
             if k not in vw['Zr']:                                                # view.py:181-183
@@ -256,12 +276,11 @@ def force_cell(ch, rowid, observation):
     states = [full_state(ch, s) for s in range(ch.S)]
     for c, value in observation.items():
         i = ch.col_index[c]
-        if ch.ctype[i] == L.CATEGORICAL and not (value % 1 == 0 and 0 <= value < ch.ncat[i]):
-            raise ValueError('Invalid Categorical(%d): %s' % (ch.ncat[i], value))
+        check_cell(ch, i, float(value))
         X[rowid, i] = float(value)
         for fs in states:
             k = fs['views'][fs['Zv'][i]]['Zr'][rowid]
-            _add(fs['stats'][(i, k)], _dev_value(ch, i, float(value)), ch.ctype[i] == L.NORMAL)
+            _add(fs['stats'][(i, k)], _dev_value(ch, i, float(value)), ch.ctype[i])
     return build(ch, X, outputs, cctypes, distargs, grids, states)
 
 
@@ -278,11 +297,13 @@ def incorporate_dim(ch, T, outputs_new, inputs=None, cctype=None, distargs=None,
     if inputs:
         raise ValueError('Cannot incorporate dim with inputs: %s.' % inputs)
     cctype = cctype or 'normal'
-    if cctype not in ('normal', 'lognormal', 'categorical'):
-        raise ValueError('Only normal, lognormal and categorical cgpms supported by cgpm_b200: %s' % (cctype,))
+    from .core import CCTYPES
+    if cctype not in CCTYPES:
+        raise ValueError('Only normal, lognormal, categorical, bernoulli, poisson, exponential and geometric cgpms '
+                         'supported by cgpm_b200: %s' % (cctype,))
     col = outputs_new[0]
     Tn = np.asarray(T, dtype=np.float64)
-    code = L.CATEGORICAL if cctype == 'categorical' else L.NORMAL
+    code = CCTYPES[cctype]
     canon = list(codec.HYPER_NAMES[code])
     if cctype == 'lognormal':
         if np.any(Tn[~np.isnan(Tn)] <= 0):
@@ -306,7 +327,8 @@ def incorporate_dim(ch, T, outputs_new, inputs=None, cctype=None, distargs=None,
                                   'grid': grid}
         hyp_new = np.zeros(4)
         for nm in names:                                                  # dim.py:180-183
-            hyp_new[canon.index(nm)] = rng.choice(g_new[canon.index(nm)])
+            gq = g_new[canon.index(nm)]
+            hyp_new[canon.index(nm)] = rng.choice(gq[~np.isnan(gq)])          # (a grid shorter than 30 is NaN-padded)
         fs['hyp'] = np.vstack([fs['hyp'], hyp_new[None, :]])
         fs['Zv'] = fs['Zv'] + [v_add]
         fs['hyper_order'] = list(fs['hyper_order']) + [names]

@@ -50,6 +50,11 @@ def _resize_rows(ch, newR):
     a = torch.full((dev.C, newR), float('nan'), dtype=torch.float64, device=dev.device)
     a[:, :keep] = t['Xcm'][:, :keep]
     t['Xcm'] = a
+    if dev.aux_cols:
+        a = torch.full((len(dev.aux_cols), newR), float('nan'), dtype=torch.float64, device=dev.device)
+        a[:, :keep] = t['Xaux'][:, :keep]
+        t['Xaux'] = a
+        dev.st.Xaux = a.data_ptr()
     t['aux_zr'] = torch.zeros((dev.S, newR), dtype=torch.int32, device=dev.device)
     dev.aux_zr_all = None               # scratch of the column kernel: re-allocated lazily for the new row count
     dev.arena = None
@@ -100,11 +105,17 @@ def _update_stats(ch, slot_sc, vals, sign):
     sg = float(sign)
     fN = torch.full_like(x, L.F_N, dtype=torch.long)
     t['stat'].index_put_((sidx, fN, pidx, cidx), torch.full_like(x, sg), accumulate=True)
-    isn = torch.from_numpy((ch.ctype[cols] == L.NORMAL)).to(dev.device).unsqueeze(0).expand(S, len(cols)).reshape(-1)
+    isn = torch.from_numpy((ch.ctype[cols] != L.CATEGORICAL)).to(dev.device).unsqueeze(0).expand(S, len(cols)).reshape(-1)
     if bool(isn.any()):
+        # the sum types: sum_x, and the second sum -- x*x (normal.py:69), gammaln(x+1) as the host computes it
+        # (poisson.py:56), nothing for the others
+        from .device import log_fact
+        second = np.where(ch.ctype[cols] == L.NORMAL, vals[cols] * vals[cols],
+                          np.where(ch.ctype[cols] == L.POISSON, log_fact(vals[cols]), 0.0))
+        x2 = torch.from_numpy(second).to(dev.device).unsqueeze(0).expand(S, len(cols)).reshape(-1)
         xs = x[isn]
         t['stat'].index_put_((sidx[isn], torch.full_like(sidx[isn], L.F_SX), pidx[isn], cidx[isn]), sg * xs, accumulate=True)
-        t['stat'].index_put_((sidx[isn], torch.full_like(sidx[isn], L.F_SXX), pidx[isn], cidx[isn]), sg * (xs * xs), accumulate=True)
+        t['stat'].index_put_((sidx[isn], torch.full_like(sidx[isn], L.F_SXX), pidx[isn], cidx[isn]), sg * x2[isn], accumulate=True)
     isc = ~isn
     if bool(isc.any()):
         off = torch.from_numpy(dev.catoff_h[cols].astype(np.int64)).to(dev.device).unsqueeze(0).expand(S, len(cols)).reshape(-1)
@@ -127,9 +138,9 @@ def incorporate(ch, rowid, observation):
     if any(math.isnan(v) for v in observation.values()):
         raise ValueError('Cannot incorporate nan: %s.' % observation)
     row = np.array([float(observation.get(c, float('nan'))) for c in ch.outputs])
+    from .structure import check_cell
     for i in range(ch.C):
-        if ch.ctype[i] == L.CATEGORICAL and not math.isnan(row[i]) and not (row[i] % 1 == 0 and 0 <= row[i] < ch.ncat[i]):
-            raise ValueError('Invalid Categorical(%d): %s' % (ch.ncat[i], row[i]))
+        check_cell(ch, i, row[i])
     row_dev = np.array([_dev_value(ch, i, row[i]) for i in range(ch.C)])
     # target cluster of the new row in every view: the given one, else cluster id 0 (view.py:149-172)
     V = dev.Vcap
@@ -149,6 +160,9 @@ def incorporate(ch, rowid, observation):
     t = dev.t
     t['Xrm'][R, :ch.C] = torch.from_numpy(row_dev).to(dev.device)
     t['Xcm'][:, R] = torch.from_numpy(row_dev).to(dev.device)
+    if dev.aux_cols:
+        from .device import log_fact
+        t['Xaux'][:, R] = torch.from_numpy(log_fact(row_dev[dev.aux_cols])).to(dev.device)
     t['zr'][:, :, R] = slot
     t['order'][:, :, R] = R
     t['nk'].scatter_add_(2, slot.long().unsqueeze(2), live.to(torch.int32).unsqueeze(2))
@@ -216,8 +230,8 @@ def force_cell(ch, rowid, observation):
     vals = np.full(ch.C, np.nan)
     for c, value in observation.items():
         i = ch.col_index[c]
-        if ch.ctype[i] == L.CATEGORICAL and not (value % 1 == 0 and 0 <= value < ch.ncat[i]):
-            raise ValueError('Invalid Categorical(%d): %s' % (ch.ncat[i], value))
+        from .structure import check_cell
+        check_cell(ch, i, float(value))
         vals[i] = _dev_value(ch, i, float(value))
     t = dev.t
     for c, value in observation.items():
@@ -225,6 +239,9 @@ def force_cell(ch, rowid, observation):
         ch.X_raw[rowid, i] = float(value)
         t['Xrm'][rowid, i] = float(vals[i])
         t['Xcm'][i, rowid] = float(vals[i])
+        if dev.auxcol_h[i] >= 0:
+            from .device import log_fact
+            t['Xaux'][int(dev.auxcol_h[i]), rowid] = float(log_fact([vals[i]])[0])
         if ch.lognormal[i]:
             ch._ln_const -= float(vals[i])
     slot_sc = t['zr'][:, :, rowid].gather(1, t['zv'].long())

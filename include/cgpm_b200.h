@@ -28,19 +28,24 @@
 extern "C" {
 #endif
 
-#define CC_ABI_VERSION 3
+#define CC_ABI_VERSION 4
 #define CC_NGRID 30          /* hyper-grid points, dim.py:176 n_grid=30        */
 #define CC_NFIELD 8          /* per (cluster, column) statistic fields          */
 
-/* column types (config.py:25-39; only the two named by the scope contract) */
+/* column types (config.py:25-39): the two named by the scope contract, and the other collapsed primitives of
+ * SURVEY.md 8(f) rank 3 ("sum types": their statistics are N, sum_x and, for poisson, sum_log_fact_x) */
 #define CC_NORMAL 0
 #define CC_CATEGORICAL 1
+#define CC_BERNOULLI 2       /* src/primitives/bernoulli.py    hypers alpha, beta */
+#define CC_POISSON 3         /* src/primitives/poisson.py      hypers a, b        */
+#define CC_EXPONENTIAL 4     /* src/primitives/exponential.py  hypers a, b        */
+#define CC_GEOMETRIC 5       /* src/primitives/geometric.py    hypers a, b        */
 
 /* statistic fields of `stat[S][CC_NFIELD][Kcap][C]`                         */
 #define CC_F_N    0   /* count of non-NaN members   (normal.py:51, categorical.py:47) */
-#define CC_F_SX   1   /* sum_x                      (normal.py:52)  */
-#define CC_F_SXX  2   /* sum_x_sq                   (normal.py:53)  */
-#define CC_F_MN   3   /* cached posterior mean      (normal.py:186) */
+#define CC_F_SX   1   /* sum_x                      (normal.py:52; x_sum / sum_x of the other sum types)  */
+#define CC_F_SXX  2   /* sum_x_sq                   (normal.py:53); poisson: sum_log_fact_x (poisson.py:56) */
+#define CC_F_MN   3   /* cached posterior mean      (normal.py:186); sum types: see cc_common.cuh count_cache */
 #define CC_F_A    4   /* cached rn/((rn+1) sn)                      */
 #define CC_F_CST  5   /* cached constant: normal G(N) - log(sn)/2 ; categorical log(N + alpha k) */
 #define CC_F_GN   6   /* cached G(N)   = lgamma((nu+N+1)/2)-lgamma((nu+N)/2)+log((r+N)/(r+N+1))/2-log(pi)/2 */
@@ -64,7 +69,12 @@ typedef struct cc_state {
     const int32_t* ctype;          /* [C]   CC_NORMAL / CC_CATEGORICAL           */
     const int32_t* ncat;           /* [C]   k of categorical(k), else 0          */
     const int32_t* catoff;         /* [C]   offset of the column's counts in `cnt` rows */
-    const double*  grids;          /* [C][4][CC_NGRID] normal: m,r,s,nu ; categorical: alpha in row 0 */
+    const double*  grids;          /* [C][4][CC_NGRID] normal: m,r,s,nu ; categorical: alpha in row 0 ; other types: their
+                                      two hypers in rows 0, 1.  A grid shorter than CC_NGRID (poisson a: poisson.py:122-124)
+                                      is padded with NaN: such points have no mass */
+    const double*  Xaux;           /* [n_aux][R] per-cell constants some column types add to their statistics, column-major:
+                                      poisson gammaln(x + 1) as the host computes it (poisson.py:56), or NULL */
+    const int32_t* auxcol;         /* [C] row of Xaux belonging to the column, -1 = none (NULL when Xaux is NULL) */
     const double*  row_alpha_grid; /* [CC_NGRID] crp.py:148-152 with n = R       */
     const double*  col_alpha_grid; /* [CC_NGRID] with n = C                      */
     /* ---- per chain -------------------------------------------------------- */

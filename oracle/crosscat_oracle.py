@@ -25,6 +25,10 @@ Reference map (all paths relative to /root/reference/src):
   normal           primitives/normal.py:64-76,128-139,165-200
   categorical      primitives/categorical.py:53-66,110-114,144-155
   lognormal        primitives/lognormal.py:56-102,151-157
+  bernoulli        primitives/bernoulli.py:46-61,107-112,141-155
+  poisson          primitives/poisson.py:49-66,119-126,147-172
+  exponential      primitives/exponential.py:47-58,109-114,140-166
+  geometric        primitives/geometric.py:47-58,105-110,140-164
   sampling         utils/general.py:80-86,123-157,203-205
   scheduler        crosscat/state.py:727-810,866-914
   queries          crosscat/sampling.py:37-116, crosscat/state.py:384-387,538-554
@@ -39,7 +43,7 @@ from collections import OrderedDict
 from math import lgamma, log
 
 import numpy as np
-from scipy.special import gammaln
+from scipy.special import betaln, gammaln
 
 LOG2 = log(2)
 LOGPI = log(math.pi)
@@ -184,6 +188,97 @@ def categorical_grids(X, n_grid=30):
 
 
 # ----------------------------------------------------------------------------
+# primitives/bernoulli.py, poisson.py, exponential.py, geometric.py: statistics [N, sum_x, sum_log_fact_x]
+# (the third slot is used by poisson only)
+
+def bernoulli_predictive(x, N, x_sum, alpha, beta):
+    """bernoulli.py:141-151."""
+    log_denom = log(N + alpha + beta)
+    if x == 1:
+        return log(x_sum + alpha) - log_denom
+    return log(N - x_sum + beta) - log_denom
+
+
+def bernoulli_marginal(N, x_sum, alpha, beta):
+    """bernoulli.py:153-155."""
+    return betaln(x_sum + alpha, N - x_sum + beta) - betaln(alpha, beta)
+
+
+def gamma_log_Z(a, b):
+    """poisson.py:169-172, exponential.py:163-166."""
+    return gammaln(a) - a*log(b)
+
+
+def poisson_predictive(x, N, sum_x, a, b):
+    """poisson.py:147-153."""
+    an, bn = a + sum_x, b + N
+    am, bm = a + (sum_x + x), b + (N + 1)
+    ZN = gamma_log_Z(an, bn)
+    ZM = gamma_log_Z(am, bm)
+    return ZM - ZN - gammaln(x+1)
+
+
+def poisson_marginal(N, sum_x, sum_log_fact_x, a, b):
+    """poisson.py:155-160."""
+    an, bn = a + sum_x, b + N
+    Z0 = gamma_log_Z(a, b)
+    ZN = gamma_log_Z(an, bn)
+    return ZN - Z0 - sum_log_fact_x
+
+
+def exponential_predictive(x, N, sum_x, a, b):
+    """exponential.py:140-146."""
+    an, bn = a + N, b + sum_x
+    am, bm = a + (N + 1), b + (sum_x + x)
+    ZN = gamma_log_Z(an, bn)
+    ZM = gamma_log_Z(am, bm)
+    return ZM - ZN
+
+
+def exponential_marginal(N, sum_x, a, b):
+    """exponential.py:148-153."""
+    an, bn = a + N, b + sum_x
+    return gamma_log_Z(an, bn) - gamma_log_Z(a, b)
+
+
+def geometric_predictive(x, N, sum_x, a, b):
+    """geometric.py:140-146."""
+    an, bn = a + N, b + sum_x
+    am, bm = a + (N + 1), b + (sum_x + x)
+    return betaln(am, bm) - betaln(an, bn)
+
+
+def geometric_marginal(N, sum_x, a, b):
+    """geometric.py:148-153."""
+    an, bn = a + N, b + sum_x
+    return betaln(an, bn) - betaln(a, b)
+
+
+def count_grids(cctype, X, n_grid=30):
+    """construct_hyper_grids of bernoulli.py:107-112, poisson.py:119-126, exponential.py:109-114, geometric.py:105-110."""
+    n = float(len(X))
+    if cctype == 'bernoulli':
+        return OrderedDict([('alpha', log_linspace(1., n, n_grid)), ('beta', log_linspace(1., n, n_grid))])
+    if cctype == 'poisson':
+        return OrderedDict([('a', np.unique(np.round(np.linspace(1, len(X), n_grid)))), ('b', log_linspace(.1, n, n_grid))])
+    if cctype == 'exponential':
+        return OrderedDict([('a', log_linspace(.5, n, n_grid)), ('b', log_linspace(.5, n, n_grid))])
+    return OrderedDict([('a', log_linspace(1, n / 2., n_grid)), ('b', log_linspace(.1, n / 2., n_grid))])
+
+
+COUNT_TYPES = ('bernoulli', 'poisson', 'exponential', 'geometric')
+
+
+def count_valid(cctype, x):
+    """The values each primitive's incorporate accepts / its logpdf gives mass to."""
+    if cctype == 'bernoulli':
+        return x in [0, 1]
+    if cctype == 'exponential':
+        return x >= 0
+    return x % 1 == 0 and x >= 0
+
+
+# ----------------------------------------------------------------------------
 # primitives/crp.py
 
 def crp_grids(n, n_grid=30):
@@ -283,13 +378,14 @@ class ODim(object):
         self.col = col
         self.cctype = cctype
         self.distargs = dict(distargs) if distargs else {}
-        if cctype not in ('normal', 'categorical', 'lognormal'):
-            raise ValueError('oracle covers normal/categorical/lognormal only: %s' % cctype)
+        if cctype not in ('normal', 'categorical', 'lognormal') + COUNT_TYPES:
+            raise ValueError('oracle does not cover cctype %s' % cctype)
         self.k = int(self.distargs['k']) if cctype == 'categorical' else 0
         self.hypers = OrderedDict(hypers) if hypers else OrderedDict()
         clean = [x for x in xcol if not math.isnan(x)]
         self.grids = normal_grids(clean) if cctype == 'normal' \
             else lognormal_grids(clean) if cctype == 'lognormal' \
+            else count_grids(cctype, clean) if cctype in COUNT_TYPES \
             else categorical_grids(clean)
         if not self.hypers:                                   # dim.py:180-183
             for h in self.grids:
@@ -298,8 +394,8 @@ class ODim(object):
 
     # sufficient statistics ---------------------------------------------------
     def _empty(self):
-        if self.cctype in ('normal', 'lognormal'):
-            return [0, 0, 0]                                  # N, sum_x, sum_x_sq (of log x for lognormal)
+        if self.cctype in ('normal', 'lognormal') + COUNT_TYPES:
+            return [0, 0, 0]                                  # N, sum_x, sum_x_sq (of log x for lognormal; sum_log_fact_x for poisson)
         return [0, np.zeros(self.k)]                          # N, counts
 
     def _add(self, st, x):
@@ -313,6 +409,13 @@ class ODim(object):
             st[0] += 1
             st[1] += math.log(x)
             st[2] += math.log(x) * math.log(x)
+        elif self.cctype in COUNT_TYPES:                      # bernoulli.py:46-53, poisson.py:49-57, exponential.py:47-53, geometric.py:47-53
+            if not count_valid(self.cctype, x):
+                raise ValueError('Invalid %s: %s' % (self.cctype.capitalize(), str(x)))
+            st[0] += 1
+            st[1] += x
+            if self.cctype == 'poisson':
+                st[2] += gammaln(x+1)
         else:                                                 # categorical.py:53-61
             if not categorical_valid(x, self.k):
                 raise ValueError('Invalid Categorical(%d): %s' % (self.k, x))
@@ -328,6 +431,11 @@ class ODim(object):
             st[0] -= 1
             st[1] -= math.log(x)
             st[2] -= math.log(x) * math.log(x)
+        elif self.cctype in COUNT_TYPES:
+            st[0] -= 1
+            st[1] -= x
+            if self.cctype == 'poisson':
+                st[2] -= gammaln(x+1)
         else:
             st[0] -= 1
             st[1][int(x)] -= 1
@@ -361,6 +469,13 @@ class ODim(object):
                 return NEG_INF
             return - math.log(x) + normal_predictive(math.log(x), st[0], st[1], st[2],
                                                      h['m'], h['r'], h['s'], h['nu'])
+        if self.cctype in COUNT_TYPES:
+            if not count_valid(self.cctype, x):
+                return NEG_INF
+            if self.cctype == 'bernoulli':
+                return bernoulli_predictive(x, st[0], st[1], h['alpha'], h['beta'])
+            f = {'poisson': poisson_predictive, 'exponential': exponential_predictive, 'geometric': geometric_predictive}[self.cctype]
+            return f(x, st[0], st[1], h['a'], h['b'])
         if not categorical_valid(x, self.k):
             return NEG_INF
         return categorical_predictive(int(x), st[0], st[1], h['alpha'])
@@ -373,6 +488,14 @@ class ODim(object):
         if self.cctype == 'lognormal':                        # lognormal.py:98-102
             return -st[1] + normal_marginal(st[0], st[1], st[2],
                                             h['m'], h['r'], h['s'], h['nu'])
+        if self.cctype == 'bernoulli':
+            return bernoulli_marginal(st[0], st[1], h['alpha'], h['beta'])
+        if self.cctype == 'poisson':
+            return poisson_marginal(st[0], st[1], st[2], h['a'], h['b'])
+        if self.cctype == 'exponential':
+            return exponential_marginal(st[0], st[1], h['a'], h['b'])
+        if self.cctype == 'geometric':
+            return geometric_marginal(st[0], st[1], h['a'], h['b'])
         return categorical_marginal(st[0], st[1], h['alpha'])
 
     def logpdf(self, x, k):
@@ -409,6 +532,12 @@ class ODim(object):
                 return {'N': st[0], 'sum_x': st[1], 'sum_x_sq': st[2]}
             if self.cctype == 'lognormal':                    # lognormal.py:131-133
                 return {'N': st[0], 'sum_log_x': st[1], 'sum_log_x_sq': st[2]}
+            if self.cctype == 'bernoulli':                    # bernoulli.py:101-102
+                return {'N': st[0], 'x_sum': st[1]}
+            if self.cctype == 'poisson':                      # poisson.py:112-114
+                return {'N': st[0], 'sum_x': st[1], 'sum_log_fact_x': st[2]}
+            if self.cctype in ('exponential', 'geometric'):
+                return {'N': st[0], 'sum_x': st[1]}
             return {'N': st[0], 'counts': list(st[1])}
         if not self.clusters:
             return [(0, pack(self._empty()))]

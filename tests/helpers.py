@@ -7,7 +7,8 @@ import crosscat_oracle as co
 from cgpm_b200 import _lib as L
 from cgpm_b200 import codec
 
-CT = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL}
+CT = {'normal': L.NORMAL, 'categorical': L.CATEGORICAL, 'lognormal': L.NORMAL, 'bernoulli': L.BERNOULLI,
+      'poisson': L.POISSON, 'exponential': L.EXPONENTIAL, 'geometric': L.GEOMETRIC}
 
 
 def small_table(n_rows=60, seed=0, nan=True):
@@ -19,6 +20,28 @@ def small_table(n_rows=60, seed=0, nan=True):
         rng = np.random.RandomState(seed + 1)
         for _ in range(max(3, n_rows // 15)):
             X[rng.randint(n_rows), rng.randint(len(cct))] = np.nan
+    return X, cct, da
+
+
+def count_table(n_rows=50, seed=0, nan=True):
+    """A table with every collapsed primitive of SURVEY 8(f) rank 3: normal, bernoulli, poisson, exponential, geometric,
+    categorical, normal, poisson -- two latent views of three clusters each."""
+    rng = np.random.RandomState(seed)
+    cct = ['normal', 'bernoulli', 'poisson', 'exponential', 'geometric', 'categorical', 'normal', 'poisson']
+    da = [None, None, None, None, None, {'k': 3}, None, None]
+    za = rng.randint(3, size=n_rows); zb = rng.randint(3, size=n_rows)
+    X = np.empty((n_rows, 8))
+    X[:, 0] = rng.normal(4.0 * za, 1.0)
+    X[:, 1] = (rng.random_sample(n_rows) < np.array([.1, .5, .9])[za]).astype(float)
+    X[:, 2] = rng.poisson(np.array([1., 6., 20.])[za])
+    X[:, 3] = rng.exponential(np.array([.3, 2., 9.])[zb])
+    X[:, 4] = rng.geometric(np.array([.7, .3, .08])[zb]) - 1
+    X[:, 5] = np.where(rng.random_sample(n_rows) < .8, zb, rng.randint(3, size=n_rows))
+    X[:, 6] = rng.normal(-3.0 * zb, .7)
+    X[:, 7] = rng.poisson(np.array([40., 3., 11.])[zb])
+    if nan:
+        for _ in range(max(3, n_rows // 12)):
+            X[rng.randint(n_rows), rng.randint(8)] = np.nan
     return X, cct, da
 
 
@@ -61,7 +84,7 @@ def device_suffstats(dev, s, ctype):
             cid = int(dl['cid'][j][pos])
             for c in cols:
                 N = dl['stat'][L.F_N, k, c]
-                if ctype[c] == L.NORMAL:
+                if ctype[c] != L.CATEGORICAL:
                     out[(int(c), cid)] = [N, dl['stat'][L.F_SX, k, c], dl['stat'][L.F_SXX, k, c]]
                 else:
                     o0 = dev.catoff_h[c]
@@ -160,6 +183,10 @@ def snapshot_engine(eng, s):
                 items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
             elif 'sum_log_x' in st:        # lognormal: the same slots hold the sums of log x
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_log_x']), 'sum_x_sq': hx(st['sum_log_x_sq'])}])
+            elif 'x_sum' in st:            # bernoulli
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['x_sum']), 'sum_x_sq': hx(0)}])
+            elif 'sum_x_sq' not in st:     # poisson (sum_log_fact_x in the third slot), exponential, geometric
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st.get('sum_log_fact_x', 0))}])
             else:
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
         out['suffstats'].append(sorted(items))

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_all_symbols():
     lib = _lib.load()
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.cc_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.cc_abi_version() == _lib.ABI_VERSION == 4
     assert lib.cc_last_error() is not None
 
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import crosscat_oracle as co
-from helpers import small_table, snapshot_oracle
+from helpers import small_table, snapshot_oracle, count_table
 
 REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_ref')
 pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'cgpm', '.built')),
@@ -33,6 +33,10 @@ def ref_snapshot(state):
                 items.append([int(k), {'N': hx(st['N']), 'counts': [hx(c) for c in st['counts']]}])
             elif 'sum_log_x' in st:        # lognormal: the same slots hold the sums of log x
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_log_x']), 'sum_x_sq': hx(st['sum_log_x_sq'])}])
+            elif 'x_sum' in st:            # bernoulli
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['x_sum']), 'sum_x_sq': hx(0)}])
+            elif 'sum_x_sq' not in st:     # poisson (third slot: sum_log_fact_x), exponential, geometric
+                items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st.get('sum_log_fact_x', 0))}])
             else:
                 items.append([int(k), {'N': hx(st['N']), 'sum_x': hx(st['sum_x']), 'sum_x_sq': hx(st['sum_x_sq'])}])
         out['suffstats'].append(sorted(items))
@@ -147,4 +151,45 @@ def test_relevance_probability_with_hypothetical_rows():
         assert o.relevance_probability(tgt, qry, col, hyp) == ref.relevance_probability(tgt, list(qry), col, hyp)
         assert o.relevance_probability(tgt, qry, col) == ref.relevance_probability(tgt, list(qry), col)
     assert snapshot_oracle(o) == ref_snapshot(ref)
+    assert o.rng.random_sample() == ref.rng.random_sample()
+
+
+@pytest.mark.parametrize('seed', [8, 9])
+def test_oracle_equals_reference_with_count_primitives(seed):
+    """bernoulli, poisson, exponential and geometric columns (bernoulli.py:141-155,
+    poisson.py:147-172, exponential.py:140-166, geometric.py:140-164 and their hyper grids) replayed against the
+    reference: whole transitions, queries, incremental edits -- bit for bit, including the stream position."""
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from cgpm.crosscat.state import State
+    X, cct, da = count_table(50, seed)
+    ref = State(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed))
+    o = co.OState(X, cctypes=cct, distargs=da, rng=np.random.RandomState(seed))
+    assert snapshot_oracle(o) == ref_snapshot(ref)
+    assert o.logpdf_score() == ref.logpdf_score()
+    kernels = ['alpha', 'view_alphas', 'column_hypers', 'rows', 'columns']
+    for it in range(3):
+        ref.transition(N=1, kernels=kernels, progress=False)
+        o.transition(N=1, kernels=kernels)
+        assert snapshot_oracle(o) == ref_snapshot(ref)
+        assert o.logpdf_score() == ref.logpdf_score()
+    q = ({1: 1, 2: 4, 3: 0.7}, {4: 2, 0: 1.5, 7: 9})
+    assert o.logpdf(-1, *q) == ref.logpdf(-1, *q)
+    assert o.logpdf(-1, {2: 2.5}) == ref.logpdf(-1, {2: 2.5}) == float('-inf')      # not a count
+    assert o.logpdf(-1, {3: -1.0}) == ref.logpdf(-1, {3: -1.0}) == float('-inf')
+    assert o.logpdf(-1, {1: 2}) == ref.logpdf(-1, {1: 2}) == float('-inf')
+
+    def both(f):
+        f(ref); f(o)
+        assert snapshot_oracle(o) == ref_snapshot(ref)
+    both(lambda s: s.incorporate(50, {0: 0.5, 1: 1, 2: 7, 3: 0.25, 4: 3, 7: 12}))
+    both(lambda s: s.incorporate(51, {2: 0, 4: 0, 5: 1}))
+    both(lambda s: s.force_cell(51, {3: 1.9, 1: 0}))
+    both(lambda s: s.unincorporate(51))
+    T = [float(v) for v in np.random.RandomState(3).poisson(5.0, size=51)]
+    both(lambda s: s.incorporate_dim(T, [90], cctype='poisson', distargs=None, v=99))
+    ref.transition(N=1, kernels=kernels, progress=False)
+    o.transition(N=1, kernels=kernels)
+    assert snapshot_oracle(o) == ref_snapshot(ref)
+    assert o.logpdf_score() == ref.logpdf_score()
     assert o.rng.random_sample() == ref.rng.random_sample()
