@@ -51,9 +51,10 @@
 #include "cc_common.cuh"
 #include "rows_common.cuh"
 
-// This file is compiled twice: as rows.cu (CC_ROWS_COUNT 0: normal and categorical columns only -- the hot
-// configuration, kept free of the other primitives' lgamma calls, which cost registers and a stack frame) and through
-// rows_counts.cu (CC_ROWS_COUNT 1: tables that also hold bernoulli / poisson / exponential / geometric columns).
+// This file is compiled twice: as rows.cu (CC_ROWS_COUNT 0: the build for all-normal tables -- the kernel sits at
+// the 128-register limit of two 256-thread CTAs per SM, and every other column type costs it registers and a stack
+// frame) and through rows_counts.cu (CC_ROWS_COUNT 1: tables that hold categorical, bernoulli, poisson, exponential
+// or geometric columns; the two-pass scoring below covers views of normal + categorical columns there).
 #ifndef CC_ROWS_COUNT
 #define CC_ROWS_COUNT 0
 #endif
@@ -68,12 +69,20 @@ extern "C" int cc_transition_rows_counts(const cc_state* st, int n_work, const c
 
 namespace {
 
-constexpr bool CTS = CC_ROWS_COUNT != 0;
+constexpr bool CTS = CC_ROWS_COUNT != 0;      // column types other than normal are compiled in
 
 enum { ST_OK = 0, ST_HANDOVER = CC_ROWS_HANDOVER, ST_GROW = CC_ROWS_GROW, ST_MIGRATE = 3 };
 
 __device__ __forceinline__ int ceil_log2(int x) {          // smallest l with (1 << l) >= x, x >= 1
     return (x <= 1) ? 0 : 32 - __clz(x - 1);
+}
+
+// gammaln(x + 1) of a poisson cell as the host computed it (cc_state.Xaux), NaN when not available
+__device__ __forceinline__ double row_aux(const Ctx& c, int col, int r) {
+    const double* xa = c.st.Xaux;
+    if (!xa || r < 0) return CUDART_NAN;
+    const int a = c.st.auxcol[col];
+    return (a < 0) ? CUDART_NAN : xa[(size_t)a * c.st.R + r];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -97,7 +106,7 @@ __device__ __forceinline__ void apply_move(const Ctx& c, const Tab<GT>& T, int r
         const double x = xrow[c.bulk ? c.col[j] : j];
         const int k = is_old ? z : zb;
         const bool isnan_x = isnan(x);
-        const int ct = wide ? c.st.ctype[c.col[j]] : c.ctype[j];
+        const int ct = !CTS ? CC_NORMAL : (wide ? c.st.ctype[c.col[j]] : c.ctype[j]);
         if (ct == CC_NORMAL) {
             const double m = hyper(c, wide, ghyp, 0, j), rr = hyper(c, wide, ghyp, 1, j), ss = hyper(c, wide, ghyp, 2, j),
                          nu = hyper(c, wide, ghyp, 3, j);
@@ -140,7 +149,7 @@ __device__ __forceinline__ void apply_move(const Ctx& c, const Tab<GT>& T, int r
                 if (isnan_x && !fresh) continue;
                 double N = fresh ? 0.0 : T.at(CC_F_N, k, j), sx = fresh ? 0.0 : T.at(CC_F_SX, k, j), sxx = fresh ? 0.0 : T.at(CC_F_SXX, k, j);
                 if (!isnan_x) {
-                    const double t2 = sum_second_term_ni(ct, x, cell_aux(c.st, c.col[j], r));
+                    const double t2 = sum_second_term_ni(ct, x, row_aux(c, c.col[j], r));
                     if (is_old) {       // scored against its own cluster first (-= x, += x), then removed
                         N -= 1.0;
                         sx = __dsub_rn(__dadd_rn(__dsub_rn(sx, x), x), x);
@@ -262,14 +271,14 @@ __device__ __forceinline__ void apply_drift(const Ctx& c, const Tab<GT>& T, int 
     const bool wide = c.wide != 0;
     const double* ghyp = c.st.hyp + (size_t)c.s * c.st.C * 4;
     for (int j = threadIdx.x; j < c.D; j += NT) {
-        const int ct = wide ? c.st.ctype[c.col[j]] : c.ctype[j];
+        const int ct = !CTS ? CC_NORMAL : (wide ? c.st.ctype[c.col[j]] : c.ctype[j]);
         if (ct == CC_CATEGORICAL) continue;
         const double x = xrow[c.bulk ? c.col[j] : j];
         if (isnan(x)) continue;
         if (ct != CC_NORMAL) {
             if constexpr (CTS) {
                 const double sx0 = T.at(CC_F_SX, z, j), sxx0 = T.at(CC_F_SXX, z, j);
-                const double t2 = sum_second_term_ni(ct, x, cell_aux(c.st, c.col[j], r));
+                const double t2 = sum_second_term_ni(ct, x, row_aux(c, c.col[j], r));
                 const double sx2 = __dadd_rn(__dsub_rn(sx0, x), x), sxx2 = __dadd_rn(__dsub_rn(sxx0, t2), t2);
                 if (sx2 != sx0 || sxx2 != sxx0) {
                     T.at(CC_F_SX, z, j) = sx2;
@@ -304,7 +313,7 @@ __device__ __forceinline__ double count_term(const Ctx& c, const Tab<GT>& T, boo
     if (isnan(x)) return 0.0;
     if (own) {
         const double sx0 = T.at(CC_F_SX, k, j), sxx0 = T.at(CC_F_SXX, k, j);
-        const double t2 = sum_second_term_ni(ct, x, cell_aux(c.st, c.col[j], r));
+        const double t2 = sum_second_term_ni(ct, x, row_aux(c, c.col[j], r));
         const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, t2);
         if (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, t2) != sxx0) drift = 1;
         if (dn) return count_pred_raw_ni(ct, x, T.at(CC_F_N, k, j) - 1.0, sx1, hyper(c, wide, ghyp, 0, j), hyper(c, wide, ghyp, 1, j));
@@ -317,7 +326,7 @@ __device__ __forceinline__ double count_term(const Ctx& c, const Tab<GT>& T, boo
 template <bool GT>
 __device__ __forceinline__ double cell_term(const Ctx& c, const Tab<GT>& T, bool wide, bool allnorm, const double* ghyp,
                                             const double* xrow, int j, int k, int ke, bool own, bool dn, bool empty, int r, int& drift) {
-    if (allnorm) return normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
+    if (!CTS || allnorm) return normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
     const int ct = wide ? c.st.ctype[c.col[j]] : c.ctype[j];
     if (ct == CC_NORMAL) return normal_term<GT>(c, T, wide, ghyp, xrow, j, k, ke, own, dn, drift);
     if constexpr (CTS) {
@@ -419,21 +428,38 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 const bool dn = own && !singleton;
                 int drift = 0;
                 double acc = 0.0, acc2 = 0.0;
-                if (!GT && allnorm && !wide) {
-                    // All-normal view, shared-memory tables.  Pass A: every (row, candidate) lane evaluates the plain
+                if (!GT && !wide && (allnorm || (CTS && c.twotypes))) {
+                    // Views of normal and categorical columns, shared-memory tables.  Pass A: every (row, candidate) lane evaluates the plain
                     // Student-t term of its columns -- straight-line code, two independent chains per trip.  Pass B:
                     // the term of the row's own cluster WITHOUT the row (view.py:416-419) is a different formula; instead
                     // of letting one lane per group run it while the others wait at every column, all g lanes of the
                     // row group share the own cluster's columns and the sum replaces the own lane's result.
+                    // (everything the loops touch is copied out of the context first: it stays in registers)
                     const int fsI = c.Kc * D;
-                    const double* hnu = c.hyp + 3 * D;
-                    const double* hr = c.hyp + D;
+                    const double* hyp0 = c.hyp;
+                    const double* hnu = hyp0 + 3 * D;
+                    const double* hr = hyp0 + D;
+                    const double* tab0 = c.tab;
+                    const double* cnt0 = tab0 + CC_NFIELD * fsI;
+                    const int* colp = c.col;
+                    const int* ctp = c.ctype;
+                    const int* ctop = c.cto;
+                    const int* ncatp = c.ncat;
+                    const int CTv = c.CTv;
+                    const bool bulk = c.bulk != 0;
                     int nodrift = 0;
                     if (cand) {
-                        const double* pe = c.tab + ke * D;
+                        const double* pe = tab0 + ke * D;
+                        const bool emptyc = ke == pslot;       // the empty cluster (a fresh one, or a lone member's own without it)
                         auto termA = [&](int jj) -> double {
-                            return normal_core(pe + jj, pe + jj, fsI, xrow[c.bulk ? c.col[jj] : jj], hnu[jj], hr[jj], false, false, nodrift,
-                                               [](double&, double&) {});
+                            const double x = xrow[bulk ? colp[jj] : jj];
+                            if (!CTS || allnorm || ctp[jj] == CC_NORMAL)
+                                return normal_core(pe + jj, pe + jj, fsI, x, hnu[jj], hr[jj], false, false, nodrift, [](double&, double&) {});
+                            // categorical.py:144-148: log(alpha + count_x) - log(N + alpha k), the second log cached
+                            if (isnan(x)) return 0.0;
+                            const double a = hyp0[jj];
+                            if (emptyc) return hr[jj];                       // cached log(alpha) - log(alpha k)
+                            return cc_log_pos(a + (cnt0 + ke * CTv + ctop[jj])[(int)x]) - pe[CC_F_CST * fsI + jj];
                         };
                         int j = cc;
                         double acc3 = 0.0, acc4 = 0.0;
@@ -446,12 +472,19 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                     // (pass B is issued before pass A's reduction: the two chains are independent and overlap)
                     double accB = 0.0;
                     if (arow) {
-                        const double* po = c.tab + z * D;
+                        const double* po = tab0 + z * D;
                         for (int j = lane & (g - 1); j < D; j += g) {
-                            const double x = xrow[c.bulk ? c.col[j] : j];
-                            if (!singleton) {
+                            const double x = xrow[bulk ? colp[j] : j];
+                            if (CTS && !allnorm && ctp[j] != CC_NORMAL) {
+                                // own cluster without the row: counts and N one lower (categorical.py:63-66,144-148)
+                                if (!singleton && !isnan(x)) {
+                                    const double a = hyp0[j];
+                                    const double cntx = (cnt0 + z * CTv + ctop[j])[(int)x];
+                                    accB += cc_log_pos(a + (cntx - 1.0)) - cc_log_pos((po[CC_F_N * fsI + j] - 1.0) + a * ncatp[j]);
+                                }
+                            } else if (!singleton) {
                                 accB += normal_core(po + j, po + j, fsI, x, hnu[j], hr[j], true, true, drift,
-                                                    [&](double& m, double& ss) { m = c.hyp[j]; ss = c.hyp[2 * D + j]; });
+                                                    [&](double& m, double& ss) { m = hyp0[j]; ss = hyp0[2 * D + j]; });
                             } else {
                                 // a lone member is scored against the empty cluster (pass A); its sums still go through -= x, += x
                                 const double sx0 = po[CC_F_SX * fsI + j], sxx0 = po[CC_F_SXX * fsI + j];
@@ -854,21 +887,26 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     const size_t tab_avail = (p.smem_bytes > (int)off) ? (size_t)p.smem_bytes - off : 0;
 
     if (tid == 0) {
-        int j = 0, ct = 0, alln = 1;
-        for (int q = 0; q < C; ++q)
-            if (zv[q] == v) {
-                c.col[j] = q;
-                if (st.ctype[q] != CC_NORMAL) alln = 0;
-                if (!p.wide) {
-                    c.cto[j] = ct;
-                    c.ctype[j] = st.ctype[q];
-                    c.ncat[j] = st.ncat[q];
+        // the view's columns, normal ones first: lanes that walk the columns side by side then evaluate the same
+        // type in the same trip (a warp pays for every branch any of its lanes takes)
+        int j = 0, ct = 0, alln = 1, two = 1;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int q = 0; q < C; ++q)
+                if (zv[q] == v && ((st.ctype[q] == CC_NORMAL) == (pass == 0))) {
+                    c.col[j] = q;
+                    if (st.ctype[q] != CC_NORMAL) alln = 0;
+                    if (st.ctype[q] > CC_CATEGORICAL) two = 0;
+                    if (!p.wide) {
+                        c.cto[j] = ct;
+                        c.ctype[j] = st.ctype[q];
+                        c.ncat[j] = st.ncat[q];
+                    }
+                    ct += st.ncat[q];
+                    ++j;
                 }
-                ct += st.ncat[q];
-                ++j;
-            }
         c.scal[6] = ct;
         c.scal[11] = alln;
+        c.scal[10] = two;
         c.scal[3] = nm0;
         c.scal[7] = 0;
         c.scal[42] = 0;
@@ -900,12 +938,20 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     }
     for (int e = tid; !p.wide && e < 4 * D; e += blockDim.x) {
         const int f = e / D, j = e - f * D;
-        c.hyp[e] = st.hyp[((size_t)s * C + c.col[j]) * 4 + f];
+        double hv = st.hyp[((size_t)s * C + c.col[j]) * 4 + f];
+        // a categorical column uses row 0 (alpha) only: row 1 caches its empty-cluster term log(alpha) - log(alpha k)
+        // (categorical.py:144-148 with no counts)
+        if (CTS && f == 1 && c.ctype[j] == CC_CATEGORICAL) {
+            const double a = st.hyp[((size_t)s * C + c.col[j]) * 4];
+            hv = log(a) - log(a * c.ncat[j]);
+        }
+        c.hyp[e] = hv;
     }
     __syncthreads();
     const int CTv = c.scal[6];
     c.CTv = CTv;
     c.allnorm = c.scal[11];
+    c.twotypes = c.scal[10];
     // shared-table capacity: Kc cluster slots (the empty-cluster record sits at slot Kc-1)
     const size_t per_cluster = (size_t)(CC_NFIELD * D + CTv) * sizeof(double);
     int Kc = (int)(tab_avail / (per_cluster ? per_cluster : 1));
@@ -1190,8 +1236,8 @@ extern "C" int CC_ROWS_ENTRY(const cc_state* st, int n_work, const cc_row_work* 
     CC_CUDA(cudaMemcpyAsync(ctype_h.data(), st->ctype, sizeof(int32_t) * st->C, cudaMemcpyDeviceToHost, stream));
     CC_CUDA(cudaStreamSynchronize(stream));            // `sorted` is a local; n_work is small
 #if !CC_ROWS_COUNT
-    for (int c = 0; c < st->C; ++c)                    // bernoulli / poisson / exponential / geometric columns: the other build
-        if (ctype_h[c] >= CC_BERNOULLI) {
+    for (int c = 0; c < st->C; ++c)                    // any column that is not normal: the other build
+        if (ctype_h[c] != CC_NORMAL) {
             CC_CUDA(cudaFreeAsync(dwork, stream));
             return cc_transition_rows_counts(st, n_work, work, perm, u, trace, trace_stride, seed, counter, stream_);
         }
@@ -1236,8 +1282,11 @@ extern "C" int CC_ROWS_ENTRY(const cc_state* st, int n_work, const cc_row_work* 
             CC_CUDA(cudaFuncSetAttribute(rows_kernel<480, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
             rows_kernel<480, 1, true><<<n_work, 512, budget, stream>>>(p);
         } else {
-            CC_CUDA(cudaFuncSetAttribute(rows_kernel<224, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
-            rows_kernel<224, 2, false><<<n_work, 256, budget, stream>>>(p);
+            // 7 consumer warps at 128 registers for all-normal tables; the build with the other column types needs more
+            // registers per thread: 6 consumer warps (224 threads, 144 registers at two CTAs per SM)
+            constexpr int NTC = CTS ? 192 : 224;
+            CC_CUDA(cudaFuncSetAttribute(rows_kernel<NTC, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+            rows_kernel<NTC, 2, false><<<n_work, NTC + 32, budget, stream>>>(p);
         }
         CC_CUDA(cudaGetLastError());
         return CC_OK;

@@ -81,7 +81,7 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
 // Everything a sweep needs, resolved once per CTA.
 struct Ctx {
     cc_state st;
-    int s, v, n, D, K0, Kc, CTv, B, lgB, NBUF, RB, bulk, xstride, wide, allnorm, Ksm, DL, base, lvl0;
+    int s, v, n, D, K0, Kc, CTv, B, lgB, NBUF, RB, bulk, xstride, wide, allnorm, twotypes, Ksm, DL, base, lvl0;
     size_t sv;
     // shared memory
     uint64_t *bar_full, *bar_empty;   // [8] each
