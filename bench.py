@@ -36,7 +36,8 @@ sys.path.insert(0, ROOT)
 
 KERNELS = ['rows', 'columns']
 C1 = dict(name='configs[1]', rows=100000, cols=50, chains=64, mixed=False, views=4, clusters=4, kcap=256, vcap=24)
-C2 = dict(name='configs[2]', rows=1000000, cols=200, chains=64, mixed=True, views=5, clusters=4, kcap=128, vcap=16)
+C2 = dict(name='configs[2]', rows=1000000, cols=200, chains=64, mixed=True, views=5, clusters=4, kcap=128, vcap=16,
+          hypers=True, ref_rows=200)
 REF_ROWS = 1000
 FP64_PEAK_FLOPS = 148 * 64 * 2 * 1.965e9          # 64 DFMA lanes per SM and clock (B200 vector FP64, 37 TFLOP/s)
 FLOPS_PER_CELL_EVAL = 2 * 60                     # one Student-t term: ~60 FP64 instructions (log kernel 35, the rest 25)
@@ -60,6 +61,23 @@ def make_table(R, C, views, clusters, mixed=False, seed=0):
     cct, da = column_types(C, mixed)
     X, _, _ = synth.gen_table(R, cct, da, n_views=views, clusters_per_view=clusters, seed=seed)
     return X, cct, da
+
+
+def supplied_hypers(X, cct):
+    """Column hyperparameters for workloads that do not run the column_hypers kernel (configs[2]): weakly informative
+    and on the scale of the data -- normal: m = column mean, r = 1, s = column variance, nu = 1; categorical: alpha = 1.
+    Without them each chain draws every hyperparameter once from its grid (dim.py:181-183: up to R for r, nu and the
+    Dirichlet alpha) and keeps it for the whole run; a column that draws a very tight variance prior then prefers -- and
+    accepts -- auxiliary views of the order of R clusters, which no practitioner's run would keep."""
+    import numpy as np
+    out = []
+    for c, t in enumerate(cct):
+        if t == 'normal':
+            col = X[:, c]
+            out.append({'m': float(np.nanmean(col)), 'r': 1.0, 's': float(np.nanvar(col)) or 1.0, 'nu': 1.0})
+        else:
+            out.append({'alpha': 1.0})
+    return out
 
 
 def initial_partitions(R, C, seed):
@@ -91,13 +109,14 @@ def run_reference(cfg, R, chains, steps, warmup, burnin):
     S = max(1, min(chains, cores))
     X, cct, da = make_table(R, cfg['cols'], cfg['views'], cfg['clusters'], cfg['mixed'])
     Zv, Zrv = initial_partitions(R, cfg['cols'], 12345)
+    hyp = supplied_hypers(X, cct) if cfg.get('hypers') else None
     if os.path.exists(os.path.join(ref, 'cgpm', '.built')):
         sys.path.insert(0, ref)
         from cgpm.crosscat.engine import Engine
         from cgpm.utils import general as gu
         eng = Engine(X, num_states=S, rng=gu.gen_rng(1), multiprocess=1, cctypes=cct, distargs=da,
                      Zv=Zv, Zrv={v: list(map(int, z)) for v, z in Zrv.items()}, alpha=1.0,
-                     view_alphas={v: 1.0 for v in Zrv})
+                     view_alphas={v: 1.0 for v in Zrv}, hypers=hyp)
         step = lambda: eng.transition(N=1, kernels=KERNELS, progress=False, multiprocess=1)
     else:
         kind = 'port'
@@ -105,7 +124,7 @@ def run_reference(cfg, R, chains, steps, warmup, burnin):
         import crosscat_oracle as co
         S = 1
         states = [co.OState(X, cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, alpha=1.0, view_alphas={v: 1.0 for v in Zrv},
-                            rng=np.random.RandomState(2 + s)) for s in range(S)]
+                            hypers=hyp, rng=np.random.RandomState(2 + s)) for s in range(S)]
         step = lambda: [o.transition(N=1, kernels=KERNELS) for o in states]
     for _ in range(burnin + warmup):
         step()
@@ -116,9 +135,10 @@ def run_reference(cfg, R, chains, steps, warmup, burnin):
     val = R * cfg['cols'] * S * steps / dt
     return dict(value=val, seconds=dt, cores=min(S, cores) if kind == 'reference' else 1, kind=kind,
                 sample='%s sample: %d rows x %d %s cols x %d chains, %d burn-in + %d warm-up + %d timed step(s) of %s, '
-                       'supplied CRP(1) init; host has %d cores'
+                       'supplied CRP(1) init%s; host has %d cores'
                        % (cfg['name'], R, cfg['cols'], 'mixed' if cfg['mixed'] else 'normal', S, burnin, warmup, steps,
-                          '+'.join(KERNELS), cores), chains=S, ms_per_step=1e3 * dt / steps)
+                          '+'.join(KERNELS), ' and hypers' if hyp else '', cores), chains=S, ms_per_step=1e3 * dt / steps,
+                rows=R)
 
 
 def reference_main(args):
@@ -126,14 +146,15 @@ def reference_main(args):
     if rank != 0:
         return
     cfg = C1 if args.gpus <= 1 else C2
-    r = run_reference(cfg, args.ref_rows, cfg['chains'], args.steps, args.warmup, min(args.burnin, 3))
+    rows = args.ref_rows or cfg.get('ref_rows', REF_ROWS)
+    r = run_reference(cfg, rows, cfg['chains'], args.steps, args.warmup, min(args.burnin, 3))
     line = {
         'impl': 'reference', 'metric': 'crosscat_gibbs_cell_updates_per_sec', 'value': r['value'],
         'unit': 'cell-updates/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': '%s sample: %d rows x %d cols, %d chains, kernels=%s (CPU reference Engine, multiprocess)'
-                               % (cfg['name'], args.ref_rows, cfg['cols'], r['chains'], KERNELS)},
+                               % (cfg['name'], r['rows'], cfg['cols'], r['chains'], KERNELS)},
         'cpu_baseline': {'value': r['value'], 'unit': 'cell-updates/s', 'cores': r['cores'], 'kind': r['kind'],
                          'sample': r['sample']},
         'e2e': {'value': r['value'], 'unit': 'cell-updates/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -218,7 +239,8 @@ def extra_config2(budget_s):
     X, cct, da = make_table(cfg['rows'], cfg['cols'], cfg['views'], cfg['clusters'], True)
     Zv, Zrv = initial_partitions(cfg['rows'], cfg['cols'], 4242)
     eng = Engine(X, num_states=S, rng=gen_rng(11), cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, alpha=1.0,
-                 view_alphas={v: 1.0 for v in Zrv}, stream='philox', Kcap=cfg['kcap'], Vcap=cfg['vcap'])
+                 view_alphas={v: 1.0 for v in Zrv}, hypers=supplied_hypers(X, cct), stream='philox', Kcap=cfg['kcap'],
+                 Vcap=cfg['vcap'])
     burn = 0
     while burn < 3 and time.time() - t0 < 0.5 * budget_s:
         eng.transition(N=1, kernels=KERNELS, progress=False)
@@ -334,7 +356,7 @@ def ours_main(args):
         # the reference forks worker processes: run it before CUDA is initialised, in a child
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', '3',
-                                  '--warmup', '1', '--burnin', '0', '--ref-rows', str(args.ref_rows)],
+                                  '--warmup', '1', '--burnin', '0', '--ref-rows', str(args.ref_rows or REF_ROWS)],
                                  capture_output=True, text=True, timeout=900)
             cpu = json.loads(out.stdout.strip().splitlines()[-1])['cpu_baseline']
         except Exception as e:
@@ -354,6 +376,8 @@ def ours_main(args):
     Zv, Zrv = initial_partitions(R, Cn, 12345)
     kw = dict(cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, alpha=1.0, view_alphas={v: 1.0 for v in Zrv},
               stream='philox', Kcap=cfg['kcap'], Vcap=cfg['vcap'])
+    if cfg.get('hypers'):
+        kw['hypers'] = supplied_hypers(X, cct)
     if world > 1:
         sh = ShardedEngine(X, num_states=S * world, rng=gen_rng(1), **kw)
         eng = sh.local
@@ -377,6 +401,7 @@ def ours_main(args):
         eng.transition(N=1, kernels=KERNELS, progress=False)
     eng.native_launches(reset=True)
     eng.start_kernel_timing()
+    eng._ch.dev.t['seq'][:, :, 0].zero_()              # per-view cycle counters: slots of views that no longer exist are stale
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -398,10 +423,12 @@ def ours_main(args):
     n_views = vs['views_total']
 
     def critical_cta():
-        """Cycles per row of the slowest (chain, view) CTA of the last rows sweep (CGPM_B200_ROWS_PROF counters)."""
+        """Cycles per row of the slowest (chain, view) CTA of the rows sweeps since the counters were last cleared
+        (CGPM_B200_ROWS_PROF counters; the timed steps, then each device-resident step)."""
         dv = eng._ch.dev
-        live = dv.t['nv'] > 0
-        return float((dv.t['seq'][:, :, 0] * live).max().item()) * 1024.0 / R
+        c = float(dv.t['seq'][:, :, 0].max().item()) * 1024.0 / R
+        dv.t['seq'][:, :, 0].zero_()
+        return c
     crit = [critical_cta()]
 
     # ---- end to end: host table + host chain state in, host state + scores out, every step -------------
@@ -425,6 +452,7 @@ def ours_main(args):
     te = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device='cuda')
     # resident variant: the chain state stays on the device, only the scores come back every step
     res_ms = []
+    critical_cta()                                      # clear: what follows is per step
     for it in range(args.e2e_steps + 1):
         barrier()
         t0 = time.perf_counter()
@@ -478,7 +506,10 @@ def ours_main(args):
                             % (cfg['name'], R, Cn, 'mixed normal/categorical' if cfg['mixed'] else 'normal', S, KERNELS,
                                ' (ShardedEngine over NCCL)' if world > 1 else ''),
                 'init': 'supplied Zv~CRP(1), Zrv~CRP(1) (the same for every chain, as in the reference arm), alpha=1, '
-                        'view_alphas=1 (SURVEY 8d); %d burn-in sweeps, then %d warm-up sweeps' % (args.burnin, args.warmup),
+                        'view_alphas=1 (SURVEY 8d)%s; %d burn-in sweeps, then %d warm-up sweeps'
+                        % ('; column hypers supplied on the scale of the data (normal: m=mean, r=1, s=var, nu=1; categorical: '
+                           'alpha=1) because column_hypers is not among the kernels' if cfg.get('hypers') else '',
+                           args.burnin, args.warmup),
                 'cache': 'inputs larger than L2: per-step traffic (table %.0f MB + chain state %.0f MB) exceeds the 126 MB L2'
                          % (X.nbytes / 1e6, n_views * R * 8 / 1e6),
                 'Kcap': eng._ch.dev.Kcap, 'Vcap': eng._ch.dev.Vcap, 'setup_s': t_setup,
@@ -551,7 +582,7 @@ def main():
     ap.add_argument('--rows', type=int, default=0)
     ap.add_argument('--cols', type=int, default=0)
     ap.add_argument('--chains', type=int, default=0)
-    ap.add_argument('--ref-rows', type=int, default=REF_ROWS)
+    ap.add_argument('--ref-rows', type=int, default=0, help='rows of the reference arm\'s sample (0: per config)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--extra-budget', type=int, default=150)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -67,11 +67,24 @@ extern "C" int cc_transition_rows_counts(const cc_state* st, int n_work, const c
                                          void* stream_);
 #endif
 
+// -DCC_ROWS_PHASE=1: thread 0 accumulates the cycles of each phase of a speculative round into st.seq[16..] (probe builds only)
+#ifndef CC_ROWS_PHASE
+#define CC_ROWS_PHASE 0
+#endif
+#if CC_ROWS_PHASE
+#define PH_DECL long long ph_t = clock64(); long long ph0 = 0, ph1 = 0, ph2 = 0, ph3 = 0, ph4 = 0, ph5 = 0, ph6 = 0, ph7 = 0; int ph_rounds = 0, ph_moves = 0;
+#define PH(v) { const long long t_ = clock64(); v += t_ - ph_t; ph_t = t_; }
+#else
+#define PH_DECL
+#define PH(v)
+#endif
+
 namespace {
 
 constexpr bool CTS = CC_ROWS_COUNT != 0;      // column types other than normal are compiled in
 
 enum { ST_OK = 0, ST_HANDOVER = CC_ROWS_HANDOVER, ST_GROW = CC_ROWS_GROW, ST_MIGRATE = 3 };
+enum { LV_SOLO = 9, SOLO_ROWS = 256 };      // window setting "one warp on its own" and the rows of one stretch
 
 __device__ __forceinline__ int ceil_log2(int x) {          // smallest l with (1 << l) >= x, x >= 1
     return (x <= 1) ? 0 : 32 - __clz(x - 1);
@@ -110,32 +123,25 @@ __device__ __forceinline__ void apply_move(const Ctx& c, const Tab<GT>& T, int r
         if (ct == CC_NORMAL) {
             const double m = hyper(c, wide, ghyp, 0, j), rr = hyper(c, wide, ghyp, 1, j), ss = hyper(c, wide, ghyp, 2, j),
                          nu = hyper(c, wide, ghyp, 3, j);
-            double N, sx, sxx, gN, gM1;
-            if (is_old) {
-                if (isnan_x) continue;
-                // scored against its own cluster first (-= x, += x: view.py:416-419), then removed
-                const double xx = __dmul_rn(x, x);
-                N = T.at(CC_F_N, k, j) - 1.0;
-                sx = __dsub_rn(__dadd_rn(__dsub_rn(T.at(CC_F_SX, k, j), x), x), x);
-                sxx = __dsub_rn(__dadd_rn(__dsub_rn(T.at(CC_F_SXX, k, j), xx), xx), xx);
-                gN = T.at(CC_F_GM1, k, j);
-                gM1 = (N >= 1.0) ? normal_G_step(gN, N - 1.0, rr, nu) : 0.0;      // G(N-1) from G(N), N the new count
-            } else if (newc) {
-                // fresh cluster object: 0 + x, 0 + x*x (normal.py:51-53,64-70)
-                if (isnan_x) { N = 0.0; sx = 0.0; sxx = 0.0; gN = T.at(CC_F_GN, pslot, j); gM1 = 0.0; }
-                else {
-                    N = 1.0; sx = __dadd_rn(0.0, x); sxx = __dadd_rn(0.0, __dmul_rn(x, x));
-                    gM1 = T.at(CC_F_GN, pslot, j);
-                    gN = normal_G_step(gM1, 0.0, rr, nu);
-                }
-            } else {
-                if (isnan_x) continue;
-                N = T.at(CC_F_N, k, j) + 1.0;
-                sx = __dadd_rn(T.at(CC_F_SX, k, j), x);
-                sxx = __dadd_rn(T.at(CC_F_SXX, k, j), __dmul_rn(x, x));
-                gM1 = T.at(CC_F_GN, k, j);
-                gN = normal_G_step(gM1, N - 1.0, rr, nu);                          // G(N) from G(N-1), N the new count
-            }
+            // One instruction stream for both clusters (a branch per role would run the two logs one after the other):
+            //   old cluster: scored against itself first (-= x, += x: view.py:416-419), then the row leaves: ((s - x) + x) - x;
+            //   new cluster: s + x, a fresh cluster object starting from 0 (normal.py:51-53,64-70).
+            // G of the new count follows from the stored neighbour by one step of the recurrence: the old cluster knows
+            // G(N - 1) (it becomes G(N')) and needs G(N' - 1); the new one knows G(N) (it becomes G(N' - 1)) and needs G(N').
+            const bool fresh = !is_old && newc;
+            if (isnan_x && !fresh) continue;               // a missing cell changes nothing; a fresh cluster still gets its record
+            const double N0 = fresh ? 0.0 : T.at(CC_F_N, k, j);
+            const double sx0 = fresh ? 0.0 : T.at(CC_F_SX, k, j), sxx0 = fresh ? 0.0 : T.at(CC_F_SXX, k, j);
+            const double Gknown = is_old ? T.at(CC_F_GM1, k, j) : T.at(CC_F_GN, fresh ? pslot : k, j);
+            const double xx = __dmul_rn(x, x);
+            const double t1 = is_old ? __dadd_rn(__dsub_rn(sx0, x), x) : sx0;
+            const double t2 = is_old ? __dadd_rn(__dsub_rn(sxx0, xx), xx) : sxx0;
+            const double N = isnan_x ? 0.0 : N0 + (is_old ? -1.0 : 1.0);
+            const double sx = isnan_x ? 0.0 : __dadd_rn(t1, is_old ? -x : x);
+            const double sxx = isnan_x ? 0.0 : __dadd_rn(t2, is_old ? -xx : xx);
+            const double Gs = normal_G_step(Gknown, N - 1.0, rr, nu);
+            const double gN = (is_old || isnan_x) ? Gknown : Gs;
+            const double gM1 = is_old ? ((N >= 1.0) ? Gs : 0.0) : (isnan_x ? 0.0 : Gknown);
             const NormalCache cc = normal_cache_fast(N, sx, sxx, gN, m, rr, ss, nu);
             T.at(CC_F_N, k, j) = N; T.at(CC_F_SX, k, j) = sx; T.at(CC_F_SXX, k, j) = sxx;
             T.at(CC_F_MN, k, j) = cc.mn; T.at(CC_F_A, k, j) = cc.a; T.at(CC_F_CST, k, j) = cc.cst;
@@ -366,12 +372,19 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
     // thread 0: measurement epoch of the window setting (see below)
     int lvl_next = lvl, ep_rounds = -1, ep_rows = 0;
     long long ep_t0 = 0;
+    // views whose staying rows do not end a window when their sums drift (see the commit below): the two-pass scoring path
+    const bool softd = !GT && !BIG && !wide && (allnorm || (CTS && c.twotypes));
+    // one warp on its own (see below): all-normal views of up to 16 columns with shared-memory tables
+    const bool solo_ok = !GT && !BIG && allnorm && !wide && D <= 16;
+    int solo_back = 2;                 // thread 0: the window setting to return to
     if (tid == 0) { c.scal[44] = lvl; c.scal[45] = lvl; }
     consumer_sync<NT>();
+    PH_DECL
 
+    const int lgNB = 31 - __clz(c.NBUF);          // (a power of two)
     auto wait_row = [&](int i) {
         const int b = (i - c.base) >> lgB;
-        mbar_wait(&c.bar_full[b & (c.NBUF - 1)], (b / c.NBUF) & 1);
+        mbar_wait(&c.bar_full[b & (c.NBUF - 1)], (b >> lgNB) & 1);
     };
     auto release_upto = [&](int pos) {          // thread 0: batches wholly before `pos` go back to the producer
         int rel = c.scal[42];
@@ -390,6 +403,176 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
             const int lgcmax = min(5 - lgk, lgD);
             const int lvlmax = lgcmax + 3;
             lvl = (c.lvl0 >= 0) ? c.lvl0 : c.scal[44 + (round & 1)];
+            if constexpr (!GT && !BIG) {
+                if (lvl == LV_SOLO && solo_ok) {
+                    // ===================== one warp on its own =====================
+                    // Views whose rows move at every other step retire about one row per round whatever the window:
+                    // what counts is the length of a round, and two CTA barriers, the publication of each warp's
+                    // verdict and the bookkeeping of the window cost more than the arithmetic.  Warp 0 sweeps a
+                    // stretch of rows alone -- 32 / gk rows per round (gk lanes = candidates per row), verdicts by
+                    // ballot, a move applied by its own lanes -- while the other warps wait at the barrier below.
+                    consumer_sync<NT>();                 // everybody has read K and the level of this round
+                    if (warp == 0) {
+                        const long long t0 = clock64();
+                        int pos = start, code = 0, nmv = 0, rdy = 0;
+                        auto release_crossing = [&](int before, int after) {       // lane 0: only when a batch was left behind
+                            if ((((after - c.base) >> lgB) != ((before - c.base) >> lgB)) || after >= n) release_upto(after);
+                        };
+                        const int pend = min(n, start + SOLO_ROWS);
+                        const int fsI = c.Kc * D;
+                        const double* hyp0 = c.hyp;
+                        while (pos < pend) {
+                            const int Ks = c.scal[0];
+                            if (Ks + 1 > 32) { code = 1; break; }
+                            const int lgkS = ceil_log2(Ks + 1), gk = 1 << lgkS;
+                            const int Ws = min(min(32 >> lgkS, Wmax), pend - pos);
+                            const int rsS = lane >> lgkS, pcS = lane & (gk - 1);
+                            const int iS = pos + rsS;
+                            const bool arowS = rsS < Ws;
+                            PH(ph0)
+                            int r = -1, z = 0, nkz = 0, ncand = 0;
+                            double uu = 0.0;
+                            const double* xrow = c.x;
+                            bool singleton = false;
+                            if (arowS) {
+                                if (iS >= rdy) { wait_row(iS); rdy = c.base + ((((iS - c.base) >> lgB) + 1) << lgB); }
+                                const int q = (iS - c.base) & RBm;
+                                r = c.rowidx[q];
+                                z = c.zrow[q];
+                                uu = c.u[q];
+                                xrow = c.x + (size_t)q * c.xstride;
+                                nkz = c.nk[z];
+                                singleton = nkz == 1;
+                                ncand = Ks + (singleton ? 0 : 1);
+                            }
+                            PH(ph1)
+                            const bool cand = arowS && pcS < ncand;
+                            const int k = (cand && pcS < Ks) ? c.live[pcS] : pslot;
+                            const bool own = cand && pcS < Ks && k == z;
+                            const int ke = (own && singleton) ? pslot : k;
+                            const bool dn = own && !singleton;
+                            int drift = 0;
+                            double lpv = -INFINITY, wv = 0.0;
+                            if (cand) {
+                                const double* pe = c.tab + ke * D;
+                                const double* po = c.tab + k * D;
+                                double acc = 0.0, acc2 = 0.0;
+                                int j = 0;
+                                for (; j + 1 < D; j += 2) {      // two independent chains: the logs overlap
+                                    const double x0 = xrow[c.bulk ? c.col[j] : j], x1 = xrow[c.bulk ? c.col[j + 1] : j + 1];
+                                    acc += normal_core_bf(pe + j, po + j, fsI, x0, hyp0[3 * D + j], hyp0[D + j], own, dn, drift,
+                                                       [&](double& m, double& ss) { m = hyp0[j]; ss = hyp0[2 * D + j]; });
+                                    acc2 += normal_core_bf(pe + j + 1, po + j + 1, fsI, x1, hyp0[3 * D + j + 1], hyp0[D + j + 1], own, dn, drift,
+                                                        [&](double& m, double& ss) { m = hyp0[j + 1]; ss = hyp0[2 * D + j + 1]; });
+                                }
+                                if (j < D) {
+                                    const double x0 = xrow[c.bulk ? c.col[j] : j];
+                                    acc += normal_core_bf(pe + j, po + j, fsI, x0, hyp0[3 * D + j], hyp0[D + j], own, dn, drift,
+                                                       [&](double& m, double& ss) { m = hyp0[j]; ss = hyp0[2 * D + j]; });
+                                }
+                                lpv = acc + acc2;
+                                wv = (pcS >= Ks) ? c.alpha : own ? (singleton ? c.alpha : (double)(nkz - 1)) : (double)c.nk[k];
+                            }
+                            PH(ph2)
+                            // the draw (as below), per row segment of gk lanes
+                            float mf = (float)lpv;
+                            for (int o = 1; o < gk; o <<= 1) mf = fmaxf(mf, __shfl_xor_sync(0xffffffffu, mf, o));
+                            const double dl = lpv - (double)mf;
+                            double inc = (dl > -80.0) ? wv * exp(fmax(dl, -80.0)) : ((dl == dl) ? 0.0 : dl);
+                            for (int t = 0; t < lgkS; ++t) {
+                                const double v = __shfl_up_sync(0xffffffffu, inc, 1 << t);
+                                if (pcS >= (1 << t)) inc += v;
+                            }
+                            const int seg0 = lane & ~(gk - 1);
+                            const double tot = __shfl_sync(0xffffffffu, inc, seg0 + max(ncand, 1) - 1);
+                            const unsigned segmask = (gk == 32) ? 0xffffffffu : ((1u << gk) - 1u);
+                            const unsigned hit = (__ballot_sync(0xffffffffu, cand && inc > uu * tot) >> seg0) & segmask;
+                            const unsigned ownb = (__ballot_sync(0xffffffffu, own) >> seg0) & segmask;
+                            const unsigned drb = (__ballot_sync(0xffffffffu, own && drift != 0) >> seg0) & segmask;
+                            const int ownpos = ownb ? (__ffs(ownb) - 1) : 0;
+                            int choice = hit ? (__ffs(hit) - 1) : -1;
+                            bool fail = false;
+                            if (arowS && choice < 0) { choice = ownpos; fail = true; }
+                            int nc = 0, dst = z;
+                            if (arowS) {
+                                nc = choice >= Ks;
+                                dst = nc ? c.scal[2] : c.live[choice];
+                            }
+                            const bool flagged = arowS && (dst != z || drb != 0);
+                            if (fail && pcS == 0) { c.scal[7] = CC_ERR_ARG; c.scal[12] = 1; c.scal[13] = iS; c.scal[14] = Ks; }
+                            const unsigned fb = __ballot_sync(0xffffffffu, flagged && pcS == 0);
+                            PH(ph3)
+                            const int Lf = fb ? (__ffs(fb) - 1) : 0;
+                            const int rstar = fb ? (Lf >> lgkS) : (Ws - 1);
+                            if (c.trace && cand && rsS <= rstar) {
+                                double* tr = c.trace + c.trace_off + (size_t)iS * c.trace_stride;
+                                if (pcS == 0) {
+                                    tr[0] = (double)r;
+                                    tr[1] = (double)ncand;
+                                    tr[2] = (double)((choice < Ks) ? c.g_cid[c.live[choice]] : (c.g_cid[c.live[Ks - 1]] + 1));
+                                }
+                                if (pcS + 3 < c.trace_stride) tr[3 + pcS] = lpv + log(wv);
+                            }
+                            if (!fb) {
+                                if (lane == 0) release_crossing(pos, pos + Ws);
+                                pos += Ws;
+                                PH(ph5)
+#if CC_ROWS_PHASE
+                                ++ph_rounds;
+#endif
+                                continue;
+                            }
+                            const int zs = __shfl_sync(0xffffffffu, z, Lf), zb = __shfl_sync(0xffffffffu, dst, Lf);
+                            const int newcI = __shfl_sync(0xffffffffu, nc, Lf), ownposS = __shfl_sync(0xffffffffu, ownpos, Lf);
+                            const int moveI = __shfl_sync(0xffffffffu, (int)(dst != z), Lf), nkzS = __shfl_sync(0xffffffffu, nkz, Lf);
+                            const int rS = __shfl_sync(0xffffffffu, r, Lf);
+                            if (moveI && newcI && (zb >= Kcap - 1 || zb >= c.Ksm - 1 || zb >= c.Kc - 1)) {
+                                if (lane == 0) release_crossing(pos, pos + rstar);
+                                pos += rstar;                   // the rounds below take this row: grow / hand over / migrate
+                                code = 1;
+                                break;
+                            }
+                            const double* xs = c.x + (size_t)((pos + rstar - c.base) & RBm) * c.xstride;
+                            PH(ph5)
+                            if (moveI) { apply_move<32, false, false>(c, T, rS, zs, zb, newcI != 0, nkzS == 1, ownposS, Ks, nkzS, xs); ++nmv; }
+                            else apply_drift<32, false>(c, T, zs, -1, xs);
+                            __syncwarp();
+                            PH(ph6)
+                            if (lane == 0) release_crossing(pos, pos + rstar + 1);
+                            pos += rstar + 1;
+                            PH(ph7)
+#if CC_ROWS_PHASE
+                            ++ph_rounds; ++ph_moves;
+#endif
+                        }
+                        if (lane == 0) {
+                            // what the stretch cost per row decides whether the next one is swept the same way
+                            float* cost = reinterpret_cast<float*>(c.scal + 46);
+                            int* age = c.scal + 55;
+                            const int done = max(pos - start, 1);
+                            const float now = (float)(clock64() - t0) / (float)done;
+                            reinterpret_cast<float*>(c.scal)[8] = now;
+                            c.scal[9] = 0;
+                            int next = LV_SOLO, fresh = -1;
+                            for (int q = 0; q < 9; ++q) {
+                                age[q] = min(age[q] + 4, 1000);
+                                if (cost[q] > 0.f && age[q] <= 48 && (fresh < 0 || cost[q] < cost[fresh])) fresh = q;
+                            }
+                            if (code == 1) next = solo_back;
+                            else if (fresh >= 0) { if (cost[fresh] < 0.97f * now) next = fresh; }
+                            else if (8 * nmv < done) next = solo_back;          // rows stopped moving: measure the windows again
+                            lvl_next = next;
+                            ep_rounds = -1;
+                            c.scal[44] = next; c.scal[45] = next;
+                            c.scal[35] = pos;
+                        }
+                    }
+                    consumer_sync<NT>();
+                    start = c.scal[35];
+                    ++round;
+                    continue;
+                }
+            }
             if (lvl > lvlmax) lvl = lvlmax;
             const int lgc = min(lvl, lgcmax);
             const int nwact = max(1, NW >> (lvl - lgc));
@@ -409,6 +592,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 double uu = 0.0;
                 int nkz = 0;
                 bool singleton = false;
+                PH(ph0)
                 if (arow) {
                     wait_row(i);
                     const int q = (i - c.base) & RBm;
@@ -420,6 +604,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                     singleton = nkz == 1;
                     ncand = K + (singleton ? 0 : 1);
                 }
+                PH(ph1)
                 cand = arow && pc < ncand;
                 const int k = (cand && pc < K) ? c.live[pc] : pslot;
                 const bool own = cand && pc < K && k == z;
@@ -521,6 +706,7 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                     // crp.py:111-124: n_k, n_k - 1 for the row's own table, alpha for a fresh / re-used singleton table
                     wv = (pc >= K) ? c.alpha : own ? (singleton ? c.alpha : (double)(nkz - 1)) : (double)c.nk[k];
                 }
+                PH(ph2)
                 // ---- the draw: first j with prefix_j > u * total over w_j exp(lp_j - max), per row group ----
                 // any common reference point near the maximum will do (it cancels in inc > u * tot): the float-rounded maximum
                 float mf = (float)lpv;
@@ -548,23 +734,34 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                     nc = choice >= K;
                     dst = nc ? c.scal[2] : c.live[choice];
                 }
-                const bool flagged = arow && (dst != z || drb != 0);
+                // A row that stays but whose `-= x; += x` moved a sum by an ulp (view.py:416-419): in views of normal (and
+                // categorical) columns it does not end the window -- the rows behind it were scored against sums that
+                // differ in the last bit, far inside the tolerance of the conditionals -- and the sums are replayed
+                // in row order when the window is committed (below).  Elsewhere it is treated like a mover.
+                const bool drifted = arow && drb != 0;
+                const bool flagged = arow && (dst != z || (!softd && drb != 0));
                 const bool leader = (lane & (g - 1)) == 0;
                 if (fail && leader) { c.scal[7] = CC_ERR_ARG; c.scal[12] = 1; c.scal[13] = i; c.scal[14] = K; }
                 const unsigned fb = __ballot_sync(0xffffffffu, flagged && leader);
-                if (fb) {
-                    if (lane == __ffs(fb) - 1) {
-                        pubw[1] = ridx; pubw[2] = z; pubw[3] = dst; pubw[4] = nc; pubw[5] = ownpos;
-                        pubw[6] = (dst != z) ? 1 : 2; pubw[7] = nkz;
-                        pubw[0] = 1;
-                    }
-                } else if (lane == 0) pubw[0] = 0;
+                const unsigned db = softd ? __ballot_sync(0xffffffffu, drifted && leader) : 0u;
+                if (fb && lane == __ffs(fb) - 1) {
+                    pubw[1] = ridx; pubw[2] = z; pubw[3] = dst; pubw[4] = nc; pubw[5] = ownpos;
+                    pubw[6] = (dst != z) ? 1 : 2; pubw[7] = nkz;
+                }
+                // word 0: bit 0 = a flagged row (words 1..7), bits 8.. = 1 + the warp's first row with drifting sums
+                if (lane == 0) pubw[0] = (fb ? 1 : 0) | (db ? ((warp * rpw + ((__ffs(db) - 1) >> lgg) + 1) << 8) : 0);
             } else if (lane == 0) pubw[0] = 0;
+            PH(ph3)
             consumer_sync<NT>();
+            PH(ph4)
             // ---- commit in order: the first flagged row of the window --------------------------------
             const int* pub0 = c.pub + (round & 1) * 16 * 8;
-            int wstar = -1;
-            for (int w = 0; w < nwact; ++w) if (pub0[w * 8]) { wstar = w; break; }
+            int wstar = -1, dmin = 0x7fffffff;
+            for (int w = 0; w < nwact; ++w) {
+                const int v = pub0[w * 8];
+                if ((v & 1) && wstar < 0) wstar = w;
+                if (v >> 8) dmin = min(dmin, (v >> 8) - 1);
+            }
             const int rstar = (wstar >= 0) ? pub0[wstar * 8 + 1] : (W - 1);
             if (c.trace && arow && cand && ridx <= rstar && cc == 0) {
                 double* tr = c.trace + c.trace_off + (size_t)i * c.trace_stride;
@@ -597,17 +794,64 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                         if (lo >= 0 && cost[lo] < best) { best = cost[lo]; next = lo; }
                         if (hi <= lvlmax && cost[hi] < best) { best = cost[hi]; next = hi; }
                     }
+                    if (solo_ok && c.lvl0 < 0) {
+                        // fewer than three rows retired per round: try (or return to) one warp on its own
+                        const float cs = reinterpret_cast<float*>(c.scal)[8];
+                        const int as = c.scal[9] = min(c.scal[9] + 1, 1000);
+                        if (cs > 0.f && as <= 48) { if (cs < 0.97f * now) { solo_back = lvl; next = LV_SOLO; } }
+                        else if (ep_rows < 3 * EP) { solo_back = lvl; next = LV_SOLO; }
+                    }
                     lvl_next = next;
                     ep_rounds = -1;
                 }
                 c.scal[44 + (round & 1)] = lvl_next;
             }
             ++round;
+#if CC_ROWS_PHASE
+            ++ph_rounds;
+#endif
+            // ---- rows that stay: replay `-= x; += x` on their clusters' sums in row order, from the first row that
+            //      reported a change (the rows before it leave the sums as they are).  One thread per (cluster, normal
+            //      column); the cached constants follow the sums.
+            bool replayed = false;
+            if (softd && dmin < ((wstar >= 0) ? rstar : W)) {
+                const int lim = (wstar >= 0) ? rstar : W;
+                const int fsI = c.Kc * D;
+                double* tab0 = c.tab;
+                for (int p = tid; p < K * D; p += NT) {
+                    const int kpos = p / D, j = p - kpos * D;
+                    if (CTS && !allnorm && c.ctype[j] != CC_NORMAL) continue;
+                    const int k = c.live[kpos];
+                    double* cell = tab0 + k * D + j;
+                    const double sx0 = cell[CC_F_SX * fsI], sxx0 = cell[CC_F_SXX * fsI];
+                    double sx = sx0, sxx = sxx0;
+                    for (int t = dmin; t < lim; ++t) {
+                        const int q = (start + t - c.base) & RBm;
+                        if (c.zrow[q] != k) continue;
+                        const double x = c.x[(size_t)q * c.xstride + (c.bulk ? c.col[j] : j)];
+                        if (isnan(x)) continue;
+                        const double xx = __dmul_rn(x, x);
+                        sx = __dadd_rn(__dsub_rn(sx, x), x);
+                        sxx = __dadd_rn(__dsub_rn(sxx, xx), xx);
+                    }
+                    if (sx != sx0 || sxx != sxx0) {
+                        cell[CC_F_SX * fsI] = sx;
+                        cell[CC_F_SXX * fsI] = sxx;
+                        const NormalCache c2 = normal_cache_fast(cell[CC_F_N * fsI], sx, sxx, cell[CC_F_GN * fsI], c.hyp[j], c.hyp[D + j],
+                                                                 c.hyp[2 * D + j], c.hyp[3 * D + j]);
+                        cell[CC_F_MN * fsI] = c2.mn; cell[CC_F_A * fsI] = c2.a; cell[CC_F_CST * fsI] = c2.cst;
+                    }
+                }
+                replayed = true;
+            }
             if (wstar < 0) {
                 start += W;
+                if (replayed) consumer_sync<NT>();          // the next round scores against the replayed sums
                 if (tid == 0) release_upto(start);
+                PH(ph5)
                 continue;
             }
+            if (replayed) consumer_sync<NT>();              // the mover's old cluster starts from the replayed sums
             const int* pw = pub0 + wstar * 8;
             const int istar = start + rstar;
             const int zs = pw[2], zb = pw[3], ownpos = pw[5], kind = pw[6], nkz = pw[7];
@@ -618,11 +862,17 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 if (!GT && zb >= c.Kc - 1) { *status = ST_MIGRATE; return istar; }
             }
             const double* xs = c.x + (size_t)((istar - c.base) & RBm) * c.xstride;
+            PH(ph5)
             if (kind == 1) apply_move<NT, GT, false>(c, T, c.rowidx[(istar - c.base) & RBm], zs, zb, newc, nkz == 1, ownpos, K, nkz, xs);
             else apply_drift<NT, GT>(c, T, zs, CTS ? c.rowidx[(istar - c.base) & RBm] : -1, xs);
             start = istar + 1;
+            PH(ph6)
             consumer_sync<NT>();
             if (tid == 0) release_upto(start);       // after the barrier: the mover's cells were read from the ring
+            PH(ph7)
+#if CC_ROWS_PHASE
+            ++ph_moves;
+#endif
             continue;
         }
 
@@ -802,6 +1052,13 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
         if (zb != z || drifted) consumer_sync<NT>();
         if (tid == 0) release_upto(start);
     }
+#if CC_ROWS_PHASE
+    if (tid == 0) {
+        int32_t* q = c.st.seq + c.sv * c.st.R + 16;
+        q[0] += (int)(ph0 >> 6); q[1] += (int)(ph1 >> 6); q[2] += (int)(ph2 >> 6); q[3] += (int)(ph3 >> 6); q[4] += (int)(ph4 >> 6);
+        q[5] += (int)(ph5 >> 6); q[6] += (int)(ph6 >> 6); q[7] += (int)(ph7 >> 6); q[8] += ph_rounds; q[9] += ph_moves;
+    }
+#endif
     return n;
 }
 

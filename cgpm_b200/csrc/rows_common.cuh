@@ -191,6 +191,45 @@ __device__ __forceinline__ double normal_core(const double* p, const double* po,
 }
 
 
+// The same cell without a branch between the two formulas: every lane runs one instruction stream and selects its
+// constants (a lane scoring the row's own cluster next to lanes scoring other clusters would otherwise make the warp
+// run the two logs one after the other).  p: the candidate's cell -- for a lone member's own cluster the empty
+// cluster's; po: the cell of the cluster whose sums go through `-= x; += x` (read by every lane, used if own).
+template <typename FS, typename MS>
+__device__ __forceinline__ double normal_core_bf(const double* p, const double* po, FS fs, double x, double nu, double rr,
+                                                 bool own, bool dn, int& drift, MS ms) {
+    const double Nf = p[CC_F_N * fs];
+    const double zz = x - p[CC_F_MN * fs];
+    const double a = p[CC_F_A * fs], cst = p[CC_F_CST * fs];
+    const double dG = p[CC_F_GM1 * fs] - p[CC_F_GN * fs];
+    const double sx0 = po[CC_F_SX * fs], sxx0 = po[CC_F_SXX * fs];
+    const double xx = __dmul_rn(x, x);
+    const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
+    const bool nanx = isnan(x);
+    if (own && !nanx && (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, xx) != sxx0)) drift = 1;
+    const double rn = rr + Nf;
+    const double sc = dn ? -a * ((rn + 1.0) * __drcp_rn(rn - 1.0)) : a;
+    const double coef = dn ? 0.5 * (nu + Nf - 1.0) : -0.5 * (nu + Nf + 1.0);
+    const double bs = dn ? cst + dG : cst;
+    const double arg = fma(sc * zz, zz, 1.0);
+    const bool exact = dn && !(arg >= 0x1p-20);       // heavy cancellation in the downdate (or NaN): the reference's posterior update
+    double t = bs + coef * cc_log_pos(exact ? 1.0 : arg);
+    if (exact) {
+        double m, ss;
+        ms(m, ss);
+        const double N1 = Nf - 1.0;
+        const double rn1 = rr + N1;
+        const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
+        double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)),
+                               __dmul_rn(__dmul_rn(rn1, mn1), mn1));
+        if (sn1 == 0.0) sn1 = ss;
+        const double b1 = 0.5 * (nu + N1 + 1.0);
+        t = (p[CC_F_GM1 * fs] - b1 * (2.0 * (p[CC_F_GN * fs] - cst))) + coef * log(sn1);
+    }
+    return nanx ? 0.0 : t;
+}
+
+
 template <bool GT>
 __device__ __forceinline__ double normal_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp,
                                               const double* xrow, int j, int k, int ke, bool own, bool dn, int& drift) {

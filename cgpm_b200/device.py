@@ -427,6 +427,14 @@ class DeviceChains(object):
             return
         t, dev = self.t, self.device
         S_, V, Cn = self.S, self.Vcap, self.C
+        # the per-cluster tables are dense over (chain, slot, column): old and new copies exist side by side for a moment
+        need = S_ * new * (8 * L.NFIELD * Cn + 8 * self.CT + 12 * V)
+        free = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+        if need > free:
+            raise L.CgpmB200Error(
+                'a view needs %d cluster slots: the per-cluster tables of %d chains x %d columns would take %.1f GB '
+                '(%.1f GB free).  Views of this size come from columns whose fixed hyperparameters favour one cluster '
+                'per row; transition column_hypers, or run fewer chains per device' % (want, S_, Cn, need / 2**30, free / 2**30))
         for name, fill in (('live', -1), ('cid', 0), ('nk', 0)):
             a = torch.full((S_, V, new), fill, dtype=torch.int32, device=dev)
             a[:, :, :old - 1] = t[name][:, :, :old - 1]

@@ -135,11 +135,13 @@ def check_against_oracle(dev, oracles, ctype, n_rows, otr, tr, rngs, tag):
 
 
 @pytest.mark.parametrize('n_rows,seed,n_init,lvl', [(60, 5, 3, None), (300, 6, 3, None), (200, 7, 45, None),
-                                                   (300, 6, 3, 0), (300, 6, 3, 2), (300, 6, 3, 9), (200, 7, 45, 0)])
+                                                   (300, 6, 3, 0), (300, 6, 3, 2), (300, 6, 3, 8), (300, 6, 3, 9),
+                                                   (200, 7, 45, 0), (200, 7, 45, 9), (1000, 6, 3, None)])
 def test_rows_trajectory_narrow_views(n_rows, seed, n_init, lvl, monkeypatch):
     """All-normal table whose views hold one or two columns (rows move at every other step): the
     speculative rounds -- adaptive window (lvl=None) or pinned with CGPM_B200_ROWS_LVL to the most rows in
-    flight (0), a middle setting and a single row group (9) -- must follow the oracle step by step
+    flight (0), a middle setting, a single row group per round (8) and one warp sweeping on its own (9; the adaptive
+    setting reaches it by itself on the 1 000-row table) -- must follow the oracle step by step
     (n_init = 45 starts from more than 32 clusters per view: one row at a time with the multi-pass
     draw, then speculative rounds once the view has shrunk below 32 clusters)."""
     from cgpm_b200.device import DeviceChains
