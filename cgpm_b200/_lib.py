@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libcgpm_b200.so')
+# CGPM_B200_LIB: another build of the same library (probe builds with phase counters; scripts/ only)
+LIB_PATH = os.environ.get('CGPM_B200_LIB') or os.path.join(HERE, 'libcgpm_b200.so')
 
 NGRID = 30
 NFIELD = 8

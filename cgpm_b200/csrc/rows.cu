@@ -85,6 +85,7 @@ constexpr bool CTS = CC_ROWS_COUNT != 0;      // column types other than normal 
 
 enum { ST_OK = 0, ST_HANDOVER = CC_ROWS_HANDOVER, ST_GROW = CC_ROWS_GROW, ST_MIGRATE = 3 };
 enum { LV_SOLO = 9, SOLO_ROWS = 256 };      // window setting "one warp on its own" and the rows of one stretch
+enum { LV_ONE = 10, ONE_ROWS = 256 };       // window setting "the whole CTA on one row" (wide views whose rows move) and its stretch
 
 __device__ __forceinline__ int ceil_log2(int x) {          // smallest l with (1 << l) >= x, x >= 1
     return (x <= 1) ? 0 : 32 - __clz(x - 1);
@@ -342,6 +343,126 @@ __device__ __forceinline__ double cell_term(const Ctx& c, const Tab<GT>& T, bool
 }
 
 // ---------------------------------------------------------------------------------------------
+// Scoring of views of normal and categorical columns with shared-memory tables, by column type: the view's normal
+// columns come first (c.Dn of them), so a lane walks its normal cells and then its categorical cells in two
+// straight-line loops -- no branch on the column type between two cells, which would keep their logs from
+// overlapping (measured on configs[2]'s mixed views: ~600 cycles per cell with the branch, one log at a time).
+struct ScoreEnv {
+    const double *tab0, *cnt0, *hyp0;
+    const int *colp, *ctop, *ncatp;
+    int fsI, D, Dn, CTv;
+    bool bulk;
+};
+__device__ __forceinline__ ScoreEnv score_env(const Ctx& c, bool allnorm) {
+    ScoreEnv e;
+    e.tab0 = c.tab; e.fsI = c.Kc * c.D; e.cnt0 = c.tab + CC_NFIELD * e.fsI; e.hyp0 = c.hyp;
+    e.colp = c.col; e.ctop = c.cto; e.ncatp = c.ncat;
+    e.D = c.D; e.Dn = (!CTS || allnorm) ? c.D : c.Dn; e.CTv = c.CTv; e.bulk = c.bulk != 0;
+    return e;
+}
+// columns j0, j0 + st, ... of the row against cluster slot ke (any cluster but the row's own one with other members;
+// emptyc: the empty cluster's record) -- view.py:408-422 through the cached forms
+__device__ __forceinline__ double score_plain(const ScoreEnv& e, const double* xrow, int ke, bool emptyc, int j0, int st) {
+    const double* pe = e.tab0 + ke * e.D;
+    const double* hnu = e.hyp0 + 3 * e.D;
+    const double* hr = e.hyp0 + e.D;
+    const int fsI = e.fsI;
+    int nodrift = 0;
+    auto termN = [&](int jj) -> double {
+        const double x = xrow[e.bulk ? e.colp[jj] : jj];
+        return normal_core(pe + jj, pe + jj, fsI, x, hnu[jj], hr[jj], false, false, nodrift, [](double&, double&) {});
+    };
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int j = j0;
+    for (; j + 3 * st < e.Dn; j += 4 * st) { a0 += termN(j); a1 += termN(j + st); a2 += termN(j + 2 * st); a3 += termN(j + 3 * st); }
+    if (j + st < e.Dn) { a0 += termN(j); a1 += termN(j + st); j += 2 * st; }
+    if (j < e.Dn) a2 += termN(j);
+    if constexpr (CTS) {
+        if (e.Dn < e.D) {
+            // categorical.py:144-148: log(alpha + count_x) - log(N + alpha k), the second log cached; the empty cluster's
+            // term log(alpha) - log(alpha k) is cached in the hyper row 1 (selected, not branched to)
+            const double* cntk = e.cnt0 + ke * e.CTv;
+            const double* cstk = pe + CC_F_CST * fsI;
+            auto termC = [&](int jj) -> double {
+                const double x = xrow[e.bulk ? e.colp[jj] : jj];
+                const bool nanx = isnan(x);
+                const double cntx = cntk[e.ctop[jj] + (nanx ? 0 : (int)x)];
+                const double lg = cc_log_pos(emptyc ? 1.0 : e.hyp0[jj] + cntx) - cstk[jj];
+                return nanx ? 0.0 : (emptyc ? hr[jj] : lg);
+            };
+            j = e.Dn + j0;
+            for (; j + 3 * st < e.D; j += 4 * st) { a0 += termC(j); a1 += termC(j + st); a2 += termC(j + 2 * st); a3 += termC(j + 3 * st); }
+            if (j + st < e.D) { a0 += termC(j); a1 += termC(j + st); j += 2 * st; }
+            if (j < e.D) a2 += termC(j);
+        }
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+// the same columns against the row's own cluster z WITHOUT the row (view.py:416-419), z not a lone member
+__device__ __forceinline__ double score_own(const ScoreEnv& e, const double* xrow, int z, int j0, int st, int& drift) {
+    const double* po = e.tab0 + z * e.D;
+    const double* hnu = e.hyp0 + 3 * e.D;
+    const double* hr = e.hyp0 + e.D;
+    const int fsI = e.fsI;
+    double b0 = 0.0, b1 = 0.0;
+    int j = j0;
+    for (; j + st < e.Dn; j += 2 * st) {
+        bool ex0, ex1;
+        const double x0 = xrow[e.bulk ? e.colp[j] : j], x1 = xrow[e.bulk ? e.colp[j + st] : j + st];
+        double t0 = normal_own_fast(po + j, fsI, x0, hnu[j], hr[j], drift, ex0);
+        double t1 = normal_own_fast(po + j + st, fsI, x1, hnu[j + st], hr[j + st], drift, ex1);
+        if (ex0) t0 = normal_own_exact(po + j, fsI, x0, hnu[j], hr[j], e.hyp0[j], e.hyp0[2 * e.D + j]);
+        if (ex1) t1 = normal_own_exact(po + j + st, fsI, x1, hnu[j + st], hr[j + st], e.hyp0[j + st], e.hyp0[2 * e.D + j + st]);
+        b0 += t0; b1 += t1;
+    }
+    if (j < e.Dn) {
+        bool ex0;
+        const double x0 = xrow[e.bulk ? e.colp[j] : j];
+        double t0 = normal_own_fast(po + j, fsI, x0, hnu[j], hr[j], drift, ex0);
+        if (ex0) t0 = normal_own_exact(po + j, fsI, x0, hnu[j], hr[j], e.hyp0[j], e.hyp0[2 * e.D + j]);
+        b0 += t0;
+    }
+    if constexpr (CTS) {
+        // counts and N one lower (categorical.py:63-66,144-148)
+        const double* cntz = e.cnt0 + z * e.CTv;
+        for (j = e.Dn + j0; j < e.D; j += st) {
+            const double x = xrow[e.bulk ? e.colp[j] : j];
+            const bool nanx = isnan(x);
+            const double a = e.hyp0[j];
+            const double cntx = cntz[e.ctop[j] + (nanx ? 0 : (int)x)];
+            const double t = cc_log_pos(nanx ? 1.0 : a + (cntx - 1.0)) - cc_log_pos((po[CC_F_N * fsI + j] - 1.0) + a * e.ncatp[j]);
+            b1 += nanx ? 0.0 : t;
+        }
+    }
+    return b0 + b1;
+}
+// a lone member is scored against the empty cluster; its cluster's sums still go through -= x, += x
+__device__ __forceinline__ void score_drift_only(const ScoreEnv& e, const double* xrow, int z, int j0, int st, int& drift) {
+    const double* po = e.tab0 + z * e.D;
+    for (int j = j0; j < e.Dn; j += st) {
+        const double x = xrow[e.bulk ? e.colp[j] : j];
+        const double sx0 = po[CC_F_SX * e.fsI + j], sxx0 = po[CC_F_SXX * e.fsI + j];
+        const double xx = __dmul_rn(x, x);
+        if (!isnan(x) && (__dadd_rn(__dsub_rn(sx0, x), x) != sx0 || __dadd_rn(__dsub_rn(sxx0, xx), xx) != sxx0)) drift = 1;
+    }
+}
+
+// One candidate of the one-row-at-a-time path (a real call: inlined next to the speculative rounds it costs the
+// sweep its register budget -- the per-CTA context went to a 736-byte local-memory frame)
+__device__ __noinline__ double score_candidate(const ScoreEnv e, const double* xrow, int k, int ke, bool emptyc, bool own, bool dn,
+                                               int j0, int st, int* drift_out) {
+    int drift = 0;
+    double acc;
+    if (dn) acc = score_own(e, xrow, k, j0, st, drift);
+    else {
+        acc = score_plain(e, xrow, ke, emptyc, j0, st);
+        if (own) score_drift_only(e, xrow, k, j0, st, drift);
+    }
+    *drift_out = drift;
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
 // One pass over row positions [i_begin, n).  Returns the position it stopped at: n when finished
 // (*status = ST_OK); otherwise the position of a row whose move cannot be applied here and the
 // reason in *status -- ST_MIGRATE: the new cluster does not fit in the shared-memory tables (GT =
@@ -377,6 +498,13 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
     // one warp on its own (see below): all-normal views of up to 16 columns with shared-memory tables
     const bool solo_ok = !GT && !BIG && allnorm && !wide && D <= 16;
     int solo_back = 2;                 // thread 0: the window setting to return to
+    // the whole CTA on one row at a time (the code of the last section below) as one more window setting: views of 32
+    // columns and more whose rows move at most steps retire one row per round whatever the window, and a round that
+    // spreads the row's (candidate, column) cells over all consumer threads is several times shorter than one that
+    // keeps them on the 32 lanes of a row group.  Stretches of ONE_ROWS rows, costed like the other settings.
+    const bool one_ok = !BIG && !wide && D >= 32 && c.lvl0 < 0;
+    int one_left = 0, one_n = 0, one_moves = 0, one_back = 2;      // (uniform over the CTA; one_back: thread 0)
+    long long one_t0 = 0;
     if (tid == 0) { c.scal[44] = lvl; c.scal[45] = lvl; }
     consumer_sync<NT>();
     PH_DECL
@@ -397,12 +525,18 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
         const int K = c.scal[0];
         bool one_row = true;
         if constexpr (!BIG) one_row = (K + 1 > 32) || (D > c.DL);
-        if (!one_row) {
+        if (!one_row && one_left == 0) {
             // ===================== speculative round =====================
             const int lgk = ceil_log2(K + 1);
             const int lgcmax = min(5 - lgk, lgD);
             const int lvlmax = lgcmax + 3;
             lvl = (c.lvl0 >= 0) ? c.lvl0 : c.scal[44 + (round & 1)];
+            if (lvl == LV_ONE && one_ok) {
+                one_left = one_n = min((int)ONE_ROWS, n - start);
+                one_moves = 0;
+                if (tid == 0) one_t0 = clock64();
+                continue;                                  // the rows of the stretch take the last section of the loop
+            }
             if constexpr (!GT && !BIG) {
                 if (lvl == LV_SOLO && solo_ok) {
                     // ===================== one warp on its own =====================
@@ -613,7 +747,21 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                 const bool dn = own && !singleton;
                 int drift = 0;
                 double acc = 0.0, acc2 = 0.0;
-                if (!GT && !wide && (allnorm || (CTS && c.twotypes))) {
+                if (CTS && !GT && !wide && (allnorm || c.twotypes)) {
+                    // The build with the other column types: the same two passes as below, each walking the view's normal
+                    // and categorical columns in separate straight-line loops (score_plain / score_own above).
+                    const ScoreEnv env = score_env(c, allnorm);
+                    if (cand) acc = score_plain(env, xrow, ke, ke == pslot, cc, gc);
+                    double accB = 0.0;
+                    if (arow) {
+                        if (!singleton) accB = score_own(env, xrow, z, lane & (g - 1), g, drift);
+                        else score_drift_only(env, xrow, z, lane & (g - 1), g, drift);
+                    }
+                    for (int o = gc >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    for (int o = (1 << ceil_log2(min(g, D))) >> 1; o > 0; o >>= 1) accB += __shfl_xor_sync(0xffffffffu, accB, o);
+                    accB = __shfl_sync(0xffffffffu, accB, lane & ~(g - 1));
+                    if (dn) acc = accB;
+                } else if (!CTS && !GT && !wide && allnorm) {
                     // Views of normal and categorical columns, shared-memory tables.  Pass A: every (row, candidate) lane evaluates the plain
                     // Student-t term of its columns -- straight-line code, two independent chains per trip.  Pass B:
                     // the term of the row's own cluster WITHOUT the row (view.py:416-419) is a different formula; instead
@@ -801,6 +949,13 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
                         if (cs > 0.f && as <= 48) { if (cs < 0.97f * now) { solo_back = lvl; next = LV_SOLO; } }
                         else if (ep_rows < 3 * EP) { solo_back = lvl; next = LV_SOLO; }
                     }
+                    if (one_ok) {
+                        // fewer than three rows retired per round: try (or return to) the whole CTA on one row
+                        const float co = reinterpret_cast<float*>(c.scal)[36];
+                        const int ao = c.scal[37] = min(c.scal[37] + 1, 1000);
+                        if (co > 0.f && ao <= 48) { if (co < 0.97f * now) { one_back = lvl; next = LV_ONE; } }
+                        else if (ep_rows < 3 * EP) { one_back = lvl; next = LV_ONE; }
+                    }
                     lvl_next = next;
                     ep_rounds = -1;
                 }
@@ -897,7 +1052,10 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
             const bool dn = own && !singleton;
             int drift = 0;
             double acc = 0.0, acc2 = 0.0;
-            if (active) {
+            if (CTS && active && !GT && !wide && (allnorm || c.twotypes)) {
+                // by column type, up to four cells in flight (score_plain / score_own above)
+                acc = score_candidate(score_env(c, allnorm), xrow, k, ke, ke == pslot, own, dn, glL, G, &drift);
+            } else if (active) {
                 int j = glL;
                 for (; j + G < D; j += 2 * G) {
                     acc += cell_term<GT>(c, T, wide, allnorm, ghyp, xrow, j, k, ke, own, dn, pc >= K, CTS ? r : -1, drift);
@@ -1051,6 +1209,32 @@ __device__ int sweep(const Ctx& c, int i_begin, int* status, int& lvl) {
         start = i + 1;
         if (zb != z || drifted) consumer_sync<NT>();
         if (tid == 0) release_upto(start);
+        if (one_left > 0) {
+            // a stretch chosen as a window setting: at its end thread 0 compares its cost per row with the measured windows
+            one_moves += (zb != z);
+            if (--one_left == 0 || start >= n) {
+                one_left = 0;
+                if (tid == 0) {
+                    float* cost = reinterpret_cast<float*>(c.scal + 46);
+                    int* age = c.scal + 55;
+                    const float now = (float)(clock64() - one_t0) / (float)max(one_n, 1);
+                    reinterpret_cast<float*>(c.scal)[36] = now;
+                    c.scal[37] = 0;
+                    int next = LV_ONE, fresh = -1;
+                    for (int q = 0; q < 9; ++q) {
+                        age[q] = min(age[q] + 4, 1000);
+                        if (cost[q] > 0.f && age[q] <= 48 && (fresh < 0 || cost[q] < cost[fresh])) fresh = q;
+                    }
+                    if (K + 1 > 32) next = one_back;
+                    else if (fresh >= 0) { if (cost[fresh] < 0.97f * now) next = fresh; }
+                    else if (8 * one_moves < one_n) next = one_back;          // rows stopped moving: measure the windows again
+                    lvl_next = next;
+                    ep_rounds = -1;
+                    c.scal[44] = next; c.scal[45] = next;
+                }
+                consumer_sync<NT>();
+            }
+        }
     }
 #if CC_ROWS_PHASE
     if (tid == 0) {
@@ -1147,7 +1331,8 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         // the view's columns, normal ones first: lanes that walk the columns side by side then evaluate the same
         // type in the same trip (a warp pays for every branch any of its lanes takes)
         int j = 0, ct = 0, alln = 1, two = 1;
-        for (int pass = 0; pass < 2; ++pass)
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1) c.scal[1] = j;                  // the normal columns come first
             for (int q = 0; q < C; ++q)
                 if (zv[q] == v && ((st.ctype[q] == CC_NORMAL) == (pass == 0))) {
                     c.col[j] = q;
@@ -1161,6 +1346,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
                     ct += st.ncat[q];
                     ++j;
                 }
+        }
         c.scal[6] = ct;
         c.scal[11] = alln;
         c.scal[10] = two;
@@ -1169,6 +1355,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
         c.scal[42] = 0;
         c.scal[43] = 0;
         for (int q = 46; q < 64; ++q) c.scal[q] = 0;
+        c.scal[8] = c.scal[9] = c.scal[36] = c.scal[37] = 0;      // measured cost / age of the solo and one-row settings
     }
     const int K0 = st.nclu[sv];
     c.K0 = K0;
@@ -1209,6 +1396,7 @@ __global__ void __launch_bounds__(NT + 32, MINB) rows_kernel(const RowsParams p)
     c.CTv = CTv;
     c.allnorm = c.scal[11];
     c.twotypes = c.scal[10];
+    c.Dn = c.scal[1];
     // shared-table capacity: Kc cluster slots (the empty-cluster record sits at slot Kc-1)
     const size_t per_cluster = (size_t)(CC_NFIELD * D + CTv) * sizeof(double);
     int Kc = (int)(tab_avail / (per_cluster ? per_cluster : 1));
@@ -1502,8 +1690,9 @@ extern "C" int CC_ROWS_ENTRY(const cc_state* st, int n_work, const cc_row_work* 
 
     const int Ksm_env = getenv("CGPM_B200_ROWS_KSM") ? atoi(getenv("CGPM_B200_ROWS_KSM")) : 0;
     const int Ksm = std::max(4, std::min(st->Kcap, Ksm_env > 0 ? Ksm_env : 1024));
-    const int per_sm = std::max(1, std::min(2, (n_work + nsm - 1) / nsm));       // CTAs per SM wanted
+    int per_sm = std::max(1, std::min(2, (n_work + nsm - 1) / nsm));       // CTAs per SM wanted
     int rc = CC_OK;
+    const int forced_smem = getenv("CGPM_B200_ROWS_SMEM_KB") ? std::max(0, atoi(getenv("CGPM_B200_ROWS_SMEM_KB"))) : 0;
     auto launch = [&](bool big) -> int {
         RowsParams p;
         p.st = *st; p.work = dwork; p.perm = perm; p.u = u; p.trace = trace; p.trace_stride = trace_stride;
@@ -1528,9 +1717,18 @@ extern "C" int CC_ROWS_ENTRY(const cc_state* st, int n_work, const cc_row_work* 
         const int fixed = 128 + 256 + 1024 + kbytes + 64 + vbytes + 256;
         int budget;
         if (big) budget = std::min(max_smem, fixed + 64 * 1024);
-        else budget = (max_smem + 1024) / per_sm - 1024 - 256;          // 1 KB per-CTA system reservation
+        else {
+            // Two CTAs per SM only if the widest view's tables still fit in half the shared memory with a dozen clusters
+            // (+ the empty-cluster record and a slot to grow into): sweeping a wide view against tables in global memory
+            // costs about four times the shared-memory sweep (measured on configs[2]), two waves of CTAs at most two.
+            if (per_sm > 1 && !forced_smem) {
+                const size_t per_cluster = ((size_t)CC_NFIELD * dmax + (size_t)st->CT * dmax / std::max(1, st->C)) * sizeof(double);
+                if ((size_t)fixed + 14 * per_cluster > (size_t)((max_smem + 1024) / 2 - 1024 - 256)) per_sm = 1;
+            }
+            budget = (max_smem + 1024) / per_sm - 1024 - 256;          // 1 KB per-CTA system reservation
+        }
         bool forced = false;
-        if (const char* e = getenv("CGPM_B200_ROWS_SMEM_KB")) { const int kb = atoi(e); if (kb > 0) { budget = fixed + kb * 1024; forced = true; } }   // tests: force small tables
+        if (forced_smem) { budget = fixed + forced_smem * 1024; forced = true; }   // tests: force small tables
         if (!forced && budget < fixed + 4096) budget = fixed + 4096;
         if (budget > max_smem) budget = max_smem;
         if (fixed > max_smem) { cc_set_error("cc_transition_rows: shared memory need %d exceeds %d", fixed, max_smem); return CC_ERR_ARG; }

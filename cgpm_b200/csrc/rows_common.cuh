@@ -24,7 +24,7 @@ struct RowsParams {
 };
 
 // How one view's rows are staged: whole rows by bulk copies when the row is short and the view holds at least a
-// quarter of it, per-cell gathers otherwise; NBUF (<= 8) batches of B (<= 32) rows within about 64 KB (at least two
+// quarter of it, per-cell gathers otherwise; NBUF (<= 8) batches of B (<= 32) rows within about 64 KB (32 KB for long rows; at least two
 // batches of one row).  The ring bounds the number of rows a speculative round can have in flight.  Host (launch
 // sizing) and device (per CTA) use the same rule.
 struct RowsStage { int bulk, stagebytes, B, NBUF; };
@@ -34,9 +34,12 @@ __host__ __device__ inline RowsStage rows_stage(int Cp, int C, int D, int allow_
     r.bulk = (allow_bulk && rowbytes <= 4096 && 4 * D >= C) ? 1 : 0;
     r.stagebytes = r.bulk ? rowbytes : ((D + 1) & ~1) * 8;
     r.B = 32; r.NBUF = 8;
-    while (r.NBUF > 4 && r.NBUF * r.B * r.stagebytes > 64 * 1024) r.NBUF >>= 1;
-    while (r.B > 1 && r.NBUF * r.B * r.stagebytes > 64 * 1024) r.B >>= 1;
-    while (r.NBUF > 2 && r.NBUF * r.B * r.stagebytes > 64 * 1024) r.NBUF >>= 1;
+    // long rows (1 KB and more) belong to wide views: their tables need the shared memory more than the ring does,
+    // and a round over such a row is long enough for 16 rows in flight to cover the HBM latency
+    const int lim = (r.stagebytes >= 1024) ? 32 * 1024 : 64 * 1024;
+    while (r.NBUF > 4 && r.NBUF * r.B * r.stagebytes > lim) r.NBUF >>= 1;
+    while (r.B > 1 && r.NBUF * r.B * r.stagebytes > lim) r.B >>= 1;
+    while (r.NBUF > 2 && r.NBUF * r.B * r.stagebytes > lim) r.NBUF >>= 1;
     return r;
 }
 
@@ -81,7 +84,7 @@ __device__ __forceinline__ uint32_t keyed_perm(uint32_t i, uint32_t n, uint32_t 
 // Everything a sweep needs, resolved once per CTA.
 struct Ctx {
     cc_state st;
-    int s, v, n, D, K0, Kc, CTv, B, lgB, NBUF, RB, bulk, xstride, wide, allnorm, twotypes, Ksm, DL, base, lvl0;
+    int s, v, n, D, Dn, K0, Kc, CTv, B, lgB, NBUF, RB, bulk, xstride, wide, allnorm, twotypes, Ksm, DL, base, lvl0;   // Dn: normal columns (they come first)
     size_t sv;
     // shared memory
     uint64_t *bar_full, *bar_empty;   // [8] each
@@ -229,6 +232,43 @@ __device__ __forceinline__ double normal_core_bf(const double* p, const double* 
     return nanx ? 0.0 : t;
 }
 
+
+// The row's own cluster without the row (the `dn` case of normal_core), split so that two cells can be in flight:
+// the straight-line part reports heavy cancellation in `exact` instead of branching, and the caller then takes
+// normal_own_exact (the reference's posterior update of the decremented sums) for that cell.
+template <typename FS>
+__device__ __forceinline__ double normal_own_fast(const double* p, FS fs, double x, double nu, double rr, int& drift, bool& exact) {
+    const double Nf = p[CC_F_N * fs];
+    const double zz = x - p[CC_F_MN * fs];
+    const double a = p[CC_F_A * fs], cst = p[CC_F_CST * fs];
+    const double dG = p[CC_F_GM1 * fs] - p[CC_F_GN * fs];
+    const double sx0 = p[CC_F_SX * fs], sxx0 = p[CC_F_SXX * fs];
+    const double xx = __dmul_rn(x, x);
+    const double sx1 = __dsub_rn(sx0, x), sxx1 = __dsub_rn(sxx0, xx);
+    const bool nanx = isnan(x);
+    if (!nanx && (__dadd_rn(sx1, x) != sx0 || __dadd_rn(sxx1, xx) != sxx0)) drift = 1;
+    const double rn = rr + Nf;
+    const double sc = -a * ((rn + 1.0) * __drcp_rn(rn - 1.0));
+    const double coef = 0.5 * (nu + Nf - 1.0);
+    const double arg = fma(sc * zz, zz, 1.0);
+    exact = !nanx && !(arg >= 0x1p-20);
+    const double t = (cst + dG) + coef * cc_log_pos(exact ? 1.0 : arg);
+    return nanx ? 0.0 : t;
+}
+template <typename FS>
+__device__ __forceinline__ double normal_own_exact(const double* p, FS fs, double x, double nu, double rr, double m, double ss) {
+    const double Nf = p[CC_F_N * fs];
+    const double xx = __dmul_rn(x, x);
+    const double sx1 = __dsub_rn(p[CC_F_SX * fs], x), sxx1 = __dsub_rn(p[CC_F_SXX * fs], xx);
+    const double N1 = Nf - 1.0;
+    const double rn1 = rr + N1;
+    const double mn1 = (rr * m + sx1) * __drcp_rn(rn1);
+    double sn1 = __dsub_rn(__dadd_rn(__dadd_rn(ss, sxx1), __dmul_rn(__dmul_rn(rr, m), m)), __dmul_rn(__dmul_rn(rn1, mn1), mn1));
+    if (sn1 == 0.0) sn1 = ss;
+    const double b1 = 0.5 * (nu + N1 + 1.0);
+    const double bs = p[CC_F_GM1 * fs] - b1 * (2.0 * (p[CC_F_GN * fs] - p[CC_F_CST * fs]));
+    return bs + 0.5 * (nu + Nf - 1.0) * log(sn1);
+}
 
 template <bool GT>
 __device__ __forceinline__ double normal_term(const Ctx& c, const Tab<GT>& T, bool wide, const double* ghyp,

@@ -191,26 +191,39 @@ def test_rows_trajectory_narrow_views(n_rows, seed, n_init, lvl, monkeypatch):
                                                   (150, 11, False, {'CGPM_B200_ROWS_LVL': '0'}),
                                                   (120, 12, True, {'CGPM_B200_ROWS_LVL': '0'}),
                                                   (150, 11, False, {'CGPM_B200_ROWS_DL': '8'}),
-                                                  (120, 12, True, {'CGPM_B200_ROWS_NO_BULK': '1'})])
+                                                  (120, 12, True, {'CGPM_B200_ROWS_NO_BULK': '1'}),
+                                                  (120, 12, True, {'CGPM_B200_ROWS_DL': '8'}),
+                                                  (600, 13, 40, {}), (600, 14, -40, {}),
+                                                  (200, 13, 40, {'CGPM_B200_ROWS_LVL': '2'}),
+                                                  (200, 13, 40, {'CGPM_B200_ROWS_DL': '8'}),
+                                                  (200, 13, 40, {'CGPM_B200_ROWS_SMEM_KB': '8'})])
 def test_rows_trajectory_wide_view(n_rows, seed, mixed, env, monkeypatch):
     """A view of 20 columns next to one of 3 (all-normal and mixed with categorical columns), swept by
     speculative rounds (adaptive, or pinned to the most rows in flight where every mover invalidates a long
     window), one row at a time (CGPM_B200_ROWS_DL=8 puts the 20-column view beyond the width limit) and with
     per-cell gathers instead of bulk row copies: all must follow the oracle step by step -- partitions,
-    member order, bit-identical statistics and per-step conditionals."""
+    member order, bit-identical statistics and per-step conditionals.
+    mixed = +-40: a 40-column view (configs[2]'s kind: every other column categorical when positive, all normal when
+    negative) started from a random 5-cluster partition, so that most rows move in the first sweep and few in the third:
+    the adaptive window goes through the whole-CTA-on-one-row setting (600 rows: an epoch of 16 rounds, then stretches
+    of 256 rows) and back to speculative rounds; pinned variants cover the by-type scoring of the speculative rounds,
+    of the one-row path and the global-table fallback at that width."""
     from cgpm_b200.device import DeviceChains
     from cgpm_b200 import codec
     from cgpm_b200.synth import gen_table
     for k_, v_ in env.items():
         monkeypatch.setenv(k_, v_)
     monkeypatch.setenv('CGPM_B200_ROWS_PROF', '1')
-    widths = (20, 3)
+    widths = (40, 3) if abs(int(mixed)) == 40 else (20, 3)
     ncol = sum(widths)
     cct = ['normal'] * ncol
     da = [None] * ncol
-    if mixed:
+    if mixed is True:
         for c in (2, 7, 13, 21):
             cct[c] = 'categorical'; da[c] = {'k': 3 + (c % 3)}
+    elif mixed == 40:
+        for c in range(1, ncol, 2):
+            cct[c] = 'categorical'; da[c] = {'k': [2, 4, 8, 16][(c // 2) % 4]}
     X, _, _ = gen_table(n_rows, cct, da, n_views=2, clusters_per_view=3, seed=seed)
     rng0 = np.random.RandomState(seed)
     for _ in range(n_rows // 5):
@@ -261,5 +274,6 @@ def test_rows_trajectory_wide_view(n_rows, seed, mixed, env, monkeypatch):
         dev.sync()
         dev.check_errors()
         trh = tr.cpu().numpy().reshape(len(work), R, TS)
-        assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == 0)      # shared-memory tables, first kernel
+        if 'CGPM_B200_ROWS_SMEM_KB' not in env:
+            assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == 0)      # shared-memory tables, first kernel
         check_against_oracle(dev, oracles, ctype, n_rows, otr, trh, rngs, (sweep, mixed, env))
