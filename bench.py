@@ -218,6 +218,17 @@ def view_stats(eng):
     return {'views_total': int((nv > 0).sum()), 'clusters_per_view_mean': float(k.mean()), 'clusters_per_view_max': int(k.max())}
 
 
+def step_stats(ms, steps):
+    """min / median / max over the timed steps of one kernel's milliseconds (calls grouped per step in launch order).
+    A step is as slow as its slowest (chain, view): one view whose rows move at most steps can set the rows phase for
+    as long as it exists, so the spread is reported beside the mean."""
+    per = max(1, len(ms) // max(steps, 1))
+    tot = sorted(sum(ms[i:i + per]) for i in range(0, len(ms) - per + 1, per))
+    if not tot:
+        return None
+    return {'min': tot[0], 'median': tot[len(tot) // 2], 'max': tot[-1]}
+
+
 def timed_steps(eng, steps, kernels):
     import torch
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -341,6 +352,7 @@ def extra_ksweep():
 # --------------------------------------------------------------------------- ours
 def ours_main(args):
     import numpy as np
+    t_begin = time.time()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
@@ -397,8 +409,24 @@ def ours_main(args):
         args.e2e_steps = 1
     for _ in range(args.burnin):
         eng.transition(N=1, kernels=KERNELS, progress=False)
+    t_warm = 0.0
     for _ in range(args.warmup):
+        torch.cuda.synchronize()
+        t_warm = time.time()
         eng.transition(N=1, kernels=KERNELS, progress=False)
+        torch.cuda.synchronize()
+        t_warm = time.time() - t_warm
+    steps_requested = args.steps
+    if world > 1 and args.time_budget > 0 and args.warmup > 0:
+        # Safety valve for the configs[2] run only: a sweep of 64 chains x 1M rows x 200 columns takes seconds, and a run
+        # the driver has to kill reports nothing.  If the K requested steps (plus the end-to-end steps behind them) would
+        # not fit in the time budget at the pace of the last warm-up step, fewer steps are timed -- the same number on
+        # every rank -- and the line says so (`steps` = what was timed, `steps_requested` = K).
+        left = args.time_budget - (time.time() - t_begin)
+        fit = int((left - 2.0 * (args.e2e_steps + 1) * 1.5 * t_warm) / max(t_warm, 1e-3))
+        tfit = torch.tensor([max(2, min(args.steps, fit))], dtype=torch.int64, device='cuda')
+        dist.all_reduce(tfit, op=dist.ReduceOp.MIN)
+        args.steps = int(tfit.item())
     eng.native_launches(reset=True)
     eng.start_kernel_timing()
     eng._ch.dev.t['seq'][:, :, 0].zero_()              # per-view cycle counters: slots of views that no longer exist are stale
@@ -499,7 +527,8 @@ def ours_main(args):
         evals = R * Cn * S * (vs['clusters_per_view_mean'] + 2.0)
         line = {
             'metric': 'crosscat_gibbs_cell_updates_per_sec', 'value': value, 'unit': 'cell-updates/s',
-            'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
+            'n_gpus': world, 'steps': args.steps, 'steps_requested': steps_requested, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {
                 'workload': '%s: %d rows x %d %s cols, %d chains per GPU, kernels=%s, philox stream, public Engine API%s'
@@ -518,7 +547,10 @@ def ours_main(args):
                     'ms_per_step': float(te.item()),
                     'what': 'Engine.load_dense(host chain state, host table) [pinned -> device, ordered rebuild of all tables], '
                             'transition(N=1), Engine.to_dense() + logpdf_score() [device -> host], every step: the worst case '
-                            'of the lovecat-style bridge (INTEGRATION.md)'},
+                            'of the lovecat-style bridge (INTEGRATION.md)',
+                    'when': 'sweeps %d.. of the same chains, after the K timed steps: a step is as slow as its slowest view, and '
+                            'which views exist changes from sweep to sweep (kernel_ms_step_stats), so e2e can be faster or '
+                            'slower than `value`' % (args.burnin + args.warmup + args.steps + 1)},
             'e2e_resident': {'value': res_val, 'unit': 'cell-updates/s', 'ms_per_step': float(tr.item()),
                              'd2h_bytes_per_step': 8 * S, 'what': 'chain state stays on the device: transition(N=1) + logpdf_score() to the host'},
             'gpu_launches': int(launches),
@@ -545,6 +577,7 @@ def ours_main(args):
                 'note': 'no SFU path in fp64: log / exp are FP64-pipe instruction sequences (north_star asks for the SFU '
                         'fraction; MUFU is used only for reciprocal seeds)'},
             'kernel_ms_per_step': {k: sum(v) / args.steps for k, v in kern_ms.items()},
+            'kernel_ms_step_stats': {k: step_stats(v, args.steps) for k, v in kern_ms.items()},
             'cpu_baseline': cpu,
             'logscore_mean': float(sc.mean()),
         }
@@ -585,6 +618,8 @@ def main():
     ap.add_argument('--ref-rows', type=int, default=0, help='rows of the reference arm\'s sample (0: per config)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--extra-budget', type=int, default=150)
+    ap.add_argument('--time-budget', type=int, default=600,
+                    help='N > 1 only: seconds the whole run may take; the timed steps are cut (and reported) if K would not fit')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true')
     args = ap.parse_args()
