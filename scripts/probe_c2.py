@@ -12,8 +12,8 @@ full = len(sys.argv) > 4
 cfg = bench.C2
 t0 = time.time()
 X, cct, da = bench.make_table(R, cfg['cols'], cfg['views'], cfg['clusters'], True)
-Zv, Zrv = bench.initial_partitions(R, cfg['cols'], 12345)
-eng = Engine(X, num_states=S, rng=gen_rng(1), cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, alpha=1.0,
+Zv, Zrv = bench.initial_partitions(R, cfg['cols'], int(os.environ.get('PROBE_PSEED', '12345')))
+eng = Engine(X, num_states=S, rng=gen_rng(int(os.environ.get('PROBE_SEED', '1'))), cctypes=cct, distargs=da, Zv=Zv, Zrv=Zrv, alpha=1.0,
              view_alphas={v: 1.0 for v in Zrv}, hypers=bench.supplied_hypers(X, cct), stream='philox', Kcap=cfg['kcap'],
              Vcap=cfg['vcap'])
 torch.cuda.synchronize()
