@@ -443,7 +443,13 @@ def ours_main(args):
     launches = eng.native_launches()
     kern_ms = eng.stop_kernel_timing()
     tms = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    rank_ms = [ms / args.steps]
     if world > 1:
+        # every rank's own device time beside the max: ranks hold different chains and never exchange anything inside a
+        # step, so the spread between them is the whole weak-scaling loss (a step ends with the slowest view anywhere)
+        allms = torch.zeros(world, dtype=torch.float64, device='cuda')
+        dist.all_gather_into_tensor(allms, tms)
+        rank_ms = [float(x) / args.steps for x in allms.tolist()]
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms = float(tms.item())
     value = R * Cn * S * world * args.steps / (ms * 1e-3)
@@ -528,7 +534,7 @@ def ours_main(args):
         line = {
             'metric': 'crosscat_gibbs_cell_updates_per_sec', 'value': value, 'unit': 'cell-updates/s',
             'n_gpus': world, 'steps': args.steps, 'steps_requested': steps_requested, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps,
+            'ms_per_step': ms / args.steps, 'ms_per_step_by_rank': rank_ms,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {
                 'workload': '%s: %d rows x %d %s cols, %d chains per GPU, kernels=%s, philox stream, public Engine API%s'
