@@ -196,7 +196,10 @@ def test_rows_trajectory_narrow_views(n_rows, seed, n_init, lvl, monkeypatch):
                                                   (600, 13, 40, {}), (600, 14, -40, {}),
                                                   (200, 13, 40, {'CGPM_B200_ROWS_LVL': '2'}),
                                                   (200, 13, 40, {'CGPM_B200_ROWS_DL': '8'}),
-                                                  (200, 13, 40, {'CGPM_B200_ROWS_SMEM_KB': '8'})])
+                                                  (200, 13, 40, {'CGPM_B200_ROWS_SMEM_KB': '8'}),
+                                                  (200, 13, 40, {'CGPM_B200_ROWS_SMEM_KB': '8', 'CGPM_B200_ROWS_DL': '8'}),
+                                                  (120, 12, True, {'CGPM_B200_ROWS_SMEM_KB': '4', 'CGPM_B200_ROWS_DL': '8'}),
+                                                  (200, 14, -40, {'CGPM_B200_ROWS_SMEM_KB': '8', 'CGPM_B200_ROWS_DL': '8'})])
 def test_rows_trajectory_wide_view(n_rows, seed, mixed, env, monkeypatch):
     """A view of 20 columns next to one of 3 (all-normal and mixed with categorical columns), swept by
     speculative rounds (adaptive, or pinned to the most rows in flight where every mover invalidates a long
@@ -207,7 +210,10 @@ def test_rows_trajectory_wide_view(n_rows, seed, mixed, env, monkeypatch):
     negative) started from a random 5-cluster partition, so that most rows move in the first sweep and few in the third:
     the adaptive window goes through the whole-CTA-on-one-row setting (600 rows: an epoch of 16 rounds, then stretches
     of 256 rows) and back to speculative rounds; pinned variants cover the by-type scoring of the speculative rounds,
-    of the one-row path and the global-table fallback at that width."""
+    of the one-row path and the global-table fallback at that width.  CGPM_B200_ROWS_SMEM_KB + CGPM_B200_ROWS_DL
+    together put the wide view on global-memory tables AND one row at a time -- how configs[2]'s 130-180-column views
+    with a dozen clusters run (by-type scoring against the global tables, score_candidate_g); the variants check that
+    the tables really left shared memory (mode 1)."""
     from cgpm_b200.device import DeviceChains
     from cgpm_b200 import codec
     from cgpm_b200.synth import gen_table
@@ -276,4 +282,6 @@ def test_rows_trajectory_wide_view(n_rows, seed, mixed, env, monkeypatch):
         trh = tr.cpu().numpy().reshape(len(work), R, TS)
         if 'CGPM_B200_ROWS_SMEM_KB' not in env:
             assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == 0)      # shared-memory tables, first kernel
+        elif 'CGPM_B200_ROWS_DL' in env:
+            assert np.all(dev.t['seq'].cpu().numpy()[:, 0, 4] == 1)      # the wide view's tables are in global memory
         check_against_oracle(dev, oracles, ctype, n_rows, otr, trh, rngs, (sweep, mixed, env))
