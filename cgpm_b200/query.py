@@ -5,7 +5,7 @@ State._validate_cgpm_query (state.py:447-476)."""
 from __future__ import annotations
 
 import ctypes as C
-
+import itertools
 import math
 
 import numpy as np
@@ -40,11 +40,89 @@ def _validate(ch, rowid, targets, constraints, simulate):
     return fresh
 
 
+FAST_ENCODE_MIN = 32       # batches of at least this many queries try the vectorised encoder first
+
+
+def _encode_fast(ch, rowids, targets_list, constraints_list, simulate):
+    """The arrays of _encode for a batch of hypothetical rows (every rowid None or outside the table:
+    state.py:447-476 has nothing to check against the data then) on a table without lognormal columns, built
+    with numpy in one piece instead of a Python loop per query.  Returns None whenever the batch needs the general
+    path: an observed row, a lognormal column, or any query the loop would reject (it then raises the reference's
+    error for the first offending query)."""
+    Q = len(rowids)
+    if Q == 0 or ch.lognormal.any():
+        return None
+    try:
+        rid = np.fromiter((-1 if r is None else r for r in rowids), dtype=np.int64, count=Q)
+    except (TypeError, ValueError):
+        return None
+    if np.any((rid >= 0) & (rid < ch.R)):
+        return None
+    cl = [c or {} for c in constraints_list]
+    ci = ch.col_index
+    try:
+        lt = np.fromiter(map(len, targets_list), dtype=np.int64, count=Q)
+        lc = np.fromiter(map(len, cl), dtype=np.int64, count=Q)
+        nt, nc = int(lt.sum()), int(lc.sum())
+        flat = itertools.chain.from_iterable          # iterating a dict yields its keys, in insertion order
+        tcol = np.fromiter(map(ci.__getitem__, flat(targets_list)), dtype=np.int64, count=nt)
+        ccol = np.fromiter(map(ci.__getitem__, flat(cl)), dtype=np.int64, count=nc)
+        if simulate:
+            tval = np.zeros(nt)
+        else:
+            tval = np.fromiter(flat(map(dict.values, targets_list)), dtype=np.float64, count=nt)
+        cval = np.fromiter(flat(map(dict.values, cl)), dtype=np.float64, count=nc)
+    except (KeyError, TypeError, ValueError, AttributeError):
+        return None              # unknown column, unhashable key, a value that is not a number: the loop reports it
+    if nt + nc == 0:
+        return None
+    Cn = len(ci) + 1
+    qt = np.repeat(np.arange(Q, dtype=np.int64), lt)
+    qc = np.repeat(np.arange(Q, dtype=np.int64), lc)
+    tkey, ckey = qt * Cn + tcol, qc * Cn + ccol
+    if Q * Cn <= (1 << 26):      # a (query, column) bitmap; sorting the keys otherwise
+        seen = np.zeros(Q * Cn, dtype=bool)
+        seen[tkey] = True
+        repeated = simulate and int(np.count_nonzero(seen)) != nt
+        overlap = nc and bool(seen[ckey].any())
+    else:
+        repeated = simulate and np.unique(tkey).size != nt
+        overlap = nc and np.intersect1d(tkey, ckey).size > 0
+    if repeated:
+        return None              # 'Columns in targets must be unique.'
+    if overlap:
+        return None              # 'Targets and constraints must be disjoint.'
+    per = lt + lc
+    off = np.zeros(Q + 1, np.int64)
+    np.cumsum(per, out=off[1:])
+    if off[-1] >= 2 ** 31:
+        return None
+    t0 = np.zeros(Q, np.int64); c0 = np.zeros(Q, np.int64)
+    np.cumsum(lt[:-1], out=t0[1:]); np.cumsum(lc[:-1], out=c0[1:])
+    pos_t = np.repeat(off[:-1] - t0, lt) + np.arange(nt)              # a query's targets first, in dict order ...
+    pos_c = np.repeat(off[:-1] + lt - c0, lc) + np.arange(nc)         # ... then its constraints
+    n = int(off[-1])
+    cols = np.empty(n, np.int32); vals = np.empty(n, np.float64); roles = np.zeros(n, np.uint8)
+    cols[pos_t] = tcol; vals[pos_t] = tval
+    cols[pos_c] = ccol; vals[pos_c] = cval; roles[pos_c] = 1
+    dev = ch.dev.device
+    return {
+        'Q': Q, 'rowid': torch.full((Q,), -1, dtype=torch.int32, device=dev),
+        'off': torch.from_numpy(off.astype(np.int32)).to(dev),
+        'col': torch.from_numpy(cols).to(dev), 'val': torch.from_numpy(vals).to(dev), 'role': torch.from_numpy(roles).to(dev),
+        'constraints': constraints_list, 'jac': np.zeros(Q), 'dead': np.zeros(Q, dtype=bool),
+    }
+
+
 def _encode(ch, rowids, targets_list, constraints_list, simulate):
     Q = len(rowids)
     if constraints_list is None:
         constraints_list = [{} for _ in range(Q)]
     assert len(targets_list) == Q and len(constraints_list) == Q
+    if Q >= FAST_ENCODE_MIN:
+        enc = _encode_fast(ch, rowids, targets_list, constraints_list, simulate)
+        if enc is not None:
+            return enc
     rid = np.full(Q, -1, np.int32)
     off = np.zeros(Q + 1, np.int32)
     cols, vals, roles = [], [], []
@@ -95,8 +173,7 @@ def logpdf_bulk(ch, chains, rowids, targets_list, constraints_list=None):
     for t in targets_list:
         assert isinstance(t, dict)
     enc = _encode(ch, rowids, targets_list, constraints_list, simulate=False)
-    out = logpdf_bulk_encoded(ch, chains, enc)
-    return [[float(x) for x in row] for row in out]
+    return logpdf_bulk_encoded(ch, chains, enc).tolist()
 
 
 def logpdf_bulk_encoded(ch, chains, enc):
@@ -153,19 +230,23 @@ def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=No
     if bad.any():
         q = int(np.nonzero(bad.any(axis=0))[0][0])
         raise ValueError('Zero density constraints: %s' % (enc['constraints'][q],))
+    # decode: per query the target columns and how each is read back (1: integer-valued, 2: lognormal, 0: as is)
+    integer = (L.CATEGORICAL, L.BERNOULLI, L.POISSON, L.GEOMETRIC)
+    plan = []
+    for q in range(Q):
+        tcols = list(targets_list[q])
+        kinds = [1 if ch.ctype[ch.col_index[c]] in integer else 2 if ch.lognormal[ch.col_index[c]] else 0 for c in tcols]
+        plan.append((tcols, kinds, range(int(soff[q]), int(soff[q + 1]))))
     res = []
     for i in range(n):
+        rows = vals[i].tolist()                  # Python floats in one pass
         per_chain = []
-        for q in range(Q):
-            tcols = list(targets_list[q])
-            is_cat = [ch.ctype[ch.col_index[c]] in (L.CATEGORICAL, L.BERNOULLI, L.POISSON, L.GEOMETRIC) for c in tcols]     # integer-valued
-            is_ln = [bool(ch.lognormal[ch.col_index[c]]) for c in tcols]
-            samples = []
-            for r in range(soff[q], soff[q + 1]):
-                samples.append({c: (int(vals[i, r, j]) if is_cat[j] else
-                                    math.exp(vals[i, r, j]) if is_ln[j] else float(vals[i, r, j]))
-                                for j, c in enumerate(tcols)})
-            per_chain.append(samples)
+        for tcols, kinds, span in plan:
+            if not any(kinds):
+                per_chain.append([dict(zip(tcols, rows[r])) for r in span])
+            else:
+                per_chain.append([{c: (int(rows[r][j]) if kinds[j] == 1 else math.exp(rows[r][j]) if kinds[j] == 2
+                                       else rows[r][j]) for j, c in enumerate(tcols)} for r in span])
         res.append(per_chain)
     return res
 

@@ -156,3 +156,83 @@ def test_constrained_crp_helpers_match_the_reference():
     assert hm.logp_crp_constrained_dependent({0: 0, 1: 0, 2: 1}, 1.0, [[0, 2]]) == -float('inf')
     with pytest.raises(ValueError):
         hm.validate_dependency_constraints(4, [[0, 1]], [(0, 1)])
+
+
+def _query_stub(R=50, names=(3, 'b', 7, 11, 'e', 20), lognormal=()):
+    """What query._encode reads of a Chains object, without a device."""
+    import types
+    import torch
+    C = len(names)
+    ch = types.SimpleNamespace()
+    ch.R = R
+    ch.col_index = {c: i for i, c in enumerate(names)}
+    ch.lognormal = np.array([c in lognormal for c in names], dtype=bool)
+    ch.X_raw = np.random.RandomState(0).normal(size=(R, C))
+    ch.X_raw[::3, 1] = np.nan
+    ch.dev = types.SimpleNamespace(device=torch.device('cpu'))
+    return ch
+
+
+def test_vectorised_query_encoder_equals_the_per_query_loop(monkeypatch):
+    """query._encode_fast (hypothetical rows, no lognormal column: one numpy pass) must produce exactly the CSR
+    arrays of the per-query loop that mirrors State._validate_cgpm_query (state.py:447-476), in the reference's
+    dict order, and must step aside (return None) for every batch the loop treats differently -- observed rows,
+    lognormal columns, and queries the reference rejects."""
+    from cgpm_b200 import query
+    ch = _query_stub()
+    names = list(ch.col_index)
+    rng = np.random.RandomState(3)
+    Q = 200
+
+    def batch(simulate):
+        rowids, tl, cl = [], [], []
+        for q in range(Q):
+            perm = [names[i] for i in rng.permutation(len(names))]
+            a, b = rng.randint(0, 4), rng.randint(0, 3)
+            t = perm[:a]
+            c = perm[a:a + b]
+            tl.append(list(t) if simulate else {k: float(rng.normal()) for k in t})
+            cl.append(None if (b == 0 and q % 2) else {k: float(rng.normal()) for k in c})
+            rowids.append([None, -1, ch.R, ch.R + 17][q % 4])
+        return rowids, tl, cl
+
+    def slow(*a):
+        monkeypatch.setattr(query, 'FAST_ENCODE_MIN', 10 ** 9)
+        try:
+            return query._encode(*a)
+        finally:
+            monkeypatch.setattr(query, 'FAST_ENCODE_MIN', 32)
+
+    for simulate in (False, True):
+        rowids, tl, cl = batch(simulate)
+        fast = query._encode_fast(ch, rowids, tl, [c if c is not None else {} for c in cl], simulate)
+        ref = slow(ch, rowids, tl, cl, simulate)
+        assert fast is not None
+        for k in ('rowid', 'off', 'col', 'val', 'role'):
+            assert fast[k].dtype == ref[k].dtype and np.array_equal(fast[k].numpy(), ref[k].numpy()), (simulate, k)
+        assert fast['Q'] == ref['Q'] and not fast['dead'].any() and not fast['jac'].any()
+        via = query._encode(ch, rowids, tl, cl, simulate)              # the public path takes the fast encoder
+        assert np.array_equal(via['val'].numpy(), ref['val'].numpy())
+
+    # batches the vectorised encoder must leave to the loop
+    rowids, tl, cl = batch(False)
+    cl = [c or {} for c in cl]
+    obs = list(rowids); obs[5] = 4
+    assert query._encode_fast(ch, obs, tl, cl, False) is None                       # an observed row
+    assert query._encode_fast(_query_stub(lognormal=('b',)), rowids, tl, cl, False) is None
+    bad = [dict(t) for t in tl]; bad[7] = {'nope': 1.0}
+    assert query._encode_fast(ch, rowids, bad, cl, False) is None                    # unknown column
+    with pytest.raises(ValueError, match='Unknown column'):
+        query._encode(ch, rowids, bad, cl, False)
+    both = [dict(t) for t in tl]; both[9] = {3: 0.5}
+    cl2 = [dict(c) for c in cl]; cl2[9] = {3: 0.25}
+    assert query._encode_fast(ch, rowids, both, cl2, False) is None                  # target also constrained
+    with pytest.raises(ValueError, match='disjoint'):
+        query._encode(ch, rowids, both, cl2, False)
+    rowids, tl, cl = batch(True)
+    cl = [c or {} for c in cl]
+    tl[11] = [7, 7]; cl[11] = {}
+    assert query._encode_fast(ch, rowids, tl, cl, True) is None                      # repeated target
+    with pytest.raises(ValueError, match='unique'):
+        query._encode(ch, rowids, tl, cl, True)
+    assert query._encode_fast(ch, [None] * 3, [{}, {}, {}], [{}, {}, {}], False) is None    # nothing to encode
