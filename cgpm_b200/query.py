@@ -195,6 +195,31 @@ def logpdf_bulk_encoded(ch, chains, enc):
     return res
 
 
+def _decode_samples(ch, targets_list, soff, vals):
+    """[chain][query] lists of sample dicts {column: value} from the kernel's [chain][sample][target] array
+    (samples soff[q]..soff[q+1] belong to query q): integer-valued types come back as int, lognormal columns on
+    their original scale (the shapes of State.simulate_bulk, state.py:505-523)."""
+    Q = len(targets_list)
+    integer = (L.CATEGORICAL, L.BERNOULLI, L.POISSON, L.GEOMETRIC)
+    plan = []
+    for q in range(Q):
+        tcols = list(targets_list[q])
+        kinds = [1 if ch.ctype[ch.col_index[c]] in integer else 2 if ch.lognormal[ch.col_index[c]] else 0 for c in tcols]
+        plan.append((tcols, kinds, range(int(soff[q]), int(soff[q + 1]))))
+    res = []
+    for i in range(vals.shape[0]):
+        rows = vals[i].tolist()                  # Python floats in one pass
+        per_chain = []
+        for tcols, kinds, span in plan:
+            if not any(kinds):
+                per_chain.append([dict(zip(tcols, rows[r])) for r in span])
+            else:
+                per_chain.append([{c: (int(rows[r][j]) if kinds[j] == 1 else math.exp(rows[r][j]) if kinds[j] == 2
+                                       else rows[r][j]) for j, c in enumerate(tcols)} for r in span])
+        res.append(per_chain)
+    return res
+
+
 def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=None):
     """Returns [len(chains)][Q] lists of N sample dicts (Engine.simulate_bulk,
     engine.py:241-251)."""
@@ -230,25 +255,7 @@ def simulate_bulk(ch, chains, rowids, targets_list, constraints_list=None, Ns=No
     if bad.any():
         q = int(np.nonzero(bad.any(axis=0))[0][0])
         raise ValueError('Zero density constraints: %s' % (enc['constraints'][q],))
-    # decode: per query the target columns and how each is read back (1: integer-valued, 2: lognormal, 0: as is)
-    integer = (L.CATEGORICAL, L.BERNOULLI, L.POISSON, L.GEOMETRIC)
-    plan = []
-    for q in range(Q):
-        tcols = list(targets_list[q])
-        kinds = [1 if ch.ctype[ch.col_index[c]] in integer else 2 if ch.lognormal[ch.col_index[c]] else 0 for c in tcols]
-        plan.append((tcols, kinds, range(int(soff[q]), int(soff[q + 1]))))
-    res = []
-    for i in range(n):
-        rows = vals[i].tolist()                  # Python floats in one pass
-        per_chain = []
-        for tcols, kinds, span in plan:
-            if not any(kinds):
-                per_chain.append([dict(zip(tcols, rows[r])) for r in span])
-            else:
-                per_chain.append([{c: (int(rows[r][j]) if kinds[j] == 1 else math.exp(rows[r][j]) if kinds[j] == 2
-                                       else rows[r][j]) for j, c in enumerate(tcols)} for r in span])
-        res.append(per_chain)
-    return res
+    return _decode_samples(ch, targets_list, soff, vals)
 
 
 # ---------------------------------------------------------------------------------------------

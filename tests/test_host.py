@@ -236,3 +236,33 @@ def test_vectorised_query_encoder_equals_the_per_query_loop(monkeypatch):
     with pytest.raises(ValueError, match='unique'):
         query._encode(ch, rowids, tl, cl, True)
     assert query._encode_fast(ch, [None] * 3, [{}, {}, {}], [{}, {}, {}], False) is None    # nothing to encode
+
+
+def test_sample_decoding_types_and_layout():
+    """query._decode_samples: the kernel's [chain][sample][target] array becomes [chain][query] lists of N dicts in
+    the query's own target order; integer-valued types as int, lognormal columns exponentiated, the rest as float."""
+    import math
+    from cgpm_b200 import query, _lib as L
+    ch = _query_stub(names=('n', 'c', 'l', 'p'), lognormal=('l',))
+    ch.ctype = [L.NORMAL, L.CATEGORICAL, L.NORMAL, L.POISSON]
+    targets = [['n', 'l'], ['c'], ['p', 'n', 'c'], ['n']]
+    Ns = [2, 1, 3, 2]
+    soff = np.concatenate([[0], np.cumsum(Ns)]).astype(np.int32)
+    rng = np.random.RandomState(5)
+    vals = np.round(rng.normal(2.0, 1.0, size=(3, int(soff[-1]), 3)) * 4)          # [chains][samples][maxt]
+    got = query._decode_samples(ch, targets, soff, vals)
+    assert len(got) == 3 and all(len(g) == 4 for g in got)
+    for i in range(3):
+        for q, t in enumerate(targets):
+            assert len(got[i][q]) == Ns[q]
+            for n_, smp in enumerate(got[i][q]):
+                r = soff[q] + n_
+                assert list(smp) == t
+                for j, c in enumerate(t):
+                    v = vals[i, r, j]
+                    if c in ('c', 'p'):
+                        assert isinstance(smp[c], int) and smp[c] == int(v)
+                    elif c == 'l':
+                        assert smp[c] == math.exp(v)
+                    else:
+                        assert isinstance(smp[c], float) and smp[c] == float(v)
