@@ -149,3 +149,95 @@ def test_reference_view_logpdf_cluster_identities():
     assert abs(o.logpdf(-1, ev) - co.logsumexp(joint)) < 1e-12
     # chain rule p(x0, x2) = p(x0) p(x2 | x0)
     assert abs(o.logpdf(-1, ev) - (o.logpdf(-1, {0: 1.}) + o.logpdf(-1, {2: 3.}, {0: 1.}))) < 1e-10
+
+
+def test_normal_predictive_agrees_with_student_t_like_the_reference_test():
+    """The cross-derivation of the reference's tests/test_teh_murphy.py:69-129 (its hyperparameter sets, its two
+    datasets): the Normal-Inverse-Gamma posterior predictive `Z(N+1) - Z(N) - log(2 pi)/2` (normal.py:165-173) is a
+    Student-t with nu_n degrees of freedom, location m_n and scale^2 = s_n (r_n + 1) / (nu_n r_n) (Murphy eq. 100).
+    The reference allows atol 1e-2; here the tolerance is 1e-9, and the same values are compared with the one-log form
+    the CUDA kernels evaluate:
+        G(N) - log(s_n)/2 - ((nu_n + 1)/2) log1p(r_n (x - m_n)^2 / ((r_n + 1) s_n)),
+        G(N) = lgamma((nu_n + 1)/2) - lgamma(nu_n/2) + log(r_n / (r_n + 1))/2 - log(pi)/2."""
+    from scipy.stats import t as student_t
+    hypers = [(1., 2., 2., 4.), (7., 18., 6., .6), (.43, 3., 15., 14.), (1.2, 11., 55., 8.)]
+    rng = np.random.RandomState(0)
+    datasets = [rng.normal(10, 3, size=100), rng.normal(-3, 7, size=100)]
+    for (m, r, s, nu) in hypers:
+        for x in datasets:
+            for n in (0, 1, 17, 100):
+                xs = x[:n]
+                N, sx, sxx = float(n), float(np.sum(xs)), float(np.sum(xs * xs))
+                mn, rn, sn, nun = co.normal_posterior(N, sx, sxx, m, r, s, nu)
+                G = math.lgamma(.5 * (nun + 1.)) - math.lgamma(.5 * nun) + .5 * math.log(rn / (rn + 1.)) - .5 * co.LOGPI
+                for xt in np.linspace(-30.5, 80.8, 15):
+                    ref = co.normal_predictive(float(xt), N, sx, sxx, m, r, s, nu)
+                    via_t = student_t.logpdf(xt, nun, loc=mn, scale=math.sqrt(sn * (rn + 1.) / (nun * rn)))
+                    kernel_form = G - .5 * math.log(sn) - .5 * (nun + 1.) * math.log1p(rn * (xt - mn) ** 2 / ((rn + 1.) * sn))
+                    assert abs(ref - via_t) <= 1e-9 * max(1., abs(ref)), (m, r, s, nu, n, xt, ref, via_t)
+                    assert abs(ref - kernel_form) <= 1e-9 * max(1., abs(ref)), (m, r, s, nu, n, xt, ref, kernel_form)
+
+
+def test_chain_rule_marginal_equals_sum_of_sequential_predictives():
+    """The identity behind every collapsed kernel, which the reference pins for the CRP (tests/test_crp.py:180-212:
+    marginal = sum of predictives) and, through Bayes / chain-rule identities, for a view
+    (tests/test_view_logpdf_cluster.py:45-92): for each primitive on the path, the marginal likelihood of a sequence
+    equals the sum of the predictive log-densities of its items taken one after the other, with the sufficient
+    statistics updated by the reference's += in between (normal.py:64-70, categorical.py:53-61, crp.py:45-52, ...)."""
+    from scipy.special import gammaln
+    rng = np.random.RandomState(11)
+    tol = lambda ref: 1e-9 * max(1., abs(ref))
+    # normal
+    for (m, r, s, nu) in [(0., 1., 1., 1.), (.5, 2., 3., 4.), (-2., .1, 20., .7)]:
+        xs = rng.normal(1.5, 2.0, size=40)
+        N = sx = sxx = 0.
+        acc = 0.
+        for x in xs:
+            acc += co.normal_predictive(float(x), N, sx, sxx, m, r, s, nu)
+            N += 1; sx += x; sxx += x * x
+        ref = co.normal_marginal(N, sx, sxx, m, r, s, nu)
+        assert abs(acc - ref) <= tol(ref), ('normal', acc, ref)
+    # categorical
+    for k, alpha in [(2, 1.), (4, .7), (16, 3.)]:
+        xs = rng.randint(k, size=60)
+        counts = np.zeros(k)
+        N, acc = 0, 0.
+        for x in xs:
+            acc += co.categorical_predictive(int(x), N, counts, alpha)
+            counts[x] += 1; N += 1
+        ref = co.categorical_marginal(N, counts, alpha)
+        assert abs(acc - ref) <= tol(ref), ('categorical', acc, ref)
+    # bernoulli, exponential, geometric, poisson
+    xs = rng.randint(2, size=50)
+    N = sx = 0; acc = 0.
+    for x in xs:
+        acc += co.bernoulli_predictive(int(x), N, sx, 1.3, .4); N += 1; sx += x
+    ref = co.bernoulli_marginal(N, sx, 1.3, .4)
+    assert abs(acc - ref) <= tol(ref), ('bernoulli', acc, ref)
+    xs = rng.exponential(2.5, size=50)
+    N = 0; sx = 0.; acc = 0.
+    for x in xs:
+        acc += co.exponential_predictive(float(x), N, sx, 1.5, .8); N += 1; sx += x
+    ref = co.exponential_marginal(N, sx, 1.5, .8)
+    assert abs(acc - ref) <= tol(ref), ('exponential', acc, ref)
+    xs = rng.geometric(.3, size=50) - 1
+    N = sx = 0; acc = 0.
+    for x in xs:
+        acc += co.geometric_predictive(int(x), N, sx, 2., 1.5); N += 1; sx += x
+    ref = co.geometric_marginal(N, sx, 2., 1.5)
+    assert abs(acc - ref) <= tol(ref), ('geometric', acc, ref)
+    xs = rng.poisson(4., size=50)
+    N = sx = 0; slf = 0.; acc = 0.
+    for x in xs:
+        acc += co.poisson_predictive(int(x), N, sx, 2., .5); N += 1; sx += x; slf += gammaln(x + 1)
+    ref = co.poisson_marginal(N, sx, slf, 2., .5)
+    assert abs(acc - ref) <= tol(ref), ('poisson', acc, ref)
+    # CRP: seat the customers of a partition one by one
+    for alpha in (.3, 1.5, 20.):
+        z = [0, 0, 1, 0, 2, 1, 1, 3, 0, 2, 4, 4, 0]
+        counts, N, acc = OrderedDict(), 0, 0.
+        for t in z:
+            acc += co.crp_predictive(t, N, counts, alpha)
+            counts[t] = counts.get(t, 0) + 1; N += 1
+        ref = co.crp_marginal(N, counts, alpha)
+        assert abs(acc - ref) <= tol(ref), ('crp', alpha, acc, ref)
