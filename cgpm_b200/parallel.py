@@ -146,6 +146,18 @@ class ShardedEngine(object):
         """[num_states][Q] lists of sample dicts, chains in global order (engine.py:241-251)."""
         return all_gather_objects(self.local.simulate_bulk(rowids, targets_list, constraints_list, Ns=Ns))
 
+    def logpdf_bulk_arrays(self, target_cols, target_vals, constraint_cols=None, constraint_vals=None):
+        """[num_states, Q] array, chains in global order: Engine.logpdf_bulk_arrays of every rank's shard."""
+        loc = self.local.logpdf_bulk_arrays(target_cols, target_vals, constraint_cols, constraint_vals)
+        loc = torch.as_tensor(np.ascontiguousarray(loc), dtype=torch.float64, device=self._device())
+        return all_gather_chains(loc, self.num_states_total).cpu().numpy()
+
+    def simulate_bulk_arrays(self, Q, target_cols, constraint_cols=None, constraint_vals=None, N=1):
+        """[num_states, Q, N, len(target_cols)] array of predictive samples, chains in global order."""
+        loc = self.local.simulate_bulk_arrays(Q, target_cols, constraint_cols, constraint_vals, N=N)
+        loc = torch.as_tensor(np.ascontiguousarray(loc), dtype=torch.float64, device=self._device())
+        return all_gather_chains(loc, self.num_states_total).cpu().numpy()
+
     def dependence_probability(self, col0, col1):
         loc = torch.as_tensor(self.local.dependence_probability(col0, col1), dtype=torch.float64, device=self._device())
         return all_gather_chains(loc, self.num_states_total).cpu().numpy().tolist()

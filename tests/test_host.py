@@ -102,7 +102,23 @@ def _gloo_worker(rank, world, port, q):
     from cgpm_b200.parallel import all_gather_objects, weighted_integrate
     objs = all_gather_objects([{'chain': i} for i in range(lo, hi)])
     lw = weighted_integrate(full.tolist(), [0.5 * x for x in full.tolist()])
-    q.put((rank, full.tolist(), full2[:, 0].tolist(), acc[0, 0].item(), [o['chain'] for o in objs], lw))
+    # the array forms of ShardedEngine's bulk queries over a stand-in for the local Engine (no device here):
+    # chain c answers c + 0.001 q for query q, and samples [c, q, n, t]
+    import types
+    import numpy as np
+    from cgpm_b200.parallel import ShardedEngine
+    sh = ShardedEngine.__new__(ShardedEngine)
+    sh.world, sh.rank, sh.num_states_total, sh.lo, sh.hi = world, rank, n, lo, hi
+    chains = np.arange(lo, hi, dtype=np.float64)
+    sh.local = types.SimpleNamespace(
+        _ch=types.SimpleNamespace(dev=types.SimpleNamespace(device=torch.device('cpu'))),
+        logpdf_bulk_arrays=lambda tc, tv, cc=None, cv=None: chains[:, None] + 0.001 * np.arange(len(tv))[None, :],
+        simulate_bulk_arrays=lambda Q, tc, cc=None, cv=None, N=1: (
+            chains[:, None, None, None] + np.zeros((1, Q, N, len(tc) + 1)))[..., :len(tc)])      # a non-contiguous view
+    la = sh.logpdf_bulk_arrays([0, 1], np.zeros((5, 2)))
+    sa = sh.simulate_bulk_arrays(4, [0, 1], N=3)
+    q.put((rank, full.tolist(), full2[:, 0].tolist(), acc[0, 0].item(), [o['chain'] for o in objs], lw,
+           la.tolist(), list(sa.shape), sa[:, 0, 0, 0].tolist()))
     dist.destroy_process_group()
 
 
@@ -119,7 +135,9 @@ def test_gather_over_two_gloo_ranks():
         p.join(timeout=60)
         assert p.exitcode == 0
     from cgpm_b200 import hostmath as hm
-    for rank, full, full2, acc, objs, lw in res:
+    for rank, full, full2, acc, objs, lw, la, sa_shape, sa_first in res:
+        assert la == [[c + 0.001 * j for j in range(5)] for c in range(7)]           # [num_states, Q] in global chain order
+        assert sa_shape == [7, 4, 3, 2] and sa_first == [float(c) for c in range(7)]
         assert full == [i * 1.5 for i in range(7)]
         assert full2 == [float(i) for i in range(7)]
         assert acc == 3.0
