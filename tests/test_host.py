@@ -284,3 +284,29 @@ def test_sample_decoding_types_and_layout():
                         assert smp[c] == math.exp(v)
                     else:
                         assert isinstance(smp[c], float) and smp[c] == float(v)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference`: rank 0 prints one JSON line that carries the contract's keys for the reference arm
+    (impl, the metric of BASELINE.json, a cpu_baseline describing this very run, an e2e block with no copies), other
+    ranks print nothing and exit 0.  Runs the reference's own Engine on a tiny sample (no GPU involved)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, 'oracle', '_ref', 'cgpm', '.built')):
+        pytest.skip('oracle/_ref not built here')
+    cmd = [sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+           '--burnin', '0', '--ref-rows', '40']
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'crosscat_gibbs_cell_updates_per_sec'      # BASELINE.json's metric
+    assert line['unit'] == 'cell-updates/s'
+    assert line['higher_is_better'] is True and line['n_gpus'] == 1 and line['steps'] == 1 and line['value'] > 0
+    cb = line['cpu_baseline']
+    assert cb['kind'] in ('reference', 'port') and cb['cores'] >= 1 and cb['value'] == line['value'] and '40 rows' in cb['sample']
+    assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2')
+    other = subprocess.run(cmd + ['--gpus', '2'], capture_output=True, text=True, timeout=60, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ''
